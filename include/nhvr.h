@@ -1,0 +1,143 @@
+/* nhvr.h — C-ABI of libnhvr_sm100.so: the B200 (sm_100a) rendering hot path of
+ * Neural-Human-Video-Rendering.
+ *
+ * The reference ships no source; every entry point below therefore cites the
+ * nearest pinned evidence (launch flag / README line) of the reference interface it stands in
+ * for, and the torch.nn call it replaces inside the (absent) reference `models/networks.py`.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers unless a name ends in _host;
+ *  - the caller owns every byte of device memory; the library allocates no device memory and
+ *    launches asynchronously on the cudaStream_t passed as `void* stream`;
+ *  - every function returns 0 on success or a negative nhvr_status; nhvr_strerror() names it;
+ *  - there is no CPU fallback: on a device that is not compute capability 10.x every compute
+ *    entry point returns NHVR_ERR_ARCH.
+ *
+ * Activation layout "P8" (planar-by-8 bf16): [N][C8][Hp][Wp][8] where C8 = ceil(C/8) and one
+ * 16-byte unit holds 8 consecutive channels of one pixel.  Hp/Wp include a halo that the WRITER
+ * fills (zeros or mirror = ReflectionPad2d), so the conv kernel never pads.  `split`=1 stores the
+ * padded image as four row/column-parity sub-images, which turns a stride-2 conv into unit shifts.
+ */
+#ifndef NHVR_H_
+#define NHVR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum nhvr_status {
+  NHVR_OK = 0,
+  NHVR_ERR_ARCH = -1,      /* not an sm_100 device */
+  NHVR_ERR_SHAPE = -2,     /* unsupported / inconsistent shape */
+  NHVR_ERR_ALIGN = -3,     /* pointer not 16-byte aligned */
+  NHVR_ERR_NULL = -4,      /* required pointer is NULL */
+  NHVR_ERR_CUDA = -5,      /* a CUDA runtime call failed (see nhvr_last_cuda_error) */
+  NHVR_ERR_SMEM = -6,      /* tile does not fit in shared / tensor memory */
+  NHVR_ERR_UNSUPPORTED = -7
+} nhvr_status;
+
+enum { NHVR_HALO_ZERO = 0, NHVR_HALO_REFLECT = 1 };
+enum { NHVR_ACT_NONE = 0, NHVR_ACT_RELU = 1, NHVR_ACT_LRELU02 = 2, NHVR_ACT_TANH = 3,
+       NHVR_ACT_TANH_SIGMOID_LAST = 4 /* tanh on all channels but the last, sigmoid on the last */ };
+enum { NHVR_CONV = 0, NHVR_CONV_TRANSPOSE = 1 /* k3 s2 p1 output_padding 1 */ };
+enum { NHVR_EPI_RAW_STATS = 0,   /* bf16 P8 un-padded conv output + per-(n,c) sum / sum-of-squares */
+       NHVR_EPI_BIAS_ACT_F32 = 1,/* bias + activation, fp32 NCHW output                            */
+       NHVR_EPI_BIAS_ACT_P8 = 2  /* bias + activation, bf16 P8 output in a consumer's format       */ };
+
+/* P8 activation descriptor (see header comment). */
+typedef struct nhvr_act_desc {
+  int32_t N, C8, H, W;
+  int32_t pad_t, pad_l, pad_b, pad_r;
+  int32_t split;     /* 0 plain, 1 four-way parity split (Hp, Wp rounded up to even) */
+  int32_t halo;      /* NHVR_HALO_* : how a writer must fill the halo */
+} nhvr_act_desc;
+
+/* One convolution layer.  Replaces nn.Conv2d / nn.ConvTranspose2d (+ the ReflectionPad2d in front)
+ * of the pix2pixHD-shaped generators the reference builds from --n_downsample_global,
+ * --n_blocks_global, --ngf_global (test_start/start.sh:15-17), --n_downsample_bg/--n_blocks_bg
+ * (start.sh:20-21), --n_blocks_translate (pretrainTrans.sh:13). */
+typedef struct nhvr_conv_desc {
+  int32_t kind;          /* NHVR_CONV / NHVR_CONV_TRANSPOSE */
+  int32_t Cin, Cout;
+  int32_t kh, kw, stride, pad;
+  int32_t N, H, W;       /* input logical size */
+  int32_t halo;          /* NHVR_HALO_* the input must carry (reflect for ReflectionPad2d, zero for padding=) */
+  int32_t epilogue;      /* NHVR_EPI_* */
+  int32_t act;           /* NHVR_ACT_* (epilogues 1, 2) */
+} nhvr_conv_desc;
+
+typedef struct nhvr_conv_plan nhvr_conv_plan;   /* opaque, host memory only */
+
+/* ---- library ---- */
+int nhvr_version(void);
+const char* nhvr_strerror(int status);
+const char* nhvr_last_cuda_error(void);
+int nhvr_arch_ok(void);                 /* 0 iff the current device is compute capability 10.x */
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t nhvr_launch_count(void);
+
+/* ---- P8 activations ---- */
+size_t nhvr_act_bytes(const nhvr_act_desc* d);   /* includes the tail slack tiles may over-read */
+/* NCHW fp32 -> P8 bf16 with halo.  Up to 4 sources are concatenated along C (the reference's
+ * torch.cat of texture / pose / Laplace / previous frame in front of the generator; evidence:
+ * --input_nc 3, --use_laplace, --pose_plus_laplace, name *_Temporal, start.sh:7,11,19,24).
+ * src[i] is [N][src_c[i]][H][W] fp32; channels beyond the sum are zero. */
+int nhvr_pack_nchw(const float* const* src, const int32_t* src_c, int32_t nsrc,
+                   void* dst, const nhvr_act_desc* dst_desc, void* stream);
+/* P8 bf16 (interior) -> NCHW fp32, first C channels. */
+int nhvr_unpack_nchw(const void* src, const nhvr_act_desc* src_desc, float* dst, int32_t C, void* stream);
+
+/* ---- convolution (tcgen05 shift-GEMM) ---- */
+int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** out);
+void nhvr_conv_plan_destroy(nhvr_conv_plan* p);
+int nhvr_conv_input_desc(const nhvr_conv_plan* p, nhvr_act_desc* in_desc);   /* format the input must have */
+int nhvr_conv_output_dims(const nhvr_conv_plan* p, int32_t* Ho, int32_t* Wo, int32_t* Cout8);
+size_t nhvr_conv_weight_bytes(const nhvr_conv_plan* p);
+double nhvr_conv_flops(const nhvr_conv_plan* p);     /* algorithmic 2*k*k*Cin*Cout*Ho*Wo*N, un-padded */
+/* tiling introspection: info[0..15] = kcp, nchunks, njobs, nruns, nacc, slab_units, Npad, bpb, nbstages,
+ * SA, SB, tmem_cols, smem_bytes, tiles_per_img, nsplit, nblocks (used by tests and DESIGN.md tables) */
+int nhvr_conv_plan_info(const nhvr_conv_plan* p, int32_t* info, int32_t n);
+/* w: fp32, Conv2d layout [Cout][Cin][kh][kw] or ConvTranspose2d layout [Cin][Cout][kh][kw]. */
+int nhvr_conv_pack_weights(const nhvr_conv_plan* p, const float* w, void* packed, void* stream);
+/* out / stats / bias meaning depends on the plan's epilogue:
+ *  RAW_STATS    : out = P8 [N][Cout8][Ho][Wo] (no halo); stats = float [N][Cout8*8][2], must be zeroed
+ *                 by the caller (sum, sum of squares over H*W, accumulated with atomics); bias unused
+ *                 (a bias in front of an affine-free InstanceNorm cancels exactly).
+ *  BIAS_ACT_F32 : out = float [N][Cout][Ho][Wo]; bias = float [Cout] or NULL.
+ *  BIAS_ACT_P8  : out = P8 in out_desc's format (interior only is written); bias as above. */
+int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const void* packed_w, const float* bias,
+                      void* out, const nhvr_act_desc* out_desc, float* stats, void* stream);
+
+/* ---- InstanceNorm2d(affine=False) apply + activation (+ residual) + halo write ----
+ * Replaces nn.InstanceNorm2d + nn.ReLU/LeakyReLU (+ the ResnetBlock skip add, + the next layer's
+ * ReflectionPad2d / zero padding).  raw: P8 un-padded; stats as produced by RAW_STATS; residual
+ * (nullable) is read at the interior of res_desc; dst is written completely, halo included. */
+int nhvr_in_apply(const void* raw, const nhvr_act_desc* raw_desc, const float* stats, float eps, int32_t act,
+                  const void* residual, const nhvr_act_desc* res_desc,
+                  void* dst, const nhvr_act_desc* dst_desc, void* stream);
+
+/* ---- texture lookup ("--TexG part --use_mask_texture", start.sh:14,18; README.md:64) ----
+ * uvp: float [N][73][H][W] = 25 part logits, 24 U, 24 V (raw UV-generator output).
+ * atlas: float [24][S][S][Ct4] (channels-last, Ct4 = Ctex rounded up to 4).
+ * tex_out: float [N][Ctex][H][W] = sum_k softmax(logits)_k * bilinear(atlas_k, u_k, v_k), k=1..24
+ *          (divided by (1-P_0) when use_mask_texture == 0).
+ * part_out (nullable): uint8 [N][H][W] argmax part (lowest index wins ties);
+ * texel_out (nullable): int16 [N][H][W][2] = (x0, y0) integer texel corner of the argmax part
+ *          (0,0 for background).  These two are the bit-exact integer contract. */
+int nhvr_texture_sample(const float* uvp, const float* atlas, int32_t N, int32_t H, int32_t W,
+                        int32_t S, int32_t Ctex, int32_t use_mask_texture,
+                        float* tex_out, uint8_t* part_out, int16_t* texel_out, void* stream);
+
+/* ---- mask / background composite (README.md:15,52,60; --bg_path start.sh:12) ----
+ * out = m*fg + (1-m)*bg.  fgm: float [N][4][H][W] (RGB in [-1,1], mask in [0,1]);
+ * bg: float [3][H][W] (bg_batched==0, broadcast) or [N][3][H][W]; out: float [N][3][H][W]. */
+int nhvr_composite(const float* fgm, const float* bg, int32_t bg_batched, int32_t N, int32_t H, int32_t W,
+                   float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NHVR_H_ */

@@ -1,0 +1,636 @@
+// Shift-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// Every Conv2d / ConvTranspose2d of the rendering path is lowered to ONE kernel shape:
+//
+//   acc[a][q0+m][:] += In8[plane][off_j + q0 + m][0:16] * W_j[0:16][:]      m = 0..127
+//
+// The P8 layout (include/nhvr.h) stores 8 channels of one pixel in one 16-byte unit and pixels of a
+// (halo-padded) image linearly, so a filter tap is a constant shift `off_j` of the linear pixel
+// index.  A tile is 128 consecutive linear output positions; its input "slab" is staged ONCE in
+// shared memory by 1-D bulk async copies (UBLKCP) and every tap is just a different start address
+// of a K-major, un-swizzled tcgen05 shared-memory descriptor (rows 16 B apart, SBO = 128 B,
+// LBO = plane stride).  No im2col expansion, no padding logic, no per-tap reload.
+// Weights are pre-packed in consumption order and streamed through a second ring.
+//
+// Roles (256 threads): warp0 = slab producer, warp1 = weight producer, warp2 = MMA issuer (one
+// thread), warp3 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> global, InstanceNorm
+// statistics by warp-shuffle column reduction, or bias + activation).
+#include "common.cuh"
+#include "p8.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+namespace nhvr {
+
+extern void note_cuda_error(cudaError_t e);
+extern void count_launch();
+extern int arch_ok_cached();
+
+constexpr int kMaxJobs = 52;
+constexpr int kMaxRuns = 8;
+constexpr int kTileM = 128;
+
+struct ConvJob {
+  int32_t a_off;   // shift (16-B units) inside a plane slab
+  int16_t acc;     // accumulator index
+  int16_t first;   // first job of its accumulator (overwrites instead of accumulating)
+};
+struct ConvRun {
+  int32_t g_off;   // offset (units) from the plane base + q0
+  int32_t len;     // units
+  int32_t s_off;   // offset (units) inside the plane slab
+};
+
+struct ConvKParams {
+  const uint4* in;
+  const uint4* w;
+  const float* bias;
+  void* out;
+  float* stats;
+  int64_t in_plane_units;
+  int64_t w_split_units;   // packed-weight units per N-split
+  int32_t C8in, kcp, nchunks, njobs, nruns, nacc;
+  int32_t slab_units, Npad, bpb, nbstages, nblocks;
+  int32_t SA, SB;
+  int32_t Wrow, Hv, Wv, oys, oxs;
+  int32_t oy[4], ox[4];
+  int32_t Ho, Wo, Cout, Cout8;
+  int32_t epilogue, act;
+  int32_t tmem_cols;
+  ActGeom og;              // BIAS_ACT_P8 destination
+  ConvRun runs[kMaxRuns];
+  ConvJob jobs[kMaxJobs];
+};
+
+// -------------------------------------------------------------------------------------------------
+// warp-level column sums: every lane holds 16 values (one row, 16 columns); on return lane l holds
+// the sum over the warp's 32 rows of column (l >> 1).  16 shuffles instead of 16*5.
+NHVR_DEVINL float warp_colsum16(const float (&v)[16], int lane) {
+  float a8[8], a4[4], a2[2], a1;
+  const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float keep = h4 ? v[i + 8] : v[i];
+    float send = h4 ? v[i] : v[i + 8];
+    a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float keep = h3 ? a8[i + 4] : a8[i];
+    float send = h3 ? a8[i] : a8[i + 4];
+    a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float keep = h2 ? a4[i + 2] : a4[i];
+    float send = h2 ? a4[i] : a4[i + 2];
+    a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    float keep = h1 ? a2[1] : a2[0];
+    float send = h1 ? a2[0] : a2[1];
+    a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+  return a1;
+}
+
+NHVR_DEVINL float apply_act(float x, int act, bool is_last) {
+  switch (act) {
+    case NHVR_ACT_RELU: return fmaxf(x, 0.f);
+    case NHVR_ACT_LRELU02: return x > 0.f ? x : 0.2f * x;
+    case NHVR_ACT_TANH: return tanhf(x);
+    case NHVR_ACT_TANH_SIGMOID_LAST: return is_last ? 1.f / (1.f + __expf(-x)) : tanhf(x);
+    default: return x;
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) conv_shiftgemm_kernel(const __grid_constant__ ConvKParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.y, split = blockIdx.z;
+  const int64_t q0 = (int64_t)blockIdx.x * kTileM;
+
+  const uint32_t a_stage_bytes = (uint32_t)P.kcp * P.slab_units * 16u;
+  const uint32_t b_block_bytes = (uint32_t)P.Npad * 32u;
+  const uint32_t b_stage_bytes = b_block_bytes * P.bpb;
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = a_smem + (size_t)P.SA * a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)P.SB * b_stage_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + P.SA;
+  uint64_t* b_full = a_empty + P.SA;
+  uint64_t* b_empty = b_full + P.SB;
+  uint64_t* acc_full = b_empty + P.SB;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+  float* s_stats = reinterpret_cast<float*>(tmem_ptr + 2);   // [Npad][2]
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P.SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < P.SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 3) {
+    tmem_alloc(tmem_ptr, (uint32_t)P.tmem_cols);
+    tmem_relinquish();
+  }
+  if (warp >= 4) {
+    for (int i = threadIdx.x - 128; i < P.Npad * 2; i += 128) s_stats[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ slab producer
+    if (lane == 0) {
+      const uint4* img = P.in + (int64_t)n * P.C8in * P.in_plane_units + q0;
+      for (int c = 0; c < P.nchunks; ++c) {
+        const int st = c % P.SA;
+        const uint32_t ph = (uint32_t)(c / P.SA) & 1u;
+        mbar_wait(&a_empty[st], ph ^ 1u);
+        mbar_arrive_expect_tx(&a_full[st], a_stage_bytes);
+        uint8_t* dst = a_smem + (size_t)st * a_stage_bytes;
+        for (int pl = 0; pl < P.kcp; ++pl) {
+          const uint4* plane = img + (int64_t)(c * P.kcp + pl) * P.in_plane_units;
+          for (int r = 0; r < P.nruns; ++r) {
+            bulk_g2s(dst + ((size_t)pl * P.slab_units + P.runs[r].s_off) * 16, plane + P.runs[r].g_off,
+                     (uint32_t)P.runs[r].len * 16u, &a_full[st]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      const uint4* wsrc = P.w + (int64_t)split * P.w_split_units;
+      const uint32_t stage_units = b_stage_bytes >> 4;
+      for (int s = 0; s < P.nbstages; ++s) {
+        const int st = s % P.SB;
+        const uint32_t ph = (uint32_t)(s / P.SB) & 1u;
+        mbar_wait(&b_empty[st], ph ^ 1u);
+        mbar_arrive_expect_tx(&b_full[st], b_stage_bytes);
+        bulk_g2s(b_smem + (size_t)st * b_stage_bytes, wsrc + (int64_t)s * stage_units, b_stage_bytes, &b_full[st]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)P.Npad);
+      const uint32_t a_lbo = (uint32_t)P.slab_units * 16u;
+      const uint32_t b_lbo = (uint32_t)P.Npad * 16u;
+      const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
+      const int qsteps = P.kcp >> 1;
+      int blk = 0;
+      for (int c = 0; c < P.nchunks; ++c) {
+        const int st = c % P.SA;
+        mbar_wait(&a_full[st], (uint32_t)(c / P.SA) & 1u);
+        tc_fence_after();
+        const uint32_t a_st = a_base + (uint32_t)st * a_stage_bytes;
+        for (int j = 0; j < P.njobs; ++j) {
+          const ConvJob job = P.jobs[j];
+          const uint32_t d_tmem = tmem_base + (uint32_t)job.acc * (uint32_t)P.Npad;
+          for (int q = 0; q < qsteps; ++q, ++blk) {
+            const int bs = blk / P.bpb, bi = blk - bs * P.bpb;
+            const int bst = bs % P.SB;
+            if (bi == 0) {
+              mbar_wait(&b_full[bst], (uint32_t)(bs / P.SB) & 1u);
+              tc_fence_after();
+            }
+            const uint64_t adesc = make_desc_nosw(a_st + (uint32_t)(2 * q) * a_lbo + (uint32_t)job.a_off * 16u, a_lbo, 128u);
+            const uint64_t bdesc = make_desc_nosw(b_base + (uint32_t)bst * b_stage_bytes + (uint32_t)bi * b_block_bytes, b_lbo, 128u);
+            const uint32_t accumulate = (c == 0 && q == 0 && job.first) ? 0u : 1u;
+            umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+            if (bi == P.bpb - 1) umma_commit(&b_empty[bst]);
+          }
+        }
+        umma_commit(&a_empty[st]);
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int we = warp - 4;                  // TMEM lane quarter == warp % 4
+    const int m = we * 32 + lane;
+    const int64_t q = q0 + m;
+    const int y = (int)(q / P.Wrow);
+    const int x = (int)(q - (int64_t)y * P.Wrow);
+    const bool valid = (y < P.Hv) && (x < P.Wv);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(we * 32) << 16);
+    const int cout_off = split * P.Npad;
+    const int ngroups = P.Npad >> 4;
+
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+
+    for (int a = 0; a < P.nacc; ++a) {
+      const int Y = y * P.oys + P.oy[a];
+      const int X = x * P.oxs + P.ox[a];
+      for (int g = 0; g < ngroups; ++g) {
+        uint32_t vr[16];
+        tmem_ld16(t_lane + (uint32_t)(a * P.Npad + g * 16), vr);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(vr[i]);
+        const int c0 = cout_off + g * 16;
+
+        if (P.epilogue == NHVR_EPI_RAW_STATS) {
+          if (valid) {
+            uint4* o = reinterpret_cast<uint4*>(P.out);
+            const int64_t u0 = (((int64_t)n * P.Cout8 + (c0 >> 3)) * P.Ho + Y) * P.Wo + X;
+            const int64_t pstride = (int64_t)P.Ho * P.Wo;
+            uint4 lo, hi;
+            lo.x = pack_bf16x2(v[0], v[1]);  lo.y = pack_bf16x2(v[2], v[3]);
+            lo.z = pack_bf16x2(v[4], v[5]);  lo.w = pack_bf16x2(v[6], v[7]);
+            hi.x = pack_bf16x2(v[8], v[9]);  hi.y = pack_bf16x2(v[10], v[11]);
+            hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
+            if ((c0 >> 3) < P.Cout8) o[u0] = lo;
+            if ((c0 >> 3) + 1 < P.Cout8) o[u0 + pstride] = hi;
+          }
+          float s[16], ss[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { s[i] = valid ? v[i] : 0.f; ss[i] = s[i] * s[i]; }
+          const float cs = warp_colsum16(s, lane);
+          const float css = warp_colsum16(ss, lane);
+          const int col = g * 16 + (lane >> 1);
+          atomicAdd(&s_stats[col * 2 + (lane & 1)], (lane & 1) ? css : cs);
+        } else if (P.epilogue == NHVR_EPI_BIAS_ACT_F32) {
+          if (valid) {
+            float* o = reinterpret_cast<float*>(P.out);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c = c0 + i;
+              if (c < P.Cout) {
+                float val = v[i] + (P.bias ? __ldg(P.bias + c) : 0.f);
+                val = apply_act(val, P.act, c == P.Cout - 1);
+                o[(((int64_t)n * P.Cout + c) * P.Ho + Y) * P.Wo + X] = val;
+              }
+            }
+          }
+        } else {  // NHVR_EPI_BIAS_ACT_P8
+          if (valid) {
+            uint4* o = reinterpret_cast<uint4*>(P.out);
+            float t[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c = c0 + i;
+              float val = (c < P.Cout) ? v[i] + (P.bias ? __ldg(P.bias + c) : 0.f) : 0.f;
+              t[i] = (c < P.Cout) ? apply_act(val, P.act, c == P.Cout - 1) : 0.f;
+            }
+            uint4 lo, hi;
+            lo.x = pack_bf16x2(t[0], t[1]);  lo.y = pack_bf16x2(t[2], t[3]);
+            lo.z = pack_bf16x2(t[4], t[5]);  lo.w = pack_bf16x2(t[6], t[7]);
+            hi.x = pack_bf16x2(t[8], t[9]);  hi.y = pack_bf16x2(t[10], t[11]);
+            hi.z = pack_bf16x2(t[12], t[13]); hi.w = pack_bf16x2(t[14], t[15]);
+            const int p0 = c0 >> 3;
+            if (p0 < P.og.C8) o[act_unit(P.og, n, p0, Y + P.og.pad_t, X + P.og.pad_l)] = lo;
+            if (p0 + 1 < P.og.C8) o[act_unit(P.og, n, p0 + 1, Y + P.og.pad_t, X + P.og.pad_l)] = hi;
+          }
+        }
+      }
+    }
+    if (P.epilogue == NHVR_EPI_RAW_STATS) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float* gs = P.stats + ((int64_t)n * P.Cout8 * 8 + cout_off) * 2;
+      const int lim = min(P.Npad, P.Cout8 * 8 - cout_off) * 2;
+      for (int i = threadIdx.x - 128; i < lim; i += 128) atomicAdd(gs + i, s_stats[i]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// weight packing: OIHW (or IOHW for transposed) fp32 -> per-MMA blocks [2][Npad][8] bf16 in
+// consumption order (chunk, job, k-step); see header comment.
+struct PackParams {
+  const float* w;
+  uint4* dst;
+  int32_t Cin, Cout, kh, kw, transposed;
+  int32_t kcp, nchunks, njobs, Npad, nsplit, nblocks_padded;
+  int16_t job_tap[kMaxJobs];   // r*kw + s of each job
+};
+
+__global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
+  const int64_t total = (int64_t)P.nsplit * P.nblocks_padded * 2 * P.Npad;
+  const int qsteps = P.kcp >> 1;
+  const int nblocks = P.nchunks * P.njobs * qsteps;
+  for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (int64_t)gridDim.x * blockDim.x) {
+    const int nrow = (int)(u % P.Npad);
+    int64_t t = u / P.Npad;
+    const int kp = (int)(t & 1); t >>= 1;
+    const int blk = (int)(t % P.nblocks_padded);
+    const int z = (int)(t / P.nblocks_padded);
+    uint32_t packed[4] = {0, 0, 0, 0};
+    if (blk < nblocks) {
+      const int qq = blk % qsteps;
+      const int j = (blk / qsteps) % P.njobs;
+      const int c = blk / (qsteps * P.njobs);
+      const int tap = P.job_tap[j];
+      const int co = z * P.Npad + nrow;
+      float vals[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int ci = (c * P.kcp + 2 * qq + kp) * 8 + e;
+        float val = 0.f;
+        if (ci < P.Cin && co < P.Cout) {
+          const int64_t idx = P.transposed ? (((int64_t)ci * P.Cout + co) * (P.kh * P.kw) + tap)
+                                           : (((int64_t)co * P.Cin + ci) * (P.kh * P.kw) + tap);
+          val = P.w[idx];
+        }
+        vals[e] = val;
+      }
+      packed[0] = pack_bf16x2(vals[0], vals[1]); packed[1] = pack_bf16x2(vals[2], vals[3]);
+      packed[2] = pack_bf16x2(vals[4], vals[5]); packed[3] = pack_bf16x2(vals[6], vals[7]);
+    }
+    P.dst[u] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  }
+}
+
+}  // namespace nhvr
+
+// =================================================================================================
+// host side: plan builder + C-ABI
+// =================================================================================================
+using namespace nhvr;
+
+struct nhvr_conv_plan {
+  nhvr_conv_desc d;
+  nhvr_act_desc in_desc;
+  ConvKParams kp;          // pointers filled at launch
+  PackParams pp;
+  int32_t Ho, Wo, Cout8, nsplit, tiles_per_img;
+  size_t smem_bytes;
+  size_t weight_bytes;
+};
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+static inline int next_pow2_cols(int c) { int p = 32; while (p < c) p <<= 1; return p; }
+
+extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** out) {
+  if (!d || !out) return NHVR_ERR_NULL;
+  if (d->Cin <= 0 || d->Cout <= 0 || d->N <= 0 || d->H <= 0 || d->W <= 0) return NHVR_ERR_SHAPE;
+  nhvr_conv_plan* p = new nhvr_conv_plan();
+  std::memset(p, 0, sizeof(*p));
+  p->d = *d;
+  ConvKParams& K = p->kp;
+  const int C8 = round_up((d->Cin + 7) / 8, 2);   // K = 16 per MMA -> an even number of planes
+  K.C8in = C8;
+  nhvr_act_desc& in = p->in_desc;
+  in.N = d->N; in.C8 = C8; in.H = d->H; in.W = d->W; in.halo = d->halo; in.split = 0;
+
+  struct Tap { int run_key; int shift; int acc; int tap; };
+  std::vector<Tap> taps;
+  std::vector<std::pair<int, int>> run_specs;   // (g_off, len) before merging, indexed by run_key
+  int nacc = 1;
+  int Ho, Wo;
+
+  if (d->kind == NHVR_CONV && d->stride == 1) {
+    in.pad_t = in.pad_b = in.pad_l = in.pad_r = d->pad;
+    const int Wp = d->W + 2 * d->pad;
+    Ho = d->H + 2 * d->pad - d->kh + 1;
+    Wo = d->W + 2 * d->pad - d->kw + 1;
+    if (Ho <= 0 || Wo <= 0) { delete p; return NHVR_ERR_SHAPE; }
+    for (int r = 0; r < d->kh; ++r) run_specs.push_back({r * Wp, kTileM + d->kw - 1});
+    for (int r = 0; r < d->kh; ++r)
+      for (int s = 0; s < d->kw; ++s) taps.push_back({r, s, 0, r * d->kw + s});
+    K.Wrow = Wp; K.Hv = Ho; K.Wv = Wo; K.oys = K.oxs = 1;
+  } else if (d->kind == NHVR_CONV && d->stride == 2) {
+    in.pad_t = in.pad_b = in.pad_l = in.pad_r = d->pad;
+    in.split = 1;
+    ActGeom g = make_geom(in);
+    const int Hq = g.Hp / 2, Wq = g.Wp / 2;
+    Ho = (d->H + 2 * d->pad - d->kh) / 2 + 1;
+    Wo = (d->W + 2 * d->pad - d->kw) / 2 + 1;
+    if (Ho <= 0 || Wo <= 0) { delete p; return NHVR_ERR_SHAPE; }
+    const int rr_n = (d->kh - 1) / 2 + 1;
+    // run key = parity-plane * rr_n + (r >> 1)
+    for (int pp = 0; pp < 4; ++pp)
+      for (int rr = 0; rr < rr_n; ++rr) run_specs.push_back({pp * Hq * Wq + rr * Wq, kTileM + (d->kw - 1) / 2});
+    for (int r = 0; r < d->kh; ++r)
+      for (int s = 0; s < d->kw; ++s) {
+        const int pp = ((r & 1) << 1) | (s & 1);
+        taps.push_back({pp * rr_n + (r >> 1), s >> 1, 0, r * d->kw + s});
+      }
+    K.Wrow = Wq; K.Hv = Ho; K.Wv = Wo; K.oys = K.oxs = 1;
+  } else if (d->kind == NHVR_CONV_TRANSPOSE) {
+    if (d->kh != 3 || d->kw != 3 || d->stride != 2 || d->pad != 1) { delete p; return NHVR_ERR_UNSUPPORTED; }
+    in.pad_t = in.pad_l = 0; in.pad_b = in.pad_r = 1;
+    in.halo = NHVR_HALO_ZERO;
+    const int Wp = d->W + 1;
+    Ho = 2 * d->H; Wo = 2 * d->W;
+    run_specs.push_back({0, kTileM + 1});
+    run_specs.push_back({Wp, kTileM + 1});
+    nacc = 4;
+    // out[2i-1+ky][2j-1+kx] += x[i][j] * w[ky][kx]; phase a (row parity): a=0 -> (di=0,ky=1); a=1 -> (0,2),(1,0)
+    const int n_opt[2] = {1, 2};
+    const int o_d[2][2] = {{0, 0}, {0, 1}};
+    const int o_k[2][2] = {{1, 1}, {2, 0}};
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int ia = 0; ia < n_opt[a]; ++ia)
+          for (int ib = 0; ib < n_opt[b]; ++ib)
+            taps.push_back({o_d[a][ia], o_d[b][ib], a * 2 + b, o_k[a][ia] * 3 + o_k[b][ib]});
+    K.Wrow = Wp; K.Hv = d->H; K.Wv = d->W; K.oys = K.oxs = 2;
+    for (int a = 0; a < 4; ++a) { K.oy[a] = a >> 1; K.ox[a] = a & 1; }
+  } else {
+    delete p; return NHVR_ERR_UNSUPPORTED;
+  }
+  if ((int)taps.size() > kMaxJobs) { delete p; return NHVR_ERR_UNSUPPORTED; }
+
+  // ---- runs: drop unused, sort by offset, merge neighbours that touch / nearly touch
+  std::vector<int> used(run_specs.size(), 0);
+  for (auto& t : taps) used[t.run_key] = 1;
+  std::vector<int> order;
+  for (size_t i = 0; i < run_specs.size(); ++i) if (used[i]) order.push_back((int)i);
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return run_specs[a].first < run_specs[b].first; });
+  std::vector<ConvRun> runs;
+  std::vector<int> key_soff(run_specs.size(), 0);
+  int slab = 0;
+  for (int k : order) {
+    const int g = run_specs[k].first, len = run_specs[k].second;
+    if (!runs.empty() && g <= runs.back().g_off + runs.back().len + 16) {
+      ConvRun& r = runs.back();
+      key_soff[k] = r.s_off + (g - r.g_off);
+      const int new_len = std::max(r.len, g + len - r.g_off);
+      slab += new_len - r.len;
+      r.len = new_len;
+    } else {
+      ConvRun r{g, len, slab};
+      key_soff[k] = slab;
+      slab += len;
+      runs.push_back(r);
+    }
+  }
+  if ((int)runs.size() > kMaxRuns) { delete p; return NHVR_ERR_UNSUPPORTED; }
+  K.nruns = (int)runs.size();
+  for (int i = 0; i < K.nruns; ++i) K.runs[i] = runs[i];
+  K.slab_units = slab;
+
+  // ---- jobs (grouped by accumulator so that "first" is well defined)
+  std::stable_sort(taps.begin(), taps.end(), [](const Tap& a, const Tap& b) { return a.acc < b.acc; });
+  K.njobs = (int)taps.size();
+  int prev_acc = -1;
+  for (int j = 0; j < K.njobs; ++j) {
+    K.jobs[j].a_off = key_soff[taps[j].run_key] + taps[j].shift;
+    K.jobs[j].acc = (int16_t)taps[j].acc;
+    K.jobs[j].first = (taps[j].acc != prev_acc) ? 1 : 0;
+    prev_acc = taps[j].acc;
+    p->pp.job_tap[j] = (int16_t)taps[j].tap;
+  }
+  K.nacc = nacc;
+
+  // ---- N (Cout) tiling
+  int Npad = round_up(d->Cout, 16);
+  int nsplit = 1;
+  const int max_n = 256 / (nacc > 2 ? 2 : 1) / (nacc > 1 ? 2 : 1);   // nacc*Npad <= 512 and Npad <= 256
+  while (Npad > std::min(256, 512 / nacc)) { nsplit *= 2; Npad = round_up((d->Cout + nsplit - 1) / nsplit, 16); }
+  (void)max_n;
+  K.Npad = Npad;
+  K.tmem_cols = next_pow2_cols(nacc * Npad);
+  p->nsplit = nsplit;
+  p->Ho = Ho; p->Wo = Wo; p->Cout8 = (d->Cout + 7) / 8;
+  K.Ho = Ho; K.Wo = Wo; K.Cout = d->Cout; K.Cout8 = p->Cout8;
+  K.epilogue = d->epilogue; K.act = d->act;
+
+  // ---- shared-memory budget: prefer two co-resident CTAs per SM (<= ~100 KB, <= 256 TMEM columns)
+  const int b_block = Npad * 32;
+  auto try_fit = [&](int budget, int& kcp, int& SA, int& bpb, int& SB) -> bool {
+    for (int cand = 8; cand >= 2; cand -= 2) {
+      if (C8 % cand) continue;
+      const int nch = C8 / cand;
+      const int sa = std::min(2, nch);
+      const long a_bytes = (long)sa * cand * slab * 16;
+      int bb = std::max(1, std::min(16384 / b_block, 8));
+      const long rem = budget - a_bytes - 1024 - (long)Npad * 8;
+      if (rem < 2L * bb * b_block) {
+        bb = 1;
+        if (rem < 2L * b_block) continue;
+      }
+      int sb = (int)std::min<long>(4, rem / ((long)bb * b_block));
+      if (sb < 2) continue;
+      kcp = cand; SA = sa; bpb = bb; SB = sb;
+      return true;
+    }
+    return false;
+  };
+  int kcp = 0, SA = 0, bpb = 0, SB = 0;
+  bool ok = false;
+  if (K.tmem_cols <= 256) ok = try_fit(100 * 1024, kcp, SA, bpb, SB);
+  if (!ok) ok = try_fit(220 * 1024, kcp, SA, bpb, SB);
+  if (!ok) { delete p; return NHVR_ERR_SMEM; }
+  K.kcp = kcp; K.SA = SA; K.bpb = bpb; K.SB = SB;
+  K.nchunks = C8 / kcp;
+  K.nblocks = K.nchunks * K.njobs * (kcp / 2);
+  K.nbstages = (K.nblocks + bpb - 1) / bpb;
+  const int nblocks_padded = K.nbstages * bpb;
+  K.w_split_units = (int64_t)nblocks_padded * 2 * Npad;
+  p->weight_bytes = (size_t)nsplit * K.w_split_units * 16;
+  p->smem_bytes = (size_t)SA * kcp * slab * 16 + (size_t)SB * bpb * b_block + (size_t)(2 * SA + 2 * SB + 1) * 8 + 8 +
+                  (size_t)Npad * 8 + 128;
+
+  ActGeom gin = make_geom(in);
+  K.in_plane_units = gin.plane_units;
+  const int64_t last_q = (int64_t)(K.Hv - 1) * K.Wrow + K.Wv;   // one past the last valid linear position
+  p->tiles_per_img = (int)((last_q + kTileM - 1) / kTileM);
+
+  PackParams& PP = p->pp;
+  PP.Cin = d->Cin; PP.Cout = d->Cout; PP.kh = d->kh; PP.kw = d->kw;
+  PP.transposed = d->kind == NHVR_CONV_TRANSPOSE;
+  PP.kcp = kcp; PP.nchunks = K.nchunks; PP.njobs = K.njobs; PP.Npad = Npad; PP.nsplit = nsplit;
+  PP.nblocks_padded = nblocks_padded;
+  *out = p;
+  return NHVR_OK;
+}
+
+extern "C" void nhvr_conv_plan_destroy(nhvr_conv_plan* p) { delete p; }
+
+extern "C" int nhvr_conv_input_desc(const nhvr_conv_plan* p, nhvr_act_desc* in_desc) {
+  if (!p || !in_desc) return NHVR_ERR_NULL;
+  *in_desc = p->in_desc;
+  return NHVR_OK;
+}
+extern "C" int nhvr_conv_output_dims(const nhvr_conv_plan* p, int32_t* Ho, int32_t* Wo, int32_t* Cout8) {
+  if (!p) return NHVR_ERR_NULL;
+  if (Ho) *Ho = p->Ho;
+  if (Wo) *Wo = p->Wo;
+  if (Cout8) *Cout8 = p->Cout8;
+  return NHVR_OK;
+}
+extern "C" size_t nhvr_conv_weight_bytes(const nhvr_conv_plan* p) { return p ? p->weight_bytes : 0; }
+extern "C" double nhvr_conv_flops(const nhvr_conv_plan* p) {
+  if (!p) return 0.0;
+  const nhvr_conv_desc& d = p->d;
+  const double px = d.kind == NHVR_CONV_TRANSPOSE ? (double)d.H * d.W : (double)p->Ho * p->Wo;
+  return 2.0 * d.kh * d.kw * d.Cin * d.Cout * px * d.N;
+}
+// introspection used by tests / DESIGN.md tables
+extern "C" int nhvr_conv_plan_info(const nhvr_conv_plan* p, int32_t* info, int32_t n) {
+  if (!p || !info) return NHVR_ERR_NULL;
+  const ConvKParams& K = p->kp;
+  const int32_t vals[] = {K.kcp, K.nchunks, K.njobs, K.nruns, K.nacc, K.slab_units, K.Npad, K.bpb, K.nbstages,
+                          K.SA, K.SB, K.tmem_cols, (int32_t)p->smem_bytes, p->tiles_per_img, p->nsplit, K.nblocks};
+  for (int i = 0; i < n && i < (int)(sizeof(vals) / sizeof(vals[0])); ++i) info[i] = vals[i];
+  return NHVR_OK;
+}
+
+extern "C" int nhvr_conv_pack_weights(const nhvr_conv_plan* p, const float* w, void* packed, void* stream) {
+  if (!p || !w || !packed) return NHVR_ERR_NULL;
+  if (((uintptr_t)packed & 15) != 0) return NHVR_ERR_ALIGN;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  PackParams PP = p->pp;
+  PP.w = w;
+  PP.dst = reinterpret_cast<uint4*>(packed);
+  const int64_t total = (int64_t)PP.nsplit * PP.nblocks_padded * 2 * PP.Npad;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+  conv_pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(PP);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
+  return NHVR_OK;
+}
+
+extern "C" int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const void* packed_w, const float* bias,
+                                 void* out, const nhvr_act_desc* out_desc, float* stats, void* stream) {
+  if (!p || !in || !packed_w || !out) return NHVR_ERR_NULL;
+  if ((((uintptr_t)in | (uintptr_t)packed_w | (uintptr_t)out) & 15) != 0) return NHVR_ERR_ALIGN;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  ConvKParams K = p->kp;
+  if (K.epilogue == NHVR_EPI_RAW_STATS && !stats) return NHVR_ERR_NULL;
+  if (K.epilogue == NHVR_EPI_BIAS_ACT_P8) {
+    if (!out_desc) return NHVR_ERR_NULL;
+    K.og = make_geom(*out_desc);
+    if (K.og.H != p->Ho || K.og.W != p->Wo || K.og.N != p->d.N) return NHVR_ERR_SHAPE;
+  }
+  K.in = reinterpret_cast<const uint4*>(in);
+  K.w = reinterpret_cast<const uint4*>(packed_w);
+  K.bias = bias;
+  K.out = out;
+  K.stats = stats;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_shiftgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
+    attr_set = true;
+  }
+  dim3 grid(p->tiles_per_img, p->d.N, p->nsplit);
+  conv_shiftgemm_kernel<<<grid, 256, p->smem_bytes, (cudaStream_t)stream>>>(K);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
+  return NHVR_OK;
+}

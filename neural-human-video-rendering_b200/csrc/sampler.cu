@@ -1,0 +1,196 @@
+// Texture lookup (IUV -> learned atlas, soft part blend) and mask/background composite.
+// Both are HBM-bound streaming kernels: one thread per pixel (sampler) / per 4 pixels (composite),
+// every global access is warp-coalesced along x; the atlas (<= 35 MB) stays L2-resident.
+//
+// Arithmetic contract (mirrors oracle/texture.py line by line; the integer part is bit-exact):
+//   part   = argmax_k logits[k], k in 0..24, lowest index wins ties        (no transcendental)
+//   u      = clamp(0.5*U + 0.5, 0, 1)   (exact in fp32: scaling by 0.5 is exact, one rounding)
+//   fx     = u * (S-1);  x0 = floor(fx);  x1 = min(x0+1, S-1);  wx = fx - x0      (same for y)
+//   sample = (1-wy)*((1-wx)*T[y0][x0] + wx*T[y0][x1]) + wy*((1-wx)*T[y1][x0] + wx*T[y1][x1])
+//   tex    = sum_{k=1..24} softmax(logits)[k] * sample_k      (/(1-P0+1e-6) if !use_mask_texture)
+#include "common.cuh"
+#include "p8.cuh"
+#include <algorithm>
+
+namespace nhvr {
+
+extern void note_cuda_error(cudaError_t e);
+extern void count_launch();
+extern int arch_ok_cached();
+
+constexpr int kParts = 24;
+
+NHVR_DEVINL float uv_act(float t) { return fminf(fmaxf(__fadd_rn(__fmul_rn(t, 0.5f), 0.5f), 0.f), 1.f); }
+
+template <int G>   // G = number of float4 channel groups per texel (Ct4 / 4)
+__global__ void __launch_bounds__(128) texture_sample_kernel(const float* __restrict__ uvp, const float4* __restrict__ atlas,
+                                                             int N, int H, int W, int S, int Ctex, int use_mask,
+                                                             float* __restrict__ tex_out, uint8_t* __restrict__ part_out,
+                                                             short2* __restrict__ texel_out) {
+  const int64_t HW = (int64_t)H * W;
+  const int64_t total = (int64_t)N * HW;
+  const float sm1 = (float)(S - 1);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / HW);
+    const int64_t pix = idx - (int64_t)n * HW;
+    const float* base = uvp + (int64_t)n * 73 * HW + pix;
+
+    float lg[25];
+#pragma unroll
+    for (int k = 0; k < 25; ++k) lg[k] = __ldg(base + (int64_t)k * HW);
+    float mx = lg[0];
+    int part = 0;
+#pragma unroll
+    for (int k = 1; k < 25; ++k) {
+      if (lg[k] > mx) { mx = lg[k]; part = k; }
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) { lg[k] = __expf(lg[k] - mx); den += lg[k]; }
+    const float inv_den = 1.f / den;
+
+    float4 acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    short2 texel = make_short2(0, 0);
+
+#pragma unroll
+    for (int k = 1; k <= kParts; ++k) {
+      const float u = uv_act(__ldg(base + (int64_t)(25 + k - 1) * HW));
+      const float v = uv_act(__ldg(base + (int64_t)(49 + k - 1) * HW));
+      const float fx = __fmul_rn(u, sm1), fy = __fmul_rn(v, sm1);
+      const float x0f = floorf(fx), y0f = floorf(fy);
+      const int x0 = (int)x0f, y0 = (int)y0f;
+      const int x1 = min(x0 + 1, S - 1), y1 = min(y0 + 1, S - 1);
+      const float wx = fx - x0f, wy = fy - y0f;
+      if (k == part) texel = make_short2((short)x0, (short)y0);
+      const float pk = lg[k] * inv_den;
+      const float w00 = (1.f - wy) * (1.f - wx) * pk, w01 = (1.f - wy) * wx * pk;
+      const float w10 = wy * (1.f - wx) * pk, w11 = wy * wx * pk;
+      const float4* T = atlas + (int64_t)(k - 1) * S * S * G;
+      const float4* t00 = T + ((int64_t)y0 * S + x0) * G;
+      const float4* t01 = T + ((int64_t)y0 * S + x1) * G;
+      const float4* t10 = T + ((int64_t)y1 * S + x0) * G;
+      const float4* t11 = T + ((int64_t)y1 * S + x1) * G;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float4 a = __ldg(t00 + g), b = __ldg(t01 + g), c = __ldg(t10 + g), d = __ldg(t11 + g);
+        acc[g].x += w00 * a.x + w01 * b.x + w10 * c.x + w11 * d.x;
+        acc[g].y += w00 * a.y + w01 * b.y + w10 * c.y + w11 * d.y;
+        acc[g].z += w00 * a.z + w01 * b.z + w10 * c.z + w11 * d.z;
+        acc[g].w += w00 * a.w + w01 * b.w + w10 * c.w + w11 * d.w;
+      }
+    }
+    float norm = 1.f;
+    if (!use_mask) norm = 1.f / (1.f - lg[0] * inv_den + 1e-6f);
+    float* o = tex_out + (int64_t)n * Ctex * HW + pix;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float vals[4] = {acc[g].x, acc[g].y, acc[g].z, acc[g].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = g * 4 + e;
+        if (c < Ctex) o[(int64_t)c * HW] = vals[e] * norm;
+      }
+    }
+    if (part_out) part_out[idx] = (uint8_t)part;
+    if (texel_out) texel_out[idx] = texel;
+  }
+}
+
+// out = m*fg + (1-m)*bg, 4 pixels per thread (float4 along x)
+__global__ void __launch_bounds__(256) composite_kernel(const float4* __restrict__ fgm, const float4* __restrict__ bg, int bg_batched,
+                                                        int N, int64_t HW4, float4* __restrict__ out) {
+  const int64_t total = (int64_t)N * HW4;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / HW4);
+    const int64_t p = idx - (int64_t)n * HW4;
+    const float4* f = fgm + (int64_t)n * 4 * HW4 + p;
+    const float4 m = __ldg(f + 3 * HW4);
+    const float4* b = bg + (bg_batched ? (int64_t)n * 3 * HW4 : 0) + p;
+    float4* o = out + (int64_t)n * 3 * HW4 + p;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float4 fg = __ldg(f + c * HW4);
+      const float4 bb = __ldg(b + c * HW4);
+      float4 r;
+      r.x = m.x * fg.x + (1.f - m.x) * bb.x;
+      r.y = m.y * fg.y + (1.f - m.y) * bb.y;
+      r.z = m.z * fg.z + (1.f - m.z) * bb.z;
+      r.w = m.w * fg.w + (1.f - m.w) * bb.w;
+      o[c * HW4] = r;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) composite_scalar_kernel(const float* __restrict__ fgm, const float* __restrict__ bg, int bg_batched,
+                                                               int N, int64_t HW, float* __restrict__ out) {
+  const int64_t total = (int64_t)N * HW;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / HW);
+    const int64_t p = idx - (int64_t)n * HW;
+    const float m = fgm[((int64_t)n * 4 + 3) * HW + p];
+    for (int c = 0; c < 3; ++c) {
+      const float fg = fgm[((int64_t)n * 4 + c) * HW + p];
+      const float bb = bg[((bg_batched ? (int64_t)n * 3 : 0) + c) * HW + p];
+      out[((int64_t)n * 3 + c) * HW + p] = m * fg + (1.f - m) * bb;
+    }
+  }
+}
+
+}  // namespace nhvr
+
+using namespace nhvr;
+
+extern "C" int nhvr_texture_sample(const float* uvp, const float* atlas, int32_t N, int32_t H, int32_t W, int32_t S,
+                                   int32_t Ctex, int32_t use_mask_texture, float* tex_out, uint8_t* part_out,
+                                   int16_t* texel_out, void* stream) {
+  if (!uvp || !atlas || !tex_out) return NHVR_ERR_NULL;
+  if (N <= 0 || H <= 0 || W <= 0 || S < 2 || S > 32767 || Ctex <= 0 || Ctex > 20) return NHVR_ERR_SHAPE;
+  if (((uintptr_t)atlas & 15) != 0) return NHVR_ERR_ALIGN;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  const int G = (Ctex + 3) / 4;
+  const int64_t total = (int64_t)N * H * W;
+  const int blocks = (int)std::min<int64_t>((total + 127) / 128, (int64_t)148 * 16 * 8);
+  const float4* a4 = reinterpret_cast<const float4*>(atlas);
+  short2* tx = reinterpret_cast<short2*>(texel_out);
+  cudaStream_t st = (cudaStream_t)stream;
+#define NHVR_LAUNCH_SAMPLER(GG) \
+  texture_sample_kernel<GG><<<blocks, 128, 0, st>>>(uvp, a4, N, H, W, S, Ctex, use_mask_texture, tex_out, part_out, tx)
+  switch (G) {
+    case 1: NHVR_LAUNCH_SAMPLER(1); break;
+    case 2: NHVR_LAUNCH_SAMPLER(2); break;
+    case 3: NHVR_LAUNCH_SAMPLER(3); break;
+    case 4: NHVR_LAUNCH_SAMPLER(4); break;
+    default: NHVR_LAUNCH_SAMPLER(5); break;
+  }
+#undef NHVR_LAUNCH_SAMPLER
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
+  return NHVR_OK;
+}
+
+extern "C" int nhvr_composite(const float* fgm, const float* bg, int32_t bg_batched, int32_t N, int32_t H, int32_t W,
+                              float* out, void* stream) {
+  if (!fgm || !bg || !out) return NHVR_ERR_NULL;
+  if (N <= 0 || H <= 0 || W <= 0) return NHVR_ERR_SHAPE;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  const int64_t HW = (int64_t)H * W;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (HW % 4 == 0) && ((((uintptr_t)fgm | (uintptr_t)bg | (uintptr_t)out) & 15) == 0);
+  if (vec) {
+    const int64_t total = (int64_t)N * (HW / 4);
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)148 * 8 * 4);
+    composite_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(fgm), reinterpret_cast<const float4*>(bg),
+                                             bg_batched, N, HW / 4, reinterpret_cast<float4*>(out));
+  } else {
+    const int64_t total = (int64_t)N * HW;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)148 * 8 * 4);
+    composite_scalar_kernel<<<blocks, 256, 0, st>>>(fgm, bg, bg_batched, N, HW, out);
+  }
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
+  return NHVR_OK;
+}
