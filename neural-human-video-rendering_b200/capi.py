@@ -1,0 +1,115 @@
+"""ctypes binding of the C-ABI in include/nhvr.h (libnhvr_sm100.so).
+
+This is the ONLY way the Python host reaches the kernels: plain pointers and sizes, the stream of
+``torch.cuda.current_stream()``.  Loading fails loudly if the library has not been built
+(``__graft_entry__.build()`` / ``make -C neural-human-video-rendering_b200/csrc``); there is no
+fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libnhvr_sm100.so")
+
+# enums (include/nhvr.h)
+HALO_ZERO, HALO_REFLECT = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU02, ACT_TANH, ACT_TANH_SIGMOID_LAST = 0, 1, 2, 3, 4
+CONV, CONV_TRANSPOSE = 0, 1
+EPI_RAW_STATS, EPI_BIAS_ACT_F32, EPI_BIAS_ACT_P8 = 0, 1, 2
+
+
+class ActDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("N", "C8", "H", "W", "pad_t", "pad_l", "pad_b", "pad_r", "split", "halo")]
+
+    def copy(self) -> "ActDesc":
+        d = ActDesc()
+        C.memmove(C.byref(d), C.byref(self), C.sizeof(ActDesc))
+        return d
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("kind", "Cin", "Cout", "kh", "kw", "stride", "pad", "N", "H", "W", "halo", "epilogue", "act")]
+
+
+# every symbol include/nhvr.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "nhvr_version": (C.c_int, []),
+    "nhvr_strerror": (C.c_char_p, [C.c_int]),
+    "nhvr_last_cuda_error": (C.c_char_p, []),
+    "nhvr_arch_ok": (C.c_int, []),
+    "nhvr_launch_count": (C.c_uint64, []),
+    "nhvr_act_bytes": (C.c_size_t, [C.POINTER(ActDesc)]),
+    "nhvr_pack_nchw": (C.c_int, [C.POINTER(_P), C.POINTER(C.c_int32), C.c_int32, _P, C.POINTER(ActDesc), _P]),
+    "nhvr_unpack_nchw": (C.c_int, [_P, C.POINTER(ActDesc), _P, C.c_int32, _P]),
+    "nhvr_conv_plan_create": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(_P)]),
+    "nhvr_conv_plan_destroy": (None, [_P]),
+    "nhvr_conv_input_desc": (C.c_int, [_P, C.POINTER(ActDesc)]),
+    "nhvr_conv_output_dims": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "nhvr_conv_weight_bytes": (C.c_size_t, [_P]),
+    "nhvr_conv_flops": (C.c_double, [_P]),
+    "nhvr_conv_plan_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_int32]),
+    "nhvr_conv_pack_weights": (C.c_int, [_P, _P, _P, _P]),
+    "nhvr_conv_forward": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(ActDesc), _P, _P]),
+    "nhvr_in_apply": (C.c_int, [_P, C.POINTER(ActDesc), _P, C.c_float, C.c_int32, _P, C.POINTER(ActDesc), _P,
+                                C.POINTER(ActDesc), _P]),
+    "nhvr_texture_sample": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P,
+                                      _P, _P]),
+    "nhvr_composite": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+}
+
+_lib = None
+
+
+class NhvrError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """dlopen the library and bind every declared symbol; raises if it is missing (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NhvrError(
+                "libnhvr_sm100.so not built at %s — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU / PyTorch fallback for this path)" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)   # AttributeError here == header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        lib = load()
+        msg = lib.nhvr_strerror(status).decode()
+        cuda = lib.nhvr_last_cuda_error().decode()
+        raise NhvrError("%s failed: %s%s" % (what or "nhvr call", msg, (" [" + cuda + "]") if cuda else ""))
+
+
+def require_device() -> None:
+    """The product path needs a CUDA sm_100 device; fail loudly otherwise."""
+    if not torch.cuda.is_available():
+        raise NhvrError("nhvr_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
+    check(load().nhvr_arch_ok(), "nhvr_arch_ok")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def launch_count() -> int:
+    return int(load().nhvr_launch_count())

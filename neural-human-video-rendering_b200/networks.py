@@ -1,0 +1,259 @@
+"""define_G / define_D — the reference's network factory API, backed by the sm_100a kernels.
+
+Mirrors the (absent) reference ``models/networks.py`` that BASELINE.json names: same factory names and
+argument meaning as public pix2pixHD ``define_G`` / ``define_D`` [SURVEY §8(b)], same ``state_dict``
+keys (``model.<idx>.weight`` / ``model.<idx>.conv_block.<j>.weight``; D: ``scale<i>_layer<j>.0.weight``)
+so a real checkpoint (``<checkpoints_dir>/<name>/<epoch>_net_<label>.pth``) loads unchanged.  Widths
+and depths come from the reference's flags: --ngf_global/--n_downsample_global/--n_blocks_global
+[REF test_start/start.sh:15-17], --n_downsample_bg/--n_blocks_bg [REF start.sh:20-21],
+--n_blocks_translate [REF pretrainTrans.sh:13].
+
+The modules hold fp32 parameters (the checkpoint format) and a bf16 packed copy in the conv kernel's
+consumption order; ``forward`` takes / returns NCHW fp32 CUDA tensors like the reference's modules and
+runs entirely through the C-ABI (nhvr_b200.ops).  No torch.nn compute op is called on this path and
+there is no fallback: a CPU tensor or a missing library raises.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import capi, ops
+from .capi import NhvrError
+
+
+# ----------------------------------------------------------------------------------------------
+# parameter holders with the reference's module indices (never called)
+# ----------------------------------------------------------------------------------------------
+class _Slot(nn.Module):
+    """Index placeholder for a parameter-free reference module (pad / norm / activation)."""
+
+    def __init__(self, what: str):
+        super().__init__()
+        self.what = what
+
+    def extra_repr(self):
+        return self.what
+
+
+class _ConvParams(nn.Module):
+    """weight/bias with nn.Conv2d (or nn.ConvTranspose2d) shapes and names."""
+
+    def __init__(self, cin, cout, k, stride=1, pad=0, transposed=False):
+        super().__init__()
+        shape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
+        self.weight = nn.Parameter(torch.empty(*shape).normal_(0.0, 0.02))   # pix2pixHD weights_init
+        bound = 1.0 / float(cin * k * k) ** 0.5 if not transposed else 1.0 / float(cout * k * k) ** 0.5
+        self.bias = nn.Parameter(torch.empty(cout).uniform_(-bound, bound))  # nn.Conv2d default bias init
+        self.cin, self.cout, self.k, self.stride, self.pad, self.transposed = cin, cout, k, stride, pad, transposed
+
+
+class _ResnetBlockParams(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.conv_block = nn.Sequential(_Slot("ReflectionPad2d(1)"), _ConvParams(dim, dim, 3, pad=1), _Slot("InstanceNorm2d"),
+                                        _Slot("ReLU"), _Slot("ReflectionPad2d(1)"), _ConvParams(dim, dim, 3, pad=1),
+                                        _Slot("InstanceNorm2d"))
+
+
+# ----------------------------------------------------------------------------------------------
+# per-shape execution engine for a GlobalGenerator-shaped conv chain
+# ----------------------------------------------------------------------------------------------
+class _Step:
+    __slots__ = ("plan", "params", "post", "residual_from", "act")
+
+
+class _ChainEngine:
+    """Buffers + conv plans of one conv chain at a fixed (N, H, W).
+
+    chain: list of dicts {params, kind, k, stride, pad, halo, norm(bool), act, res('save'|'add'|None)}
+    The last layer has norm=False and writes fp32 NCHW with bias + ``final_act``.
+    """
+
+    def __init__(self, chain: List[dict], N: int, H: int, W: int, device, final_act: int, out_channels: int):
+        self.N, self.H, self.W = N, H, W
+        self.device = device
+        self.chain = chain
+        self.plans: List[ops.ConvPlan] = []
+        h, w = H, W
+        for i, L in enumerate(chain):
+            last = i == len(chain) - 1
+            p: _ConvParams = L["params"]
+            epi = capi.EPI_BIAS_ACT_F32 if last else capi.EPI_RAW_STATS
+            plan = ops.ConvPlan(capi.CONV_TRANSPOSE if p.transposed else capi.CONV, p.cin, p.cout, p.k, p.stride, p.pad,
+                                N, h, w, L["halo"], epi, final_act if last else capi.ACT_NONE)
+            self.plans.append(plan)
+            h, w = plan.Ho, plan.Wo
+        self.out = torch.empty(N, out_channels, h, w, dtype=torch.float32, device=device)
+        # input buffers: one per distinct input descriptor, rotating triple for residual chains
+        self._bufs: Dict[tuple, List[ops.P8Buffer]] = {}
+        self._raws: Dict[tuple, ops.P8Buffer] = {}
+        self.in_bufs: List[ops.P8Buffer] = []
+        self.raw_bufs: List[Optional[ops.P8Buffer]] = []
+        live: Optional[ops.P8Buffer] = None      # residual source that a later apply still has to read
+        for i, plan in enumerate(self.plans):
+            d = plan.in_desc
+            key = tuple(getattr(d, f) for f, _ in capi.ActDesc._fields_)
+            pool = self._bufs.setdefault(key, [])
+            # in_bufs[i] is written by the apply after conv i-1 (pack for i == 0): it must not be the live
+            # residual source nor the buffer conv i-1 reads
+            prev = self.in_bufs[-1] if self.in_bufs else None
+            chosen = next((b for b in pool if b is not live and b is not prev), None)
+            if chosen is None:
+                chosen = ops.P8Buffer(d.copy(), device)
+                pool.append(chosen)
+            self.in_bufs.append(chosen)
+            if i > 0 and chain[i - 1].get("res") == "add":
+                live = None                          # consumed by the apply that just wrote `chosen`
+            if chain[i].get("res") == "save":
+                live = chosen
+            if i < len(self.plans) - 1:
+                rd = plan.raw_desc()
+                rkey = (rd.N, rd.C8, rd.H, rd.W)
+                if rkey not in self._raws:
+                    self._raws[rkey] = ops.P8Buffer(rd, device)
+                self.raw_bufs.append(self._raws[rkey])
+            else:
+                self.raw_bufs.append(None)
+        # InstanceNorm statistics: one zero-fill per forward
+        sizes = [N * pl.Cout8 * 8 * 2 for pl in self.plans[:-1]]
+        self.stats_all = torch.zeros(max(1, sum(sizes)), dtype=torch.float32, device=device)
+        self.stats: List[torch.Tensor] = []
+        off = 0
+        for s in sizes:
+            self.stats.append(self.stats_all[off:off + s])
+            off += s
+        self.flops = sum(pl.flops for pl in self.plans)
+        self.weight_versions: Optional[tuple] = None
+
+    def pack_weights(self) -> None:
+        for L, plan in zip(self.chain, self.plans):
+            plan.pack_weights(L["params"].weight)
+
+    def maybe_repack(self) -> None:
+        ver = tuple(L["params"].weight._version for L in self.chain) + tuple(L["params"].weight.data_ptr() for L in self.chain)
+        if ver != self.weight_versions:
+            self.pack_weights()
+            self.weight_versions = ver
+
+    def run(self, inputs: Sequence[torch.Tensor]) -> torch.Tensor:
+        ops.pack_nchw(inputs, self.in_bufs[0])
+        return self.run_packed()
+
+    def run_packed(self) -> torch.Tensor:
+        """Run the chain assuming in_bufs[0] already holds the packed input."""
+        self.stats_all.zero_()
+        res_src: Optional[ops.P8Buffer] = None
+        n = len(self.plans)
+        for i, (L, plan) in enumerate(zip(self.chain, self.plans)):
+            x = self.in_bufs[i]
+            if L.get("res") == "save":
+                res_src = x
+            if i == n - 1:
+                plan.forward(x, self.out.data_ptr(), bias=L["params"].bias)
+                break
+            raw = self.raw_bufs[i]
+            plan.forward(x, raw.ptr, stats=self.stats[i])
+            ops.in_apply(raw, self.stats[i], L["act"], self.in_bufs[i + 1],
+                         residual=res_src if L.get("res") == "add" else None)
+            if L.get("res") == "add":
+                res_src = None
+        return self.out
+
+
+class GlobalGeneratorB200(nn.Module):
+    """pix2pixHD GlobalGenerator shape on the sm_100a kernels (see module docstring).
+
+    final: 'tanh' | 'none' | 'tanh_sigmoid_last' (SPEC D3 / D9).
+    """
+
+    def __init__(self, input_nc, output_nc, ngf=64, n_downsampling=3, n_blocks=9, final="tanh"):
+        super().__init__()
+        self.input_nc, self.output_nc, self.ngf = input_nc, output_nc, ngf
+        self.n_downsampling, self.n_blocks, self.final = n_downsampling, n_blocks, final
+        model: List[nn.Module] = [_Slot("ReflectionPad2d(3)"), _ConvParams(input_nc, ngf, 7, pad=3), _Slot("InstanceNorm2d"),
+                                  _Slot("ReLU")]
+        for i in range(n_downsampling):
+            mult = 2 ** i
+            model += [_ConvParams(ngf * mult, ngf * mult * 2, 3, stride=2, pad=1), _Slot("InstanceNorm2d"), _Slot("ReLU")]
+        mult = 2 ** n_downsampling
+        for _ in range(n_blocks):
+            model += [_ResnetBlockParams(ngf * mult)]
+        for i in range(n_downsampling):
+            mult = 2 ** (n_downsampling - i)
+            model += [_ConvParams(ngf * mult, ngf * mult // 2, 3, stride=2, pad=1, transposed=True),
+                      _Slot("InstanceNorm2d"), _Slot("ReLU")]
+        model += [_Slot("ReflectionPad2d(3)"), _ConvParams(ngf, output_nc, 7, pad=3)]
+        if final == "tanh":
+            model += [_Slot("Tanh")]
+        self.model = nn.Sequential(*model)
+        self._engines: Dict[tuple, _ChainEngine] = {}
+
+    # ---- chain description -------------------------------------------------------------------
+    def _chain(self) -> List[dict]:
+        R, Z = capi.HALO_REFLECT, capi.HALO_ZERO
+        chain: List[dict] = []
+        mods = list(self.model)
+        convs = [m for m in mods if isinstance(m, (_ConvParams, _ResnetBlockParams))]
+        for m in convs:
+            if isinstance(m, _ResnetBlockParams):
+                chain.append(dict(params=m.conv_block[1], halo=R, act=capi.ACT_RELU, res="save"))
+                chain.append(dict(params=m.conv_block[5], halo=R, act=capi.ACT_NONE, res="add"))
+            else:
+                chain.append(dict(params=m, halo=R if m.k == 7 else Z, act=capi.ACT_RELU, res=None))
+        return chain
+
+    def _final_act(self) -> int:
+        return {"tanh": capi.ACT_TANH, "none": capi.ACT_NONE, "tanh_sigmoid_last": capi.ACT_TANH_SIGMOID_LAST}[self.final]
+
+    def engine(self, N: int, H: int, W: int) -> _ChainEngine:
+        dev = self.model[1].weight.device
+        key = (N, H, W, dev.index)
+        eng = self._engines.get(key)
+        if eng is None:
+            capi.require_device()
+            if dev.type != "cuda":
+                raise NhvrError("GlobalGeneratorB200 parameters must live on a CUDA device (call .cuda()); no CPU path")
+            eng = _ChainEngine(self._chain(), N, H, W, dev, self._final_act(), self.output_nc)
+            self._engines[key] = eng
+        eng.maybe_repack()
+        return eng
+
+    def forward(self, x, *more):
+        """x (and optional further tensors, concatenated along C): NCHW fp32 CUDA -> NCHW fp32 CUDA."""
+        xs = (x,) + tuple(more)
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or any(
+                t.requires_grad for t in xs)):
+            raise NhvrError("backward through the sm_100a conv chain is not built yet (forward/inference only); "
+                            "wrap the call in torch.no_grad()")
+        for t in xs:
+            if not t.is_cuda:
+                raise NhvrError("nhvr_b200 modules take CUDA tensors only (no CPU fallback)")
+        cin = sum(t.shape[1] for t in xs)
+        if cin != self.input_nc:
+            raise NhvrError("expected %d input channels, got %d" % (self.input_nc, cin))
+        N, _, H, W = x.shape
+        eng = self.engine(N, H, W)
+        out = eng.run([t.float() for t in xs])
+        return out
+
+
+def define_G(input_nc, output_nc, ngf, netG="global", n_downsample_global=3, n_blocks_global=9, n_local_enhancers=1,
+             n_blocks_local=3, norm="instance", gpu_ids: Sequence[int] = ()):
+    """pix2pixHD ``define_G`` signature [SURVEY §8(b); named by BASELINE.json].
+
+    netG: 'global' | 'bg' (tanh), 'temporal' (RGB tanh + mask sigmoid), 'translate' (UV generator, raw 73 ch).
+    """
+    if norm != "instance":
+        raise NotImplementedError("only norm='instance' (the reference default) is built on sm_100a")
+    final = {"global": "tanh", "bg": "tanh", "temporal": "tanh_sigmoid_last", "translate": "none"}.get(netG)
+    if final is None:
+        raise NotImplementedError("generator [%s] not implemented" % netG)
+    net = GlobalGeneratorB200(input_nc, output_nc, ngf, n_downsample_global, n_blocks_global, final=final)
+    if len(gpu_ids) > 0:
+        net.cuda(gpu_ids[0])
+    elif torch.cuda.is_available():
+        net.cuda()
+    return net

@@ -1,0 +1,162 @@
+"""Thin Python operators over the C-ABI (include/nhvr.h): P8 buffers, conv plans, InstanceNorm apply,
+texture lookup, composite.  torch is used only to own device memory and to name the stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import capi
+from .capi import ActDesc, ConvDesc, check, load, ptr, stream_ptr
+
+
+class P8Buffer:
+    """A P8 (planar-by-8 bf16, halo-padded) activation in device memory."""
+
+    def __init__(self, desc: ActDesc, device=None, zero: bool = True):
+        self.desc = desc
+        nbytes = load().nhvr_act_bytes(C.byref(desc))
+        alloc = torch.zeros if zero else torch.empty
+        self.mem = alloc(nbytes, dtype=torch.uint8, device=device or torch.device("cuda"))
+
+    @property
+    def ptr(self) -> int:
+        return self.mem.data_ptr()
+
+
+def make_desc(N, C8, H, W, pad=(0, 0, 0, 0), split=0, halo=capi.HALO_ZERO) -> ActDesc:
+    d = ActDesc()
+    d.N, d.C8, d.H, d.W = N, C8, H, W
+    d.pad_t, d.pad_l, d.pad_b, d.pad_r = pad
+    d.split, d.halo = split, halo
+    return d
+
+
+def pack_nchw(srcs: Sequence[torch.Tensor], dst: P8Buffer) -> None:
+    """cat(srcs, dim=1) fp32 NCHW -> P8 bf16 with halo (nhvr_pack_nchw)."""
+    n = len(srcs)
+    arr = (C.c_void_p * n)()
+    cs = (C.c_int32 * n)()
+    keep = []
+    for i, s in enumerate(srcs):
+        s = s.contiguous()
+        assert s.dtype == torch.float32 and s.is_cuda and s.dim() == 4
+        assert s.shape[0] == dst.desc.N and s.shape[2] == dst.desc.H and s.shape[3] == dst.desc.W, \
+            (tuple(s.shape), dst.desc.N, dst.desc.H, dst.desc.W)
+        keep.append(s)
+        arr[i] = s.data_ptr()
+        cs[i] = s.shape[1]
+    check(load().nhvr_pack_nchw(arr, cs, n, dst.ptr, C.byref(dst.desc), stream_ptr()), "nhvr_pack_nchw")
+
+
+def unpack_nchw(src: P8Buffer, channels: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    d = src.desc
+    if out is None:
+        out = torch.empty(d.N, channels, d.H, d.W, dtype=torch.float32, device=src.mem.device)
+    check(load().nhvr_unpack_nchw(src.ptr, C.byref(d), out.data_ptr(), channels, stream_ptr()), "nhvr_unpack_nchw")
+    return out
+
+
+class ConvPlan:
+    """One conv layer lowered to the tcgen05 shift-GEMM kernel (nhvr_conv_plan_*)."""
+
+    def __init__(self, kind, Cin, Cout, k, stride, pad, N, H, W, halo, epilogue, act=capi.ACT_NONE):
+        d = ConvDesc()
+        d.kind, d.Cin, d.Cout, d.kh, d.kw, d.stride, d.pad = kind, Cin, Cout, k, k, stride, pad
+        d.N, d.H, d.W, d.halo, d.epilogue, d.act = N, H, W, halo, epilogue, act
+        self.desc = d
+        h = C.c_void_p()
+        check(load().nhvr_conv_plan_create(C.byref(d), C.byref(h)), "nhvr_conv_plan_create")
+        self.handle = h
+        self.in_desc = ActDesc()
+        check(load().nhvr_conv_input_desc(h, C.byref(self.in_desc)), "nhvr_conv_input_desc")
+        ho, wo, c8 = C.c_int32(), C.c_int32(), C.c_int32()
+        check(load().nhvr_conv_output_dims(h, C.byref(ho), C.byref(wo), C.byref(c8)), "nhvr_conv_output_dims")
+        self.Ho, self.Wo, self.Cout8 = ho.value, wo.value, c8.value
+        self.Cout, self.Cin, self.N = Cout, Cin, N
+        self.epilogue = epilogue
+        self.weight_bytes = load().nhvr_conv_weight_bytes(h)
+        self.flops = load().nhvr_conv_flops(h)
+        self.packed: Optional[torch.Tensor] = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                load().nhvr_conv_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        arr = (C.c_int32 * 16)()
+        check(load().nhvr_conv_plan_info(self.handle, arr, 16))
+        keys = ("kcp", "nchunks", "njobs", "nruns", "nacc", "slab_units", "Npad", "bpb", "nbstages", "SA", "SB",
+                "tmem_cols", "smem_bytes", "tiles_per_img", "nsplit", "nblocks")
+        return dict(zip(keys, list(arr)))
+
+    def raw_desc(self) -> ActDesc:
+        """Descriptor of the RAW_STATS output (un-padded P8)."""
+        return make_desc(self.N, self.Cout8, self.Ho, self.Wo)
+
+    def pack_weights(self, w: torch.Tensor) -> torch.Tensor:
+        w = w.detach().contiguous().float()
+        assert w.is_cuda
+        if self.packed is None:
+            self.packed = torch.empty(self.weight_bytes, dtype=torch.uint8, device=w.device)
+        check(load().nhvr_conv_pack_weights(self.handle, w.data_ptr(), self.packed.data_ptr(), stream_ptr()),
+              "nhvr_conv_pack_weights")
+        return self.packed
+
+    def forward(self, x: P8Buffer, out_ptr: int, bias: Optional[torch.Tensor] = None,
+                out_desc: Optional[ActDesc] = None, stats: Optional[torch.Tensor] = None) -> None:
+        assert self.packed is not None, "pack_weights() first"
+        check(load().nhvr_conv_forward(self.handle, x.ptr, self.packed.data_ptr(), ptr(bias), out_ptr,
+                                       C.byref(out_desc) if out_desc is not None else None, ptr(stats), stream_ptr()),
+              "nhvr_conv_forward")
+
+
+def in_apply(raw: P8Buffer, stats: torch.Tensor, act: int, dst: P8Buffer, residual: Optional[P8Buffer] = None,
+             eps: float = 1e-5) -> None:
+    check(load().nhvr_in_apply(raw.ptr, C.byref(raw.desc), stats.data_ptr(), eps, act,
+                               residual.ptr if residual is not None else None,
+                               C.byref(residual.desc) if residual is not None else None,
+                               dst.ptr, C.byref(dst.desc), stream_ptr()), "nhvr_in_apply")
+
+
+def atlas_to_channels_last(atlas: torch.Tensor) -> torch.Tensor:
+    """[24, Ctex, S, S] fp32 -> [24, S, S, Ct4] fp32 (the gather-friendly layout nhvr_texture_sample reads)."""
+    P, Ct, S, _ = atlas.shape
+    ct4 = (Ct + 3) // 4 * 4
+    out = torch.zeros(P, S, S, ct4, dtype=torch.float32, device=atlas.device)
+    out[..., :Ct] = atlas.detach().float().permute(0, 2, 3, 1)
+    return out.contiguous()
+
+
+def texture_sample(uvp: torch.Tensor, atlas_cl: torch.Tensor, Ctex: int, use_mask_texture: bool = True,
+                   tex_out: Optional[torch.Tensor] = None, want_indices: bool = True):
+    """nhvr_texture_sample: returns (tex [N,Ctex,H,W] f32, part [N,H,W] u8, texel [N,H,W,2] i16)."""
+    assert uvp.is_cuda and uvp.dtype == torch.float32 and uvp.is_contiguous() and uvp.shape[1] == 73
+    N, _, H, W = uvp.shape
+    S = atlas_cl.shape[1]
+    if tex_out is None:
+        tex_out = torch.empty(N, Ctex, H, W, dtype=torch.float32, device=uvp.device)
+    part = torch.empty(N, H, W, dtype=torch.uint8, device=uvp.device) if want_indices else None
+    texel = torch.empty(N, H, W, 2, dtype=torch.int16, device=uvp.device) if want_indices else None
+    check(load().nhvr_texture_sample(uvp.data_ptr(), atlas_cl.data_ptr(), N, H, W, S, Ctex, int(use_mask_texture),
+                                     tex_out.data_ptr(), ptr(part), ptr(texel), stream_ptr()), "nhvr_texture_sample")
+    return tex_out, part, texel
+
+
+def composite(fgm: torch.Tensor, bg: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nhvr_composite: out = m*fg + (1-m)*bg."""
+    assert fgm.is_cuda and fgm.dtype == torch.float32 and fgm.is_contiguous() and fgm.shape[1] == 4
+    assert bg.is_cuda and bg.dtype == torch.float32 and bg.is_contiguous()
+    N, _, H, W = fgm.shape
+    batched = int(bg.dim() == 4 and bg.shape[0] == N and N > 1)
+    if out is None:
+        out = torch.empty(N, 3, H, W, dtype=torch.float32, device=fgm.device)
+    check(load().nhvr_composite(fgm.data_ptr(), bg.data_ptr(), batched, N, H, W, out.data_ptr(), stream_ptr()),
+          "nhvr_composite")
+    return out

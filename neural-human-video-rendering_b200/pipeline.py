@@ -1,0 +1,175 @@
+"""The rendering hot path end to end on one B200, and its clip sharding across GPUs.
+
+Call stack (inferred from REF test_start/start.sh:6-28):
+
+    uvp  = netTransG(pose)                   UV generator              [REF pretrainTrans.sh:13]
+    tex  = texture_sample(atlas, uvp)        "--TexG part"             [REF start.sh:13-14,18]
+    fgm  = netG(cat(tex, pose, prev))        temporal generator        [REF start.sh:7,15-17]
+    bg'  = netBG(bg)                         once per clip             [REF start.sh:12,20-21]
+    out  = m*fg + (1-m)*bg'                  composite                 [REF README.md:15,52,60]
+    prev <- out   (zeros at clip start, SPEC D8)
+
+Attribute names equal oracle/pipeline.py's RenderModel so the two exchange ``state_dict``s.
+Inference shards independent clips: no collective.  Several clips can advance in
+lock-step as the batch dimension (``render_clips``); the per-step launch sequence is captured once in
+a CUDA graph and replayed, so the host issues one graph launch per frame step.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import capi, ops
+from .networks import define_G
+
+N_PARTS = 24
+UV_CHANNELS = 25 + 2 * N_PARTS
+
+
+class RenderPipeline(nn.Module):
+    def __init__(self, pose_nc: int = 3, tex_nc: int = 3, size: int = 512, atlas_size: int = 200,
+                 ngf_global: int = 48, n_downsample_global: int = 2, n_blocks_global: int = 10,
+                 ngf_translate: int = 64, n_downsample_translate: int = 2, n_blocks_translate: int = 5,
+                 ngf_bg: int = 48, n_downsample_bg: int = 2, n_blocks_bg: int = 2, use_mask_texture: bool = True):
+        super().__init__()
+        self.pose_nc, self.tex_nc, self.size, self.atlas_size = pose_nc, tex_nc, size, atlas_size
+        self.use_mask_texture = use_mask_texture
+        self.netTransG = define_G(pose_nc, UV_CHANNELS, ngf_translate, "translate", n_downsample_translate,
+                                  n_blocks_translate)
+        self.netG = define_G(tex_nc + pose_nc + 3, 4, ngf_global, "temporal", n_downsample_global, n_blocks_global)
+        self.netBG = define_G(3, 3, ngf_bg, "bg", n_downsample_bg, n_blocks_bg)
+        self.atlas = nn.Parameter(torch.empty(N_PARTS, tex_nc, atlas_size, atlas_size).uniform_(-1, 1))
+        self.bg = nn.Parameter(torch.empty(3, size, size).uniform_(-1, 1))
+        self._atlas_cl: Optional[torch.Tensor] = None
+        self._atlas_ver = None
+        self._graphs: Dict[tuple, "_StepGraph"] = {}
+
+    # ------------------------------------------------------------------ pieces
+    def atlas_channels_last(self) -> torch.Tensor:
+        ver = (self.atlas._version, self.atlas.data_ptr())
+        if self._atlas_cl is None or ver != self._atlas_ver:
+            self._atlas_cl = ops.atlas_to_channels_last(self.atlas)
+            self._atlas_ver = ver
+        return self._atlas_cl
+
+    @torch.no_grad()
+    def refine_bg(self) -> torch.Tensor:
+        return self.netBG(self.bg.detach().unsqueeze(0))[0].clone()
+
+    @torch.no_grad()
+    def render_frame(self, pose: torch.Tensor, prev: torch.Tensor, bg_refined: torch.Tensor,
+                     want_indices: bool = True) -> Dict[str, torch.Tensor]:
+        uvp = self.netTransG(pose)
+        tex, part, texel = ops.texture_sample(uvp, self.atlas_channels_last(), self.tex_nc, self.use_mask_texture,
+                                              want_indices=want_indices)
+        fgm = self.netG(tex, pose, prev)
+        out = ops.composite(fgm, bg_refined)
+        return {"out": out, "fgm": fgm, "tex": tex, "uvp": uvp, "part": part, "texel": texel}
+
+    @torch.no_grad()
+    def render_clip(self, poses: torch.Tensor, use_graph: bool = True) -> torch.Tensor:
+        """poses [T, pose_nc, H, W] (CUDA fp32) -> frames [T, 3, H, W]."""
+        return self.render_clips(poses.unsqueeze(0), use_graph=use_graph)[0]
+
+    @torch.no_grad()
+    def render_clips(self, poses: torch.Tensor, use_graph: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """poses [B, T, pose_nc, H, W]: B independent clips advanced in lock-step -> [B, T, 3, H, W].
+
+        ``poses`` may live in (pinned) host memory: each step's poses are copied host->device inside
+        the step; ``out`` may be a pinned host tensor the frames are copied back into.
+        """
+        B, T = poses.shape[:2]
+        H, W = poses.shape[-2:]
+        dev = self.bg.device
+        step = self.step_graph(B, H, W, use_graph)
+        step.reset()
+        if out is None:
+            out = torch.empty(B, T, 3, H, W, dtype=torch.float32, device=dev)
+        for t in range(T):
+            step.pose.copy_(poses[:, t], non_blocking=True)
+            step.run()
+            out[:, t].copy_(step.out, non_blocking=True)
+        return out
+
+    def step_graph(self, B: int, H: int, W: int, use_graph: bool = True) -> "_StepGraph":
+        key = (B, H, W, use_graph)
+        g = self._graphs.get(key)
+        if g is None:
+            g = _StepGraph(self, B, H, W, use_graph)
+            self._graphs[key] = g
+        return g
+
+
+class _StepGraph:
+    """One frame step for B lock-step clips with static buffers; optionally a captured CUDA graph."""
+
+    def __init__(self, pipe: RenderPipeline, B: int, H: int, W: int, use_graph: bool):
+        capi.require_device()
+        self.pipe = pipe
+        dev = pipe.bg.device
+        self.pose = torch.zeros(B, pipe.pose_nc, H, W, dtype=torch.float32, device=dev)
+        self.prev = torch.zeros(B, 3, H, W, dtype=torch.float32, device=dev)
+        self.out = self.prev          # the composite writes the next step's previous frame in place
+        self.bg_refined = pipe.refine_bg()
+        self.engT = pipe.netTransG.engine(B, H, W)
+        self.engG = pipe.netG.engine(B, H, W)
+        self.tex = torch.empty(B, pipe.tex_nc, H, W, dtype=torch.float32, device=dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = 0
+        if use_graph:
+            # warm up on a side stream (attribute set-up, weight packing), then capture
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._body()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.reset()
+            g = torch.cuda.CUDAGraph()
+            n0 = capi.launch_count()
+            with torch.cuda.graph(g):
+                self._body()
+            self.launches_per_step = capi.launch_count() - n0
+            self.graph = g
+            self.reset()
+        else:
+            n0 = capi.launch_count()
+            self._body()
+            self.launches_per_step = capi.launch_count() - n0
+            self.reset()
+
+    def reset(self) -> None:
+        self.prev.zero_()
+
+    def _body(self) -> None:
+        pipe = self.pipe
+        uvp = self.engT.run([self.pose])
+        ops.texture_sample(uvp, pipe.atlas_channels_last(), pipe.tex_nc, pipe.use_mask_texture, tex_out=self.tex,
+                           want_indices=False)
+        fgm = self.engG.run([self.tex, self.pose, self.prev])
+        ops.composite(fgm, self.bg_refined, out=self.prev)
+
+    def run(self) -> None:
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body()
+
+
+# ------------------------------------------------------------------ clip sharding (no collective)
+def shard_frames(n_frames: int, world_size: int, rank: int, clips_per_rank: int = 1) -> List[Tuple[int, int]]:
+    """Contiguous clip ranges [(start, stop), ...] of a length-n_frames sequence owned by ``rank``.
+
+    The sequence is cut into world_size*clips_per_rank contiguous clips (the first ``rem`` one frame
+    longer); rank r owns clips r*clips_per_rank .. (r+1)*clips_per_rank-1.  Each clip restarts the
+    previous-frame state at zeros (SPEC D8), so parity is defined per clip.
+    """
+    n_clips = world_size * clips_per_rank
+    base, rem = divmod(n_frames, n_clips)
+    bounds = [0]
+    for c in range(n_clips):
+        bounds.append(bounds[-1] + base + (1 if c < rem else 0))
+    return [(bounds[c], bounds[c + 1]) for c in range(rank * clips_per_rank, (rank + 1) * clips_per_rank)]
