@@ -76,6 +76,12 @@ int nhvr_version(void);
 const char* nhvr_strerror(int status);
 const char* nhvr_last_cuda_error(void);
 int nhvr_arch_ok(void);                 /* 0 iff the current device is compute capability 10.x */
+/* 16-bit element type of P8 activations and packed weights (the tcgen05 kind::f16 operands):
+ * 0 = bf16 (default), 1 = IEEE fp16 (same tensor throughput, 3 more mantissa bits, saturating
+ * conversion).  Process-wide; buffers and packed weights written under one setting must be consumed
+ * under the same setting. */
+int nhvr_set_operand_dtype(int is_f16);
+int nhvr_get_operand_dtype(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t nhvr_launch_count(void);
 

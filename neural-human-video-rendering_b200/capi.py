@@ -45,6 +45,8 @@ SYMBOLS = {
     "nhvr_last_cuda_error": (C.c_char_p, []),
     "nhvr_arch_ok": (C.c_int, []),
     "nhvr_launch_count": (C.c_uint64, []),
+    "nhvr_set_operand_dtype": (C.c_int, [C.c_int]),
+    "nhvr_get_operand_dtype": (C.c_int, []),
     "nhvr_act_bytes": (C.c_size_t, [C.POINTER(ActDesc)]),
     "nhvr_pack_nchw": (C.c_int, [C.POINTER(_P), C.POINTER(C.c_int32), C.c_int32, _P, C.POINTER(ActDesc), _P]),
     "nhvr_unpack_nchw": (C.c_int, [_P, C.POINTER(ActDesc), _P, C.c_int32, _P]),
@@ -64,6 +66,7 @@ SYMBOLS = {
     "nhvr_composite": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
 }
 
+DEFAULT_OPERAND = "bf16"
 _lib = None
 
 
@@ -85,7 +88,19 @@ def load() -> C.CDLL:
             fn.restype = res
             fn.argtypes = args
         _lib = lib
+        lib.nhvr_set_operand_dtype(1 if os.environ.get("NHVR_OPERAND", DEFAULT_OPERAND) == "f16" else 0)
     return _lib
+
+
+def set_operand_dtype(name: str) -> None:
+    """'bf16' or 'f16': element type of activations / packed weights (see include/nhvr.h).  Engines built
+    under one setting must not be reused under the other (weights are re-packed only on version change)."""
+    assert name in ("bf16", "f16")
+    load().nhvr_set_operand_dtype(1 if name == "f16" else 0)
+
+
+def operand_dtype() -> str:
+    return "f16" if load().nhvr_get_operand_dtype() else "bf16"
 
 
 def check(status: int, what: str = "") -> None:

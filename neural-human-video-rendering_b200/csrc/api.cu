@@ -9,6 +9,8 @@ namespace nhvr {
 static std::atomic<uint64_t> g_launches{0};
 static char g_last_err[256] = "";
 static int g_arch_state = -1;   // -1 unknown, 0 bad, 1 ok
+static int g_operand_f16 = 0;
+int operand_f16() { return g_operand_f16; }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -49,3 +51,6 @@ extern "C" const char* nhvr_strerror(int status) {
 extern "C" const char* nhvr_last_cuda_error(void) { return nhvr::g_last_err; }
 extern "C" int nhvr_arch_ok(void) { return nhvr::arch_ok_cached() == 1 ? 0 : NHVR_ERR_ARCH; }
 extern "C" uint64_t nhvr_launch_count(void) { return nhvr::g_launches.load(); }
+
+extern "C" int nhvr_set_operand_dtype(int is_f16) { nhvr::g_operand_f16 = is_f16 ? 1 : 0; return NHVR_OK; }
+extern "C" int nhvr_get_operand_dtype(void) { return nhvr::g_operand_f16; }

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #define NHVR_DEVINL __device__ __forceinline__
@@ -113,18 +114,29 @@ NHVR_DEVINL uint64_t make_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint
   return d;
 }
 
-// Instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, dense.
-// [4,6) c_format=1(F32), [7,10) a_format=1(BF16), [10,13) b_format=1(BF16), [15] a_major=0, [16] b_major=0,
+// Instruction descriptor for kind::f16: D=f32, A=B=bf16 or fp16, both K-major, dense.
+// [4,6) c_format=1(F32), [7,10) a_format (0 F16 / 1 BF16), [10,13) b_format, [15] a_major=0, [16] b_major=0,
 // [17,23) N>>3, [24,29) M>>4.
-__host__ __device__ inline uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+__host__ __device__ inline uint32_t make_idesc_16(uint32_t M, uint32_t N, int f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;   // F16 = 0, BF16 = 1
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
-NHVR_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
+// 16-bit operand element type of the whole path: bf16 (f16 == 0) or IEEE fp16 (f16 != 0).  Both feed
+// tcgen05.mma kind::f16 at the same rate; fp16 keeps 3 more mantissa bits (conversion saturates).
+NHVR_DEVINL uint32_t pack2(float lo, float hi, int f16) {
+  uint32_t r;
+  if (f16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
-NHVR_DEVINL float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
-NHVR_DEVINL float bf16hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+NHVR_DEVINL float unpack_lo(uint32_t v, int f16) {
+  if (f16) { __half2 h = *reinterpret_cast<__half2*>(&v); return __low2float(h); }
+  return __uint_as_float(v << 16);
+}
+NHVR_DEVINL float unpack_hi(uint32_t v, int f16) {
+  if (f16) { __half2 h = *reinterpret_cast<__half2*>(&v); return __high2float(h); }
+  return __uint_as_float(v & 0xFFFF0000u);
+}
 
 }  // namespace nhvr

@@ -28,6 +28,7 @@ namespace nhvr {
 extern void note_cuda_error(cudaError_t e);
 extern void count_launch();
 extern int arch_ok_cached();
+extern int operand_f16();
 
 constexpr int kMaxJobs = 52;
 constexpr int kMaxRuns = 8;
@@ -60,6 +61,7 @@ struct ConvKParams {
   int32_t Ho, Wo, Cout, Cout8;
   int32_t epilogue, act;
   int32_t tmem_cols;
+  int32_t f16;             // operand element type: 0 bf16, 1 fp16
   ActGeom og;              // BIAS_ACT_P8 destination
   ConvRun runs[kMaxRuns];
   ConvJob jobs[kMaxJobs];
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(256, 1) conv_shiftgemm_kernel(const __grid_con
   } else if (warp == 2) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)P.Npad);
+      const uint32_t idesc = make_idesc_16(kTileM, (uint32_t)P.Npad, P.f16);
       const uint32_t a_lbo = (uint32_t)P.slab_units * 16u;
       const uint32_t b_lbo = (uint32_t)P.Npad * 16u;
       const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
@@ -249,10 +251,10 @@ __global__ void __launch_bounds__(256, 1) conv_shiftgemm_kernel(const __grid_con
             const int64_t u0 = (((int64_t)n * P.Cout8 + (c0 >> 3)) * P.Ho + Y) * P.Wo + X;
             const int64_t pstride = (int64_t)P.Ho * P.Wo;
             uint4 lo, hi;
-            lo.x = pack_bf16x2(v[0], v[1]);  lo.y = pack_bf16x2(v[2], v[3]);
-            lo.z = pack_bf16x2(v[4], v[5]);  lo.w = pack_bf16x2(v[6], v[7]);
-            hi.x = pack_bf16x2(v[8], v[9]);  hi.y = pack_bf16x2(v[10], v[11]);
-            hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
+            lo.x = pack2(v[0], v[1], P.f16);  lo.y = pack2(v[2], v[3], P.f16);
+            lo.z = pack2(v[4], v[5], P.f16);  lo.w = pack2(v[6], v[7], P.f16);
+            hi.x = pack2(v[8], v[9], P.f16);  hi.y = pack2(v[10], v[11], P.f16);
+            hi.z = pack2(v[12], v[13], P.f16); hi.w = pack2(v[14], v[15], P.f16);
             if ((c0 >> 3) < P.Cout8) o[u0] = lo;
             if ((c0 >> 3) + 1 < P.Cout8) o[u0 + pstride] = hi;
           }
@@ -287,10 +289,10 @@ __global__ void __launch_bounds__(256, 1) conv_shiftgemm_kernel(const __grid_con
               t[i] = (c < P.Cout) ? apply_act(val, P.act, c == P.Cout - 1) : 0.f;
             }
             uint4 lo, hi;
-            lo.x = pack_bf16x2(t[0], t[1]);  lo.y = pack_bf16x2(t[2], t[3]);
-            lo.z = pack_bf16x2(t[4], t[5]);  lo.w = pack_bf16x2(t[6], t[7]);
-            hi.x = pack_bf16x2(t[8], t[9]);  hi.y = pack_bf16x2(t[10], t[11]);
-            hi.z = pack_bf16x2(t[12], t[13]); hi.w = pack_bf16x2(t[14], t[15]);
+            lo.x = pack2(t[0], t[1], P.f16);  lo.y = pack2(t[2], t[3], P.f16);
+            lo.z = pack2(t[4], t[5], P.f16);  lo.w = pack2(t[6], t[7], P.f16);
+            hi.x = pack2(t[8], t[9], P.f16);  hi.y = pack2(t[10], t[11], P.f16);
+            hi.z = pack2(t[12], t[13], P.f16); hi.w = pack2(t[14], t[15], P.f16);
             const int p0 = c0 >> 3;
             if (p0 < P.og.C8) o[act_unit(P.og, n, p0, Y + P.og.pad_t, X + P.og.pad_l)] = lo;
             if (p0 + 1 < P.og.C8) o[act_unit(P.og, n, p0 + 1, Y + P.og.pad_t, X + P.og.pad_l)] = hi;
@@ -322,6 +324,7 @@ struct PackParams {
   uint4* dst;
   int32_t Cin, Cout, kh, kw, transposed;
   int32_t kcp, nchunks, njobs, Npad, nsplit, nblocks_padded;
+  int32_t f16;
   int16_t job_tap[kMaxJobs];   // r*kw + s of each job
 };
 
@@ -354,8 +357,8 @@ __global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
         }
         vals[e] = val;
       }
-      packed[0] = pack_bf16x2(vals[0], vals[1]); packed[1] = pack_bf16x2(vals[2], vals[3]);
-      packed[2] = pack_bf16x2(vals[4], vals[5]); packed[3] = pack_bf16x2(vals[6], vals[7]);
+      packed[0] = pack2(vals[0], vals[1], P.f16); packed[1] = pack2(vals[2], vals[3], P.f16);
+      packed[2] = pack2(vals[4], vals[5], P.f16); packed[3] = pack2(vals[6], vals[7], P.f16);
     }
     P.dst[u] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
   }
@@ -594,6 +597,7 @@ extern "C" int nhvr_conv_pack_weights(const nhvr_conv_plan* p, const float* w, v
   if (!arch_ok_cached()) return NHVR_ERR_ARCH;
   PackParams PP = p->pp;
   PP.w = w;
+  PP.f16 = operand_f16();
   PP.dst = reinterpret_cast<uint4*>(packed);
   const int64_t total = (int64_t)PP.nsplit * PP.nblocks_padded * 2 * PP.Npad;
   const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
@@ -616,6 +620,7 @@ extern "C" int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const 
     K.og = make_geom(*out_desc);
     if (K.og.H != p->Ho || K.og.W != p->Wo || K.og.N != p->d.N) return NHVR_ERR_SHAPE;
   }
+  K.f16 = operand_f16();
   K.in = reinterpret_cast<const uint4*>(in);
   K.w = reinterpret_cast<const uint4*>(packed_w);
   K.bias = bias;

@@ -11,6 +11,7 @@ namespace nhvr {
 extern void note_cuda_error(cudaError_t e);
 extern void count_launch();
 extern int arch_ok_cached();
+extern int operand_f16();
 
 // map a padded destination coordinate to its logical source; returns false for "write zeros"
 NHVR_DEVINL bool dst_to_src(const ActGeom& g, int yy, int xx, int& y, int& x) {
@@ -30,6 +31,7 @@ struct PackParams2 {
   int32_t nsrc;
   uint4* dst;
   ActGeom g;
+  int32_t f16;
 };
 
 __global__ void __launch_bounds__(256) pack_nchw_kernel(const __grid_constant__ PackParams2 P) {
@@ -62,14 +64,14 @@ __global__ void __launch_bounds__(256) pack_nchw_kernel(const __grid_constant__ 
       }
     }
     uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    o.x = pack2(v[0], v[1], P.f16); o.y = pack2(v[2], v[3], P.f16);
+    o.z = pack2(v[4], v[5], P.f16); o.w = pack2(v[6], v[7], P.f16);
     P.dst[(int64_t)np * g.plane_units + plane_unit(g, yy, xx)] = o;
   }
 }
 
 __global__ void __launch_bounds__(256) unpack_nchw_kernel(const uint4* __restrict__ src, ActGeom g, float* __restrict__ dst,
-                                                          int C) {
+                                                          int C, int f16) {
   const int np = blockIdx.y;
   const int n = np / g.C8, p = np - n * g.C8;
   const int64_t HW = (int64_t)g.H * g.W;
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(256) unpack_nchw_kernel(const uint4* __restric
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = p * 8 + e;
-      if (c < C) dst[((int64_t)n * C + c) * HW + i] = (e & 1) ? bf16hi(w[e >> 1]) : bf16lo(w[e >> 1]);
+      if (c < C) dst[((int64_t)n * C + c) * HW + i] = (e & 1) ? unpack_hi(w[e >> 1], f16) : unpack_lo(w[e >> 1], f16);
     }
   }
 }
@@ -93,6 +95,7 @@ struct ApplyParams {
   ActGeom rg, sg, dg;    // raw, residual, destination geometry
   float eps, inv_hw;
   int32_t act;
+  int32_t f16;
 };
 
 __global__ void __launch_bounds__(256) in_apply_kernel(const __grid_constant__ ApplyParams P) {
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(256) in_apply_kernel(const __grid_constant__ A
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float xv = (e & 1) ? bf16hi(rw[e >> 1]) : bf16lo(rw[e >> 1]);
+        const float xv = (e & 1) ? unpack_hi(rw[e >> 1], P.f16) : unpack_lo(rw[e >> 1], P.f16);
         float t = fmaf(xv, scale[e], shift[e]);
         if (P.act == NHVR_ACT_RELU) t = fmaxf(t, 0.f);
         else if (P.act == NHVR_ACT_LRELU02) t = t > 0.f ? t : 0.2f * t;
@@ -132,10 +135,10 @@ __global__ void __launch_bounds__(256) in_apply_kernel(const __grid_constant__ A
         const uint4 s = P.res[act_unit(P.sg, n, p, y + P.sg.pad_t, x + P.sg.pad_l)];
         const uint32_t sw[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] += (e & 1) ? bf16hi(sw[e >> 1]) : bf16lo(sw[e >> 1]);
+        for (int e = 0; e < 8; ++e) v[e] += (e & 1) ? unpack_hi(sw[e >> 1], P.f16) : unpack_lo(sw[e >> 1], P.f16);
       }
-      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      o.x = pack2(v[0], v[1], P.f16); o.y = pack2(v[2], v[3], P.f16);
+      o.z = pack2(v[4], v[5], P.f16); o.w = pack2(v[6], v[7], P.f16);
     }
     P.dst[(int64_t)np * g.plane_units + plane_unit(g, yy, xx)] = o;
   }
@@ -173,6 +176,7 @@ extern "C" int nhvr_pack_nchw(const float* const* src, const int32_t* src_c, int
   P.nsrc = nsrc;
   P.dst = reinterpret_cast<uint4*>(dst);
   P.g = make_geom(*dst_desc);
+  P.f16 = operand_f16();
   if (csum > P.g.C8 * 8) return NHVR_ERR_SHAPE;
   const int planes = P.g.N * P.g.C8;
   dim3 grid(grid_x_for((int64_t)P.g.Hp * P.g.Wp, planes), planes);
@@ -192,7 +196,7 @@ extern "C" int nhvr_unpack_nchw(const void* src, const nhvr_act_desc* src_desc, 
   // planes beyond ceil(C/8) hold nothing we need; but blockIdx.y indexes n*C8+p, so launch all
   dim3 grid(grid_x_for((int64_t)g.H * g.W, g.N * g.C8), g.N * g.C8);
   (void)planes;
-  unpack_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(src), g, dst, C);
+  unpack_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(src), g, dst, C, operand_f16());
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
@@ -219,6 +223,7 @@ extern "C" int nhvr_in_apply(const void* raw, const nhvr_act_desc* raw_desc, con
   P.eps = eps;
   P.inv_hw = 1.0f / ((float)P.rg.H * (float)P.rg.W);
   P.act = act;
+  P.f16 = operand_f16();
   const int planes = P.dg.N * P.dg.C8;
   dim3 grid(grid_x_for((int64_t)P.dg.Hp * P.dg.Wp, planes), planes);
   in_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);

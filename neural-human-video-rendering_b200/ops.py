@@ -12,6 +12,35 @@ from . import capi
 from .capi import ActDesc, ConvDesc, check, load, ptr, stream_ptr
 
 
+# bench.py's per-kernel roofline pass: when PROFILE is a list, every launch below is bracketed by CUDA
+# events on the launching stream and recorded as (kind, algorithmic work, start, stop).
+PROFILE = None
+
+
+class _prof:
+    __slots__ = ("kind", "work", "e0")
+
+    def __init__(self, kind: str, work: float):
+        self.kind, self.work, self.e0 = kind, work, None
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.kind, self.work, self.e0, e1))
+        return False
+
+
+def _act_interior_bytes(d: ActDesc) -> float:
+    return float(d.N) * d.C8 * d.H * d.W * 16.0
+
+
 class P8Buffer:
     """A P8 (planar-by-8 bf16, halo-padded) activation in device memory."""
 
@@ -48,7 +77,9 @@ def pack_nchw(srcs: Sequence[torch.Tensor], dst: P8Buffer) -> None:
         keep.append(s)
         arr[i] = s.data_ptr()
         cs[i] = s.shape[1]
-    check(load().nhvr_pack_nchw(arr, cs, n, dst.ptr, C.byref(dst.desc), stream_ptr()), "nhvr_pack_nchw")
+    work = sum(float(k.numel()) * 4.0 for k in keep) + _act_interior_bytes(dst.desc)
+    with _prof("pack", work):
+        check(load().nhvr_pack_nchw(arr, cs, n, dst.ptr, C.byref(dst.desc), stream_ptr()), "nhvr_pack_nchw")
 
 
 def unpack_nchw(src: P8Buffer, channels: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -112,17 +143,21 @@ class ConvPlan:
     def forward(self, x: P8Buffer, out_ptr: int, bias: Optional[torch.Tensor] = None,
                 out_desc: Optional[ActDesc] = None, stats: Optional[torch.Tensor] = None) -> None:
         assert self.packed is not None, "pack_weights() first"
-        check(load().nhvr_conv_forward(self.handle, x.ptr, self.packed.data_ptr(), ptr(bias), out_ptr,
-                                       C.byref(out_desc) if out_desc is not None else None, ptr(stats), stream_ptr()),
-              "nhvr_conv_forward")
+        with _prof("conv", self.flops):
+            check(load().nhvr_conv_forward(self.handle, x.ptr, self.packed.data_ptr(), ptr(bias), out_ptr,
+                                           C.byref(out_desc) if out_desc is not None else None, ptr(stats), stream_ptr()),
+                  "nhvr_conv_forward")
 
 
 def in_apply(raw: P8Buffer, stats: torch.Tensor, act: int, dst: P8Buffer, residual: Optional[P8Buffer] = None,
              eps: float = 1e-5) -> None:
-    check(load().nhvr_in_apply(raw.ptr, C.byref(raw.desc), stats.data_ptr(), eps, act,
-                               residual.ptr if residual is not None else None,
-                               C.byref(residual.desc) if residual is not None else None,
-                               dst.ptr, C.byref(dst.desc), stream_ptr()), "nhvr_in_apply")
+    # algorithmic bytes: read raw (+ residual), write the interior once
+    work = _act_interior_bytes(raw.desc) * (3.0 if residual is not None else 2.0)
+    with _prof("in_apply", work):
+        check(load().nhvr_in_apply(raw.ptr, C.byref(raw.desc), stats.data_ptr(), eps, act,
+                                   residual.ptr if residual is not None else None,
+                                   C.byref(residual.desc) if residual is not None else None,
+                                   dst.ptr, C.byref(dst.desc), stream_ptr()), "nhvr_in_apply")
 
 
 def atlas_to_channels_last(atlas: torch.Tensor) -> torch.Tensor:
@@ -144,8 +179,10 @@ def texture_sample(uvp: torch.Tensor, atlas_cl: torch.Tensor, Ctex: int, use_mas
         tex_out = torch.empty(N, Ctex, H, W, dtype=torch.float32, device=uvp.device)
     part = torch.empty(N, H, W, dtype=torch.uint8, device=uvp.device) if want_indices else None
     texel = torch.empty(N, H, W, 2, dtype=torch.int16, device=uvp.device) if want_indices else None
-    check(load().nhvr_texture_sample(uvp.data_ptr(), atlas_cl.data_ptr(), N, H, W, S, Ctex, int(use_mask_texture),
-                                     tex_out.data_ptr(), ptr(part), ptr(texel), stream_ptr()), "nhvr_texture_sample")
+    # algorithmic bytes: 73 fp32 channels read + Ctex fp32 written per pixel; atlas L2-resident, excluded
+    with _prof("sampler", float(N) * H * W * (73 + Ctex) * 4.0):
+        check(load().nhvr_texture_sample(uvp.data_ptr(), atlas_cl.data_ptr(), N, H, W, S, Ctex, int(use_mask_texture),
+                                         tex_out.data_ptr(), ptr(part), ptr(texel), stream_ptr()), "nhvr_texture_sample")
     return tex_out, part, texel
 
 
@@ -157,6 +194,8 @@ def composite(fgm: torch.Tensor, bg: torch.Tensor, out: Optional[torch.Tensor] =
     batched = int(bg.dim() == 4 and bg.shape[0] == N and N > 1)
     if out is None:
         out = torch.empty(N, 3, H, W, dtype=torch.float32, device=fgm.device)
-    check(load().nhvr_composite(fgm.data_ptr(), bg.data_ptr(), batched, N, H, W, out.data_ptr(), stream_ptr()),
-          "nhvr_composite")
+    # algorithmic bytes: (3 fg + 1 mask + 3 bg) read + 3 written, fp32, bg counted per frame
+    with _prof("composite", float(N) * H * W * 10 * 4.0):
+        check(load().nhvr_composite(fgm.data_ptr(), bg.data_ptr(), batched, N, H, W, out.data_ptr(), stream_ptr()),
+              "nhvr_composite")
     return out

@@ -9,6 +9,10 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    import torch
+    # the oracle is fp32: no TF32 shortcuts when it runs on the GPU as the checker
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu via gpurun)")
 
 
