@@ -109,7 +109,7 @@ int nhvr_conv_plan_info(const nhvr_conv_plan* p, int32_t* info, int32_t n);
 /* w: fp32, Conv2d layout [Cout][Cin][kh][kw] or ConvTranspose2d layout [Cin][Cout][kh][kw]. */
 int nhvr_conv_pack_weights(const nhvr_conv_plan* p, const float* w, void* packed, void* stream);
 /* out / stats / bias meaning depends on the plan's epilogue:
- *  RAW_STATS    : out = P8 [N][Cout8][Ho][Wo] (no halo); stats = float [N][Cout8*8][2], must be zeroed
+ *  RAW_STATS    : out = P8 [N][Cout8][Ho][Wo] (no halo, Cout8 = ceil(Cout/8) rounded up to even); stats = float [N][Cout8*8][2], must be zeroed
  *                 by the caller (sum, sum of squares over H*W, accumulated with atomics); bias unused
  *                 (a bias in front of an affine-free InstanceNorm cancels exactly).
  *  BIAS_ACT_F32 : out = float [N][Cout][Ho][Wo]; bias = float [Cout] or NULL.

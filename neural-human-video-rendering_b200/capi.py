@@ -66,7 +66,10 @@ SYMBOLS = {
     "nhvr_composite": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
 }
 
-DEFAULT_OPERAND = "bf16"
+# fp16 operands are the default: measured on B200 at 512^2 against the fp32 oracle the temporal generator is
+# within max-abs 1e-2 / 63 dB with fp16 operands but 8e-2 / 45 dB with bf16 (profiles/r01_precision.log), and
+# only the former meets the 2e-2 / 45 dB parity bar.  Same tcgen05 kind::f16 rate.  NHVR_OPERAND=bf16 selects bf16.
+DEFAULT_OPERAND = "f16"
 _lib = None
 
 

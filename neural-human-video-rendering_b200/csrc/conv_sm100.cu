@@ -506,7 +506,10 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   K.Npad = Npad;
   K.tmem_cols = next_pow2_cols(nacc * Npad);
   p->nsplit = nsplit;
-  p->Ho = Ho; p->Wo = Wo; p->Cout8 = (d->Cout + 7) / 8;
+  p->Ho = Ho; p->Wo = Wo;
+  // P8 outputs carry an even number of planes (zero channels beyond Cout) so that they can feed the next
+  // conv directly: one MMA consumes K = 16 channels = 2 planes
+  p->Cout8 = round_up((d->Cout + 7) / 8, 2);
   K.Ho = Ho; K.Wo = Wo; K.Cout = d->Cout; K.Cout8 = p->Cout8;
   K.epilogue = d->epilogue; K.act = d->act;
 
@@ -533,7 +536,14 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   };
   int kcp = 0, SA = 0, bpb = 0, SB = 0;
   bool ok = false;
-  if (K.tmem_cols <= 256) ok = try_fit(100 * 1024, kcp, SA, bpb, SB);
+  if (const char* tune = std::getenv("NHVR_CONV_TUNE")) {   // experiments: "kcp,SA,bpb,SB"
+    int a, b, c, e;
+    if (std::sscanf(tune, "%d,%d,%d,%d", &a, &b, &c, &e) == 4 && a >= 2 && (a % 2) == 0 && C8 % a == 0 && b >= 1 && c >= 1 && e >= 2) {
+      const long need = (long)std::min(b, C8 / a) * a * slab * 16 + (long)e * c * b_block + 2048 + (long)Npad * 8;
+      if (need <= 227 * 1024) { kcp = a; SA = std::min(b, C8 / a); bpb = c; SB = e; ok = true; }
+    }
+  }
+  if (!ok && K.tmem_cols <= 256) ok = try_fit(100 * 1024, kcp, SA, bpb, SB);
   if (!ok) ok = try_fit(220 * 1024, kcp, SA, bpb, SB);
   if (!ok) { delete p; return NHVR_ERR_SMEM; }
   K.kcp = kcp; K.SA = SA; K.bpb = bpb; K.SB = SB;

@@ -100,7 +100,12 @@ class BaseOptions:
     def parse(self, args=None, save=False):
         if not self.initialized:
             self.initialize()
-        self.opt = self.parser.parse_args(args)
+        import sys as _sys
+        argv = list(_sys.argv[1:] if args is None else args)
+        # pretrainTrans.sh:16 ends with a line-continuation backslash at EOF, which bash passes on as a
+        # literal "\\" argument; drop it so the script runs unmodified
+        argv = [a for a in argv if a.strip() != "\\"]
+        self.opt = self.parser.parse_args(argv)
         self.opt.isTrain = self.isTrain
         ids = [int(s) for s in str(self.opt.gpu_ids).split(",") if s.strip() != ""]
         self.opt.gpu_ids = [i for i in ids if i >= 0]

@@ -1,0 +1,185 @@
+"""CPU suite: C-ABI library loads and exports every declared symbol; conv plan builder (host-only);
+P8 geometry; clip sharding incl. a world_size-2 gloo run; pose rasteriser; checkpoint naming."""
+import ctypes as C
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    from nhvr_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "nhvr.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(nhvr_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = capi.load()
+    for name in declared:
+        assert hasattr(lib, name), "library does not export %s" % name
+    assert declared == set(capi.SYMBOLS.keys()), declared ^ set(capi.SYMBOLS.keys())
+    assert lib.nhvr_version() >= 100
+    assert lib.nhvr_strerror(-1).decode().startswith("device is not compute capability 10")
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only check")
+def test_compute_entry_points_fail_loudly_without_sm100():
+    from nhvr_b200 import capi
+    lib = capi.load()
+    assert lib.nhvr_arch_ok() == -1
+    with pytest.raises(capi.NhvrError):
+        capi.require_device()
+    # a compute call off-device must return the ARCH error, never succeed silently (dummy non-null pointers)
+    buf = (C.c_float * 64)()
+    st = lib.nhvr_composite(C.cast(buf, C.c_void_p), C.cast(buf, C.c_void_p), 0, 1, 2, 2, C.cast(buf, C.c_void_p), None)
+    assert st == -1
+
+
+def _plan(kind, cin, cout, k, s, p, N, H, W, halo, epi):
+    from nhvr_b200 import ops
+    return ops.ConvPlan(kind, cin, cout, k, s, p, N, H, W, halo, epi)
+
+
+def test_conv_plans_of_the_reference_networks():
+    """Plan builder is host code: tile counts, job/run programs and budgets for every layer shape of
+    G_main (ngf 48), TransG (ngf 64) and D (ndf 64) at 512^2."""
+    from nhvr_b200 import capi
+    R, Z = capi.HALO_REFLECT, capi.HALO_ZERO
+    cases = [
+        (capi.CONV, 9, 48, 7, 1, 3, 1, 512, 512, R, 49, 1),
+        (capi.CONV, 48, 96, 3, 2, 1, 1, 512, 512, Z, 9, 1),
+        (capi.CONV, 96, 192, 3, 2, 1, 1, 256, 256, Z, 9, 1),
+        (capi.CONV, 192, 192, 3, 1, 1, 1, 128, 128, R, 9, 1),
+        (capi.CONV_TRANSPOSE, 192, 96, 3, 2, 1, 1, 128, 128, Z, 9, 4),
+        (capi.CONV_TRANSPOSE, 96, 48, 3, 2, 1, 1, 256, 256, Z, 9, 4),
+        (capi.CONV, 48, 4, 7, 1, 3, 1, 512, 512, R, 49, 1),
+        (capi.CONV, 64, 73, 7, 1, 3, 1, 512, 512, R, 49, 1),
+        (capi.CONV, 256, 256, 3, 1, 1, 8, 128, 128, R, 9, 1),
+        (capi.CONV, 6, 64, 4, 2, 2, 1, 512, 512, Z, 16, 1),
+        (capi.CONV, 256, 512, 4, 1, 2, 1, 65, 65, Z, 16, 1),
+        (capi.CONV, 512, 1, 4, 1, 2, 1, 66, 66, Z, 16, 1),
+    ]
+    for kind, cin, cout, k, s, p, N, H, W, halo, njobs, nacc in cases:
+        pl = _plan(kind, cin, cout, k, s, p, N, H, W, halo, capi.EPI_RAW_STATS)
+        info = pl.info()
+        assert info["njobs"] == njobs and info["nacc"] == nacc
+        assert info["smem_bytes"] <= 227 * 1024 and info["tmem_cols"] <= 512 and info["nacc"] * info["Npad"] <= info["tmem_cols"]
+        assert info["Npad"] % 16 == 0 and info["Npad"] * info["nsplit"] >= cout
+        assert info["kcp"] % 2 == 0 and info["kcp"] * info["nchunks"] * 8 >= cin
+        assert info["nblocks"] == info["nchunks"] * info["njobs"] * info["kcp"] // 2
+        if kind == capi.CONV_TRANSPOSE:
+            assert (pl.Ho, pl.Wo) == (2 * H, 2 * W)
+        else:
+            assert (pl.Ho, pl.Wo) == ((H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1)
+        # linearised tiling covers every valid output position with 128-row tiles
+        assert info["tiles_per_img"] * 128 >= (pl.Ho if kind == capi.CONV else H) * 1
+        assert pl.flops == pytest.approx(2.0 * k * k * cin * cout * (H * W if kind == capi.CONV_TRANSPOSE else pl.Ho * pl.Wo) * N)
+    # the bottleneck conv: one merged run of 3 rows, 130 tiles per 128^2 image (~128 CTAs)
+    pl = _plan(capi.CONV, 192, 192, 3, 1, 1, 1, 128, 128, R, capi.EPI_RAW_STATS)
+    assert pl.info()["nruns"] == 1 and pl.info()["slab_units"] == 390 and pl.info()["tiles_per_img"] == 130
+    assert pl.flops == pytest.approx(10.87e9, rel=1e-3)
+
+
+def test_conv_plan_rejects_bad_shapes():
+    from nhvr_b200 import capi
+    with pytest.raises(capi.NhvrError):
+        _plan(capi.CONV, 0, 8, 3, 1, 1, 1, 8, 8, 0, 0)
+    with pytest.raises(capi.NhvrError):
+        _plan(capi.CONV_TRANSPOSE, 8, 8, 4, 2, 1, 1, 8, 8, 0, 0)
+    with pytest.raises(capi.NhvrError):
+        _plan(capi.CONV, 8, 8, 9, 1, 4, 1, 8, 8, 0, 0)          # 81 taps > job table
+
+
+def test_p8_geometry_bytes():
+    from nhvr_b200 import ops, capi
+    lib = capi.load()
+    d = ops.make_desc(2, 3, 10, 12, (1, 1, 1, 1), 0, capi.HALO_REFLECT)
+    assert lib.nhvr_act_bytes(C.byref(d)) == (2 * 3 * 12 * 14 + 2048) * 16
+    d = ops.make_desc(1, 2, 9, 11, (1, 1, 1, 1), 1, capi.HALO_ZERO)       # split rounds 11x13 up to 12x14
+    assert lib.nhvr_act_bytes(C.byref(d)) == (1 * 2 * 12 * 14 + 2048) * 16
+
+
+def test_shard_frames_partitions_exactly():
+    from nhvr_b200.pipeline import shard_frames
+    for n, world, cpr in [(4096, 8, 1), (4096, 8, 4), (100, 8, 1), (100, 3, 2), (5, 8, 1), (0, 2, 1)]:
+        seen = []
+        for r in range(world):
+            clips = shard_frames(n, world, r, cpr)
+            assert len(clips) == cpr
+            for a, b in clips:
+                assert 0 <= a <= b <= n
+                seen += list(range(a, b))
+        assert seen == list(range(n))                     # contiguous, ordered, no overlap, nothing lost
+    assert shard_frames(4096, 8, 3, 1) == [(1536, 2048)]
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from nhvr_b200.pipeline import shard_frames
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    mine = shard_frames(101, world, rank, 2)
+    # each rank "renders" its clips: frame value = index; max-over-ranks timing via all_reduce MAX as in bench.py
+    frames = torch.zeros(101)
+    for a, b in mine:
+        frames[a:b] = torch.arange(a, b, dtype=torch.float32) + 1
+    dist.all_reduce(frames, op=dist.ReduceOp.SUM)
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        q.put((frames.tolist(), t.item()))
+    dist.destroy_process_group()
+
+
+def test_clip_sharding_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    frames, tmax = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert frames == [float(i + 1) for i in range(101)]      # every frame rendered by exactly one rank
+    assert tmax == 2.0
+
+
+def test_pose_rasteriser_on_reference_fixture():
+    from nhvr_b200 import pose
+    kp = pose.read_keypoints(os.path.join(GOLD, "keypoints_frame0.json"))
+    assert kp.shape == (25, 3) and (kp[:, 2] > 0.4).all()          # all 25 joints detected
+    assert 200 < kp[:, 0].min() and kp[:, 1].max() < 900
+    m = pose.pose_maps(kp[None], 128, pose_nc=6)
+    assert m.shape == (1, 6, 128, 128) and m.min() == -1.0 and m.max() <= 1.0
+    assert (m[0, 3:] == 0).all()                                    # Laplace channels absent in the fixture
+    drawn = (m[0, :3] > -1).any(0)
+    assert 0.005 < drawn.mean() < 0.2
+    ys, xs = np.nonzero(drawn)
+    assert abs(xs.mean() - kp[:, 0].mean() / 8) < 12 and abs(ys.mean() - kp[:, 1].mean() / 8) < 20
+    # alignment is the identity without a target and a pure scale/shift with one
+    seq = np.stack([kp, kp])
+    assert np.array_equal(pose.align_to_target(seq, None), seq)
+    tgt = seq.copy(); tgt[:, :, :2] = tgt[:, :, :2] * 0.5 + 10
+    al = pose.align_to_target(seq, tgt)
+    assert np.allclose(al[:, :, :2], tgt[:, :, :2], atol=1e-2)
+
+
+def test_checkpoint_naming_roundtrip(tmp_path):
+    from nhvr_b200.pipeline import RenderPipeline
+    from nhvr_b200.checkpoint import save_pipeline, load_pipeline, net_path
+    kw = dict(size=16, atlas_size=4, ngf_global=8, n_blocks_global=1, ngf_translate=8, n_blocks_translate=1, ngf_bg=8, n_blocks_bg=1)
+    a, b = RenderPipeline(**kw).cpu(), RenderPipeline(**kw).cpu()
+    save_pipeline(a, str(tmp_path), 30)
+    assert os.path.isfile(net_path(str(tmp_path), 30, "G")) and net_path("d", 30, "TransG").endswith("30_net_TransG.pth")
+    assert load_pipeline(b, str(tmp_path), 30)
+    for (k, v), (_, w) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(v.cpu(), w.cpu()), k
+    assert not load_pipeline(b, str(tmp_path), 31)
