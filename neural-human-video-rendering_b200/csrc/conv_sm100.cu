@@ -150,72 +150,99 @@ __global__ void __launch_bounds__(256, 1) conv_shiftgemm_kernel(const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------------------------ slab producer
-    if (lane == 0) {
+    {
       const uint4* img = P.in + (int64_t)n * P.C8in * P.in_plane_units + q0;
-      for (int c = 0; c < P.nchunks; ++c) {
-        const int st = c % P.SA;
-        const uint32_t ph = (uint32_t)(c / P.SA) & 1u;
+      int st = 0;
+      uint32_t ph = 0;
+      for (int c = 0; c < P.nchunks; ++c, st = (st + 1 == P.SA) ? 0 : st + 1, ph ^= (st == 0) ? 1u : 0u) {
         mbar_wait(&a_empty[st], ph ^ 1u);
-        mbar_arrive_expect_tx(&a_full[st], a_stage_bytes);
-        uint8_t* dst = a_smem + (size_t)st * a_stage_bytes;
-        for (int pl = 0; pl < P.kcp; ++pl) {
-          const uint4* plane = img + (int64_t)(c * P.kcp + pl) * P.in_plane_units;
-          for (int r = 0; r < P.nruns; ++r) {
-            bulk_g2s(dst + ((size_t)pl * P.slab_units + P.runs[r].s_off) * 16, plane + P.runs[r].g_off,
-                     (uint32_t)P.runs[r].len * 16u, &a_full[st]);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&a_full[st], a_stage_bytes);
+          uint8_t* dst = a_smem + (size_t)st * a_stage_bytes;
+          for (int pl = 0; pl < P.kcp; ++pl) {
+            const uint4* plane = img + (int64_t)(c * P.kcp + pl) * P.in_plane_units;
+            for (int r = 0; r < P.nruns; ++r) {
+              bulk_g2s(dst + ((size_t)pl * P.slab_units + P.runs[r].s_off) * 16, plane + P.runs[r].g_off,
+                       (uint32_t)P.runs[r].len * 16u, &a_full[st]);
+            }
           }
         }
+        __syncwarp();
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ weight producer
-    if (lane == 0) {
+    {
       const uint4* wsrc = P.w + (int64_t)split * P.w_split_units;
       const uint32_t stage_units = b_stage_bytes >> 4;
+      int st = 0;
+      uint32_t ph = 0;
       for (int s = 0; s < P.nbstages; ++s) {
-        const int st = s % P.SB;
-        const uint32_t ph = (uint32_t)(s / P.SB) & 1u;
         mbar_wait(&b_empty[st], ph ^ 1u);
-        mbar_arrive_expect_tx(&b_full[st], b_stage_bytes);
-        bulk_g2s(b_smem + (size_t)st * b_stage_bytes, wsrc + (int64_t)s * stage_units, b_stage_bytes, &b_full[st]);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&b_full[st], b_stage_bytes);
+          bulk_g2s(b_smem + (size_t)st * b_stage_bytes, wsrc, b_stage_bytes, &b_full[st]);
+        }
+        __syncwarp();
+        wsrc += stage_units;
+        if (++st == P.SB) { st = 0; ph ^= 1u; }
       }
     }
     __syncwarp();
   } else if (warp == 2) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // One thread feeds the tensor core, so this loop is kept to a handful of integer ops per MMA:
+    // descriptors are advanced incrementally in 16-byte units, ring positions by counters (no div/mod).
+    {
       const uint32_t idesc = make_idesc_16(kTileM, (uint32_t)P.Npad, P.f16);
-      const uint32_t a_lbo = (uint32_t)P.slab_units * 16u;
-      const uint32_t b_lbo = (uint32_t)P.Npad * 16u;
-      const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
-      const int qsteps = P.kcp >> 1;
-      int blk = 0;
+      const uint32_t a_lbo_u = (uint32_t)P.slab_units;            // plane stride, 16-B units
+      const uint32_t b_lbo_u = (uint32_t)P.Npad;
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);          // SBO = 128 B, version 1, no swizzle
+      const uint32_t a_lo0 = ((smem_u32(a_smem) & 0x3FFFFu) >> 4) | (a_lbo_u << 16);
+      const uint32_t b_lo0 = ((smem_u32(b_smem) & 0x3FFFFu) >> 4) | (b_lbo_u << 16);
+      const uint32_t a_stage_u = a_stage_bytes >> 4, b_block_u = b_block_bytes >> 4;
+      const uint32_t a_qstep_u = 2u * a_lbo_u;
+      const int qsteps = P.kcp >> 1, njobs = P.njobs, bpb = P.bpb, SA = P.SA, SB = P.SB;
+      const uint32_t npad = (uint32_t)P.Npad;
+      int ast = 0, bst = 0, bi = 0;
+      uint32_t aph = 0, bph = 0;
+      uint32_t b_lo = b_lo0;
       for (int c = 0; c < P.nchunks; ++c) {
-        const int st = c % P.SA;
-        mbar_wait(&a_full[st], (uint32_t)(c / P.SA) & 1u);
+        mbar_wait(&a_full[ast], aph);
         tc_fence_after();
-        const uint32_t a_st = a_base + (uint32_t)st * a_stage_bytes;
-        for (int j = 0; j < P.njobs; ++j) {
+        const uint32_t a_st_lo = a_lo0 + (uint32_t)ast * a_stage_u;
+        const uint32_t first_mask = (c == 0) ? 1u : 0u;
+        for (int j = 0; j < njobs; ++j) {
           const ConvJob job = P.jobs[j];
-          const uint32_t d_tmem = tmem_base + (uint32_t)job.acc * (uint32_t)P.Npad;
-          for (int q = 0; q < qsteps; ++q, ++blk) {
-            const int bs = blk / P.bpb, bi = blk - bs * P.bpb;
-            const int bst = bs % P.SB;
+          const uint32_t d_tmem = tmem_base + (uint32_t)job.acc * npad;
+          uint32_t a_lo = a_st_lo + (uint32_t)job.a_off;
+          uint32_t overwrite = first_mask & (uint32_t)job.first;
+          for (int q = 0; q < qsteps; ++q) {
             if (bi == 0) {
-              mbar_wait(&b_full[bst], (uint32_t)(bs / P.SB) & 1u);
+              mbar_wait(&b_full[bst], bph);
               tc_fence_after();
             }
-            const uint64_t adesc = make_desc_nosw(a_st + (uint32_t)(2 * q) * a_lbo + (uint32_t)job.a_off * 16u, a_lbo, 128u);
-            const uint64_t bdesc = make_desc_nosw(b_base + (uint32_t)bst * b_stage_bytes + (uint32_t)bi * b_block_bytes, b_lbo, 128u);
-            const uint32_t accumulate = (c == 0 && q == 0 && job.first) ? 0u : 1u;
-            umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
-            if (bi == P.bpb - 1) umma_commit(&b_empty[bst]);
+            const uint64_t adesc = ((uint64_t)desc_hi << 32) | a_lo;
+            const uint64_t bdesc = ((uint64_t)desc_hi << 32) | b_lo;
+            if (elect_one()) umma_bf16(d_tmem, adesc, bdesc, idesc, overwrite ^ 1u);
+            __syncwarp();
+            overwrite = 0;
+            a_lo += a_qstep_u;
+            b_lo += b_block_u;
+            if (++bi == bpb) {
+              if (elect_one()) umma_commit(&b_empty[bst]);
+              __syncwarp();
+              bi = 0;
+              if (++bst == SB) { bst = 0; bph ^= 1u; b_lo = b_lo0; }
+            }
           }
         }
-        umma_commit(&a_empty[st]);
+        if (elect_one()) umma_commit(&a_empty[ast]);
+        __syncwarp();
+        if (++ast == SA) { ast = 0; aph ^= 1u; }
       }
-      umma_commit(acc_full);
+      if (elect_one()) umma_commit(acc_full);
     }
     __syncwarp();
   } else if (warp >= 4) {
