@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -173,7 +173,7 @@ def workload_config(clips):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--clips", type=int, default=4, help="independent clips advanced in lock-step per GPU")
     ap.add_argument("--impl", type=str, default="b200")
@@ -295,7 +295,7 @@ def main():
     if rank == 0:
         out = {"metric": "frames/sec rendered @512x512", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
                "warmup": Wm, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "bf16", "data": "synthetic poses, random-init weights (no checkpoint offline)",
+               "dtype": capi.operand_dtype() + " operands, f32 accumulate", "data": "synthetic poses, random-init weights (no checkpoint offline)",
                "config": workload_config(B), "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "frames_checksum": checksum},

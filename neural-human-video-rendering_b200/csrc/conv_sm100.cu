@@ -12,8 +12,8 @@
 // LBO = plane stride).  No im2col expansion, no padding logic, no per-tap reload.
 // Weights are pre-packed in consumption order and streamed through a second ring.
 //
-// Roles (256 threads): warp0 = slab producer, warp1 = weight producer, warp2 = MMA issuer (one
-// thread), warp3 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> global, InstanceNorm
+// Roles (384 threads): warp0 = slab producer, warp1 = weight producer, warp2 = MMA issuer (one
+// thread), warp3 = TMEM allocator, warps 4-11 = epilogue (TMEM -> registers -> global, InstanceNorm
 // statistics by warp-shuffle column reduction, or bias + activation).
 #include "common.cuh"
 #include "p8.cuh"
@@ -31,6 +31,7 @@ extern int arch_ok_cached();
 extern int operand_f16();
 
 constexpr int kMaxJobs = 52;
+constexpr int kMaxMma = 208;   // jobs x k-steps per chunk
 constexpr int kMaxRuns = 8;
 constexpr int kTileM = 128;
 
@@ -38,6 +39,11 @@ struct ConvJob {
   int32_t a_off;   // shift (16-B units) inside a plane slab
   int16_t acc;     // accumulator index
   int16_t first;   // first job of its accumulator (overwrites instead of accumulating)
+};
+struct ConvMma {     // one tcgen05.mma of a chunk: precomputed so the issue loop has no arithmetic chains
+  int32_t a_off;     // (job shift + k-step plane offset) in 16-B units inside the chunk slab
+  uint16_t acc_col;  // accumulator column offset in TMEM
+  uint16_t first;    // overwrites its accumulator when executed in the first chunk
 };
 struct ConvRun {
   int32_t g_off;   // offset (units) from the plane base + q0
@@ -62,9 +68,11 @@ struct ConvKParams {
   int32_t epilogue, act;
   int32_t tmem_cols;
   int32_t f16;             // operand element type: 0 bf16, 1 fp16
+  int32_t debug;           // NHVR_CONV_DEBUG experiments (results are wrong when set): 1 no MMA, 2 unshifted A, 4 double issue
   ActGeom og;              // BIAS_ACT_P8 destination
+  int32_t mmas_per_chunk, stages_per_chunk;
   ConvRun runs[kMaxRuns];
-  ConvJob jobs[kMaxJobs];
+  ConvMma mma[kMaxMma];
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -110,11 +118,16 @@ NHVR_DEVINL float apply_act(float x, int act, bool is_last) {
   }
 }
 
-__global__ void __launch_bounds__(256, 1) conv_shiftgemm_kernel(const __grid_constant__ ConvKParams P) {
+constexpr int kThreads = 384;       // warps 0-3: roles, warps 4-11: epilogue
+
+__global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __grid_constant__ ConvKParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.y, split = blockIdx.z;
   const int64_t q0 = (int64_t)blockIdx.x * kTileM;
+  // K-chunk order is rotated per CTA: neighbouring CTAs stream different parts of the (shared) packed
+  // weights at any instant instead of all hitting the same L2 lines in lock-step.
+  const int rot = (int)(blockIdx.x % (unsigned)P.nchunks);
 
   const uint32_t a_stage_bytes = (uint32_t)P.kcp * P.slab_units * 16u;
   const uint32_t b_block_bytes = (uint32_t)P.Npad * 32u;
@@ -141,7 +154,7 @@ __global__ void __launch_bounds__(256, 1) conv_shiftgemm_kernel(const __grid_con
     tmem_relinquish();
   }
   if (warp >= 4) {
-    for (int i = threadIdx.x - 128; i < P.Npad * 2; i += 128) s_stats[i] = 0.f;
+    for (int i = threadIdx.x - 128; i < P.Npad * 2; i += 256) s_stats[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -154,13 +167,14 @@ __global__ void __launch_bounds__(256, 1) conv_shiftgemm_kernel(const __grid_con
       const uint4* img = P.in + (int64_t)n * P.C8in * P.in_plane_units + q0;
       int st = 0;
       uint32_t ph = 0;
+      int cc = rot;                                   // chunk order rotated per CTA (see kernel header)
       for (int c = 0; c < P.nchunks; ++c, st = (st + 1 == P.SA) ? 0 : st + 1, ph ^= (st == 0) ? 1u : 0u) {
         mbar_wait(&a_empty[st], ph ^ 1u);
         if (elect_one()) {
           mbar_arrive_expect_tx(&a_full[st], a_stage_bytes);
           uint8_t* dst = a_smem + (size_t)st * a_stage_bytes;
           for (int pl = 0; pl < P.kcp; ++pl) {
-            const uint4* plane = img + (int64_t)(c * P.kcp + pl) * P.in_plane_units;
+            const uint4* plane = img + (int64_t)(cc * P.kcp + pl) * P.in_plane_units;
             for (int r = 0; r < P.nruns; ++r) {
               bulk_g2s(dst + ((size_t)pl * P.slab_units + P.runs[r].s_off) * 16, plane + P.runs[r].g_off,
                        (uint32_t)P.runs[r].len * 16u, &a_full[st]);
@@ -168,14 +182,17 @@ __global__ void __launch_bounds__(256, 1) conv_shiftgemm_kernel(const __grid_con
           }
         }
         __syncwarp();
+        if (++cc == P.nchunks) cc = 0;
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ weight producer
     {
-      const uint4* wsrc = P.w + (int64_t)split * P.w_split_units;
+      const uint4* wbase = P.w + (int64_t)split * P.w_split_units;
       const uint32_t stage_units = b_stage_bytes >> 4;
+      int gs = rot * P.stages_per_chunk;              // global stage index, rotated start
+      const uint4* wsrc = wbase + (int64_t)gs * stage_units;
       int st = 0;
       uint32_t ph = 0;
       for (int s = 0; s < P.nbstages; ++s) {
@@ -186,6 +203,7 @@ __global__ void __launch_bounds__(256, 1) conv_shiftgemm_kernel(const __grid_con
         }
         __syncwarp();
         wsrc += stage_units;
+        if (++gs == P.nbstages) { gs = 0; wsrc = wbase; }
         if (++st == P.SB) { st = 0; ph ^= 1u; }
       }
     }
@@ -202,52 +220,48 @@ __global__ void __launch_bounds__(256, 1) conv_shiftgemm_kernel(const __grid_con
       const uint32_t a_lo0 = ((smem_u32(a_smem) & 0x3FFFFu) >> 4) | (a_lbo_u << 16);
       const uint32_t b_lo0 = ((smem_u32(b_smem) & 0x3FFFFu) >> 4) | (b_lbo_u << 16);
       const uint32_t a_stage_u = a_stage_bytes >> 4, b_block_u = b_block_bytes >> 4;
-      const uint32_t a_qstep_u = 2u * a_lbo_u;
-      const int qsteps = P.kcp >> 1, njobs = P.njobs, bpb = P.bpb, SA = P.SA, SB = P.SB;
-      const uint32_t npad = (uint32_t)P.Npad;
+      const int nmma = P.mmas_per_chunk, bpb = P.bpb, SA = P.SA, SB = P.SB, nchunks = P.nchunks;
+      const int dbg = P.debug;
       int ast = 0, bst = 0, bi = 0;
       uint32_t aph = 0, bph = 0;
       uint32_t b_lo = b_lo0;
-      for (int c = 0; c < P.nchunks; ++c) {
+      const bool leader = elect_one();
+      for (int c = 0; c < nchunks; ++c) {
         mbar_wait(&a_full[ast], aph);
         tc_fence_after();
         const uint32_t a_st_lo = a_lo0 + (uint32_t)ast * a_stage_u;
         const uint32_t first_mask = (c == 0) ? 1u : 0u;
-        for (int j = 0; j < njobs; ++j) {
-          const ConvJob job = P.jobs[j];
-          const uint32_t d_tmem = tmem_base + (uint32_t)job.acc * npad;
-          uint32_t a_lo = a_st_lo + (uint32_t)job.a_off;
-          uint32_t overwrite = first_mask & (uint32_t)job.first;
-          for (int q = 0; q < qsteps; ++q) {
-            if (bi == 0) {
-              mbar_wait(&b_full[bst], bph);
-              tc_fence_after();
-            }
-            const uint64_t adesc = ((uint64_t)desc_hi << 32) | a_lo;
-            const uint64_t bdesc = ((uint64_t)desc_hi << 32) | b_lo;
-            if (elect_one()) umma_bf16(d_tmem, adesc, bdesc, idesc, overwrite ^ 1u);
-            __syncwarp();
-            overwrite = 0;
-            a_lo += a_qstep_u;
-            b_lo += b_block_u;
-            if (++bi == bpb) {
-              if (elect_one()) umma_commit(&b_empty[bst]);
-              __syncwarp();
-              bi = 0;
-              if (++bst == SB) { bst = 0; bph ^= 1u; b_lo = b_lo0; }
-            }
+#pragma unroll 2
+        for (int i = 0; i < nmma; ++i) {
+          const ConvMma e = P.mma[i];
+          if (bi == 0) {
+            mbar_wait(&b_full[bst], bph);
+            tc_fence_after();
+          }
+          const uint64_t adesc = ((uint64_t)desc_hi << 32) | (a_st_lo + ((dbg & 2) ? 0u : (uint32_t)e.a_off));
+          const uint64_t bdesc = ((uint64_t)desc_hi << 32) | b_lo;
+          if (leader) {
+            if (!(dbg & 1)) umma_bf16(tmem_base + e.acc_col, adesc, bdesc, idesc, (first_mask & e.first) ^ 1u);
+            if (dbg & 4) umma_bf16(tmem_base + e.acc_col, adesc, bdesc, idesc, 1u);
+          }
+          b_lo += b_block_u;
+          if (++bi == bpb) {
+            if (leader) umma_commit(&b_empty[bst]);
+            bi = 0;
+            if (++bst == SB) { bst = 0; bph ^= 1u; b_lo = b_lo0; }
           }
         }
-        if (elect_one()) umma_commit(&a_empty[ast]);
-        __syncwarp();
+        if (leader) umma_commit(&a_empty[ast]);
         if (++ast == SA) { ast = 0; aph ^= 1u; }
       }
+      __syncwarp();
       if (elect_one()) umma_commit(acc_full);
     }
     __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int we = warp - 4;                  // TMEM lane quarter == warp % 4
+    const int we = warp & 3;                  // TMEM lane quarter == warp % 4
+    const int half = (warp - 4) >> 2;         // warps 4-7 take the even column groups, 8-11 the odd ones
     const int m = we * 32 + lane;
     const int64_t q = q0 + m;
     const int y = (int)(q / P.Wrow);
@@ -260,10 +274,10 @@ __global__ void __launch_bounds__(256, 1) conv_shiftgemm_kernel(const __grid_con
     mbar_wait(acc_full, 0);
     tc_fence_after();
 
-    for (int a = 0; a < P.nacc; ++a) {
+    for (int a = 0; a < ((P.debug & 8) ? 0 : P.nacc); ++a) {
       const int Y = y * P.oys + P.oy[a];
       const int X = x * P.oxs + P.ox[a];
-      for (int g = 0; g < ngroups; ++g) {
+      for (int g = half; g < ngroups; g += 2) {
         uint32_t vr[16];
         tmem_ld16(t_lane + (uint32_t)(a * P.Npad + g * 16), vr);
         tmem_ld_wait();
@@ -285,6 +299,7 @@ __global__ void __launch_bounds__(256, 1) conv_shiftgemm_kernel(const __grid_con
             if ((c0 >> 3) < P.Cout8) o[u0] = lo;
             if ((c0 >> 3) + 1 < P.Cout8) o[u0 + pstride] = hi;
           }
+          if (!(P.debug & 16)) {
           float s[16], ss[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) { s[i] = valid ? v[i] : 0.f; ss[i] = s[i] * s[i]; }
@@ -292,6 +307,7 @@ __global__ void __launch_bounds__(256, 1) conv_shiftgemm_kernel(const __grid_con
           const float css = warp_colsum16(ss, lane);
           const int col = g * 16 + (lane >> 1);
           atomicAdd(&s_stats[col * 2 + (lane & 1)], (lane & 1) ? css : cs);
+          }
         } else if (P.epilogue == NHVR_EPI_BIAS_ACT_F32) {
           if (valid) {
             float* o = reinterpret_cast<float*>(P.out);
@@ -328,10 +344,10 @@ __global__ void __launch_bounds__(256, 1) conv_shiftgemm_kernel(const __grid_con
       }
     }
     if (P.epilogue == NHVR_EPI_RAW_STATS) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       float* gs = P.stats + ((int64_t)n * P.Cout8 * 8 + cout_off) * 2;
       const int lim = min(P.Npad, P.Cout8 * 8 - cout_off) * 2;
-      for (int i = threadIdx.x - 128; i < lim; i += 128) atomicAdd(gs + i, s_stats[i]);
+      for (int i = threadIdx.x - 128; i < lim; i += 256) atomicAdd(gs + i, s_stats[i]);
     }
   }
 
@@ -514,11 +530,12 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   // ---- jobs (grouped by accumulator so that "first" is well defined)
   std::stable_sort(taps.begin(), taps.end(), [](const Tap& a, const Tap& b) { return a.acc < b.acc; });
   K.njobs = (int)taps.size();
+  std::vector<ConvJob> jobs(K.njobs);
   int prev_acc = -1;
   for (int j = 0; j < K.njobs; ++j) {
-    K.jobs[j].a_off = key_soff[taps[j].run_key] + taps[j].shift;
-    K.jobs[j].acc = (int16_t)taps[j].acc;
-    K.jobs[j].first = (taps[j].acc != prev_acc) ? 1 : 0;
+    jobs[j].a_off = key_soff[taps[j].run_key] + taps[j].shift;
+    jobs[j].acc = (int16_t)taps[j].acc;
+    jobs[j].first = (taps[j].acc != prev_acc) ? 1 : 0;
     prev_acc = taps[j].acc;
     p->pp.job_tap[j] = (int16_t)taps[j].tap;
   }
@@ -543,29 +560,33 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   // ---- shared-memory budget: prefer two co-resident CTAs per SM (<= ~100 KB, <= 256 TMEM columns)
   const int b_block = Npad * 32;
   auto try_fit = [&](int budget, int& kcp, int& SA, int& bpb, int& SB) -> bool {
+    long best_score = -1;
     for (int cand = 8; cand >= 2; cand -= 2) {
       if (C8 % cand) continue;
       const int nch = C8 / cand;
       const int sa = std::min(2, nch);
       const long a_bytes = (long)sa * cand * slab * 16;
-      int bb = std::max(1, std::min(16384 / b_block, 8));
+      const int bpc = (int)taps.size() * cand / 2;          // MMA blocks per chunk
+      if (bpc > kMaxMma) continue;
       const long rem = budget - a_bytes - 1024 - (long)Npad * 8;
-      if (rem < 2L * bb * b_block) {
-        bb = 1;
-        if (rem < 2L * b_block) continue;
+      for (int dv = 8; dv >= 1; --dv) {                      // blocks per B stage: a divisor of bpc, stage <= 16 KB
+        if (bpc % dv || (long)dv * b_block > 16384) continue;
+        const int sb = (int)std::min<long>(6, rem / ((long)dv * b_block));
+        if (sb < 2) continue;
+        // score: weight bytes in flight, mild preference for >= 3 stages and for fewer, larger chunks
+        const long score = (long)std::min(sb, 4) * dv * b_block + (sb >= 3 ? 4096 : 0) + cand * 64;
+        if (score > best_score) { best_score = score; kcp = cand; SA = sa; bpb = dv; SB = sb; }
+        break;
       }
-      int sb = (int)std::min<long>(4, rem / ((long)bb * b_block));
-      if (sb < 2) continue;
-      kcp = cand; SA = sa; bpb = bb; SB = sb;
-      return true;
     }
-    return false;
+    return best_score >= 0;
   };
   int kcp = 0, SA = 0, bpb = 0, SB = 0;
   bool ok = false;
   if (const char* tune = std::getenv("NHVR_CONV_TUNE")) {   // experiments: "kcp,SA,bpb,SB"
     int a, b, c, e;
-    if (std::sscanf(tune, "%d,%d,%d,%d", &a, &b, &c, &e) == 4 && a >= 2 && (a % 2) == 0 && C8 % a == 0 && b >= 1 && c >= 1 && e >= 2) {
+    if (std::sscanf(tune, "%d,%d,%d,%d", &a, &b, &c, &e) == 4 && a >= 2 && (a % 2) == 0 && C8 % a == 0 && b >= 1 && c >= 1 && e >= 2 &&
+        ((int)taps.size() * a / 2) % c == 0 && (int)taps.size() * a / 2 <= kMaxMma) {
       const long need = (long)std::min(b, C8 / a) * a * slab * 16 + (long)e * c * b_block + 2048 + (long)Npad * 8;
       if (need <= 227 * 1024) { kcp = a; SA = std::min(b, C8 / a); bpb = c; SB = e; ok = true; }
     }
@@ -575,9 +596,18 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   if (!ok) { delete p; return NHVR_ERR_SMEM; }
   K.kcp = kcp; K.SA = SA; K.bpb = bpb; K.SB = SB;
   K.nchunks = C8 / kcp;
-  K.nblocks = K.nchunks * K.njobs * (kcp / 2);
-  K.nbstages = (K.nblocks + bpb - 1) / bpb;
-  const int nblocks_padded = K.nbstages * bpb;
+  K.mmas_per_chunk = K.njobs * (kcp / 2);
+  K.stages_per_chunk = K.mmas_per_chunk / bpb;           // bpb divides mmas_per_chunk by construction
+  K.nblocks = K.nchunks * K.mmas_per_chunk;
+  K.nbstages = K.nchunks * K.stages_per_chunk;
+  const int nblocks_padded = K.nblocks;
+  for (int j = 0; j < K.njobs; ++j)
+    for (int q = 0; q < kcp / 2; ++q) {
+      ConvMma& m = K.mma[j * (kcp / 2) + q];
+      m.a_off = jobs[j].a_off + 2 * q * slab;
+      m.acc_col = (uint16_t)(jobs[j].acc * Npad);
+      m.first = (uint16_t)((jobs[j].first && q == 0) ? 1 : 0);
+    }
   K.w_split_units = (int64_t)nblocks_padded * 2 * Npad;
   p->weight_bytes = (size_t)nsplit * K.w_split_units * 16;
   p->smem_bytes = (size_t)SA * kcp * slab * 16 + (size_t)SB * bpb * b_block + (size_t)(2 * SA + 2 * SB + 1) * 8 + 8 +
@@ -658,6 +688,7 @@ extern "C" int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const 
     if (K.og.H != p->Ho || K.og.W != p->Wo || K.og.N != p->d.N) return NHVR_ERR_SHAPE;
   }
   K.f16 = operand_f16();
+  { const char* dbg = std::getenv("NHVR_CONV_DEBUG"); K.debug = dbg ? std::atoi(dbg) : 0; }
   K.in = reinterpret_cast<const uint4*>(in);
   K.w = reinterpret_cast<const uint4*>(packed_w);
   K.bias = bias;
@@ -670,7 +701,7 @@ extern "C" int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const 
     attr_set = true;
   }
   dim3 grid(p->tiles_per_img, p->d.N, p->nsplit);
-  conv_shiftgemm_kernel<<<grid, 256, p->smem_bytes, (cudaStream_t)stream>>>(K);
+  conv_shiftgemm_kernel<<<grid, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(K);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }

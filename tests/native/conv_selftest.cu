@@ -207,7 +207,10 @@ int main(int argc, char** argv) {
         {"PERF c3s2 48->96 512^2 b1", NHVR_CONV, 48, 96, 3, 2, 1, 1, 512, 512, Z, NHVR_EPI_RAW_STATS, 0},
         {"PERF ct 96->48 256^2 b1", NHVR_CONV_TRANSPOSE, 96, 48, 3, 2, 1, 1, 256, 256, Z, NHVR_EPI_RAW_STATS, 0},
     };
+    int pidx = -1;
     for (auto& c : perf) {
+      ++pidx;
+      if (only > 100 && pidx != only - 101) continue;   // 101 + i selects perf case i only
       // run without CPU reference: reuse run_case machinery would be too slow; time only
       nhvr_conv_desc d{}; d.kind = c.kind; d.Cin = c.Cin; d.Cout = c.Cout; d.kh = d.kw = c.k; d.stride = c.stride; d.pad = c.pad;
       d.N = c.N; d.H = c.H; d.W = c.W; d.halo = c.halo; d.epilogue = c.epi; d.act = c.act;
@@ -221,7 +224,7 @@ int main(int argc, char** argv) {
       const size_t ob = (size_t)c.N * Cout8 * 8 * Ho * Wo * 4 + (1 << 20);
       CK(cudaMalloc(&d_out, ob)); CK(cudaMalloc(&d_stats, (size_t)c.N * Cout8 * 16 * 4)); CK(cudaMemset(d_stats, 0, (size_t)c.N * Cout8 * 16 * 4));
       cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-      const int iters = 20;
+      const int iters = (only > 100) ? 3 : 20;
       for (int it = 0; it < iters + 3; ++it) {
         if (it == 3) CK(cudaEventRecord(e0, 0));
         int s = nhvr_conv_forward(plan, d_p8, d_wp, nullptr, d_out, nullptr, d_stats, 0);
