@@ -143,6 +143,25 @@ int nhvr_texture_sample(const float* uvp, const float* atlas, int32_t N, int32_t
 int nhvr_composite(const float* fgm, const float* bg, int32_t bg_batched, int32_t N, int32_t H, int32_t W,
                    float* out, void* stream);
 
+/* ---- training-side reductions (fp32 in, fp64 accumulate) ----
+ * Each call ADDS partial sums into a caller-zeroed double accumulator; the host divides by the element
+ * count to get the mean the reference's torch losses return (pretrain_start.sh:31-37 --lambda_L2 /
+ * --lambda_UV / --lambda_Prob / --lambda_Temp; pix2pixHD GANLoss(use_lsgan) and feature matching). */
+int nhvr_loss_sum_sq_diff(const float* a, const float* b, int64_t n, double* acc, void* stream);   /* L2 / MSE  */
+int nhvr_loss_sum_abs_diff(const float* a, const float* b, int64_t n, double* acc, void* stream);  /* L1        */
+int nhvr_loss_sum_sq_const(const float* a, float target, int64_t n, double* acc, void* stream);    /* LSGAN     */
+/* uvp float [N][73][H][W]; dp_i int32 [N][H][W] (DensePose part, 0 = background); dp_uv float [N][2][H][W].
+ * acc3[0] += sum over foreground of |u_k-U| + |v_k-V| (k = ground-truth part, u = clamp(.5*U+.5,0,1));
+ * acc3[1] += foreground pixel count; acc3[2] += sum of 25-way cross-entropy of the part logits. */
+int nhvr_loss_uv_prob(const float* uvp, const int32_t* dp_i, const float* dp_uv, int32_t N, int32_t H, int32_t W,
+                      double* acc3, void* stream);
+/* acc += sum |cur - warp(prev, flow)|, flow float [N][2][H][W] in pixels (dx, dy), bilinear, border clamp. */
+int nhvr_loss_temporal(const float* cur, const float* prev, const float* flow, int32_t N, int32_t C, int32_t H,
+                       int32_t W, double* acc, void* stream);
+/* AvgPool2d(3, stride 2, padding 1, count_include_pad=False) between discriminator scales (pix2pixHD
+ * MultiscaleDiscriminator.downsample): in float [N][C][H][W] -> out float [N][C][(H+1)/2][(W+1)/2]. */
+int nhvr_avgpool3s2(const float* in, int32_t N, int32_t C, int32_t H, int32_t W, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

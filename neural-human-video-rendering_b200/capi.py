@@ -64,6 +64,12 @@ SYMBOLS = {
     "nhvr_texture_sample": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P,
                                       _P, _P]),
     "nhvr_composite": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "nhvr_loss_sum_sq_diff": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    "nhvr_loss_sum_abs_diff": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    "nhvr_loss_sum_sq_const": (C.c_int, [_P, C.c_float, C.c_int64, _P, _P]),
+    "nhvr_loss_uv_prob": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "nhvr_loss_temporal": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "nhvr_avgpool3s2": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
 }
 
 # fp16 operands are the default: measured on B200 at 512^2 against the fp32 oracle the temporal generator is

@@ -1,0 +1,202 @@
+// Training-side reductions (fp32 inputs, fp64 accumulation: the 1e-3 relative bound on losses is met with
+// orders of magnitude to spare) and the discriminator's inter-scale AvgPool2d(3, s2, p1,
+// count_include_pad=False).  All are streaming, coalesced, one pass over their inputs.
+//
+// Every loss kernel ADDS partial sums into a caller-zeroed double accumulator array; the host divides
+// by the element count (the reference's torch losses are means; evidence for the terms:
+// train_start/pretrain_start.sh:31-37 --lambda_L2/--lambda_UV/--lambda_Prob/--lambda_Temp,
+// pix2pixHD GANLoss / feature matching).
+#include "common.cuh"
+#include "p8.cuh"
+#include <algorithm>
+
+namespace nhvr {
+
+extern void note_cuda_error(cudaError_t e);
+extern void count_launch();
+extern int arch_ok_cached();
+
+NHVR_DEVINL double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-reduce K partial sums (one double each per thread) and add them to acc[0..K)
+template <int K>
+NHVR_DEVINL void block_accumulate(const double (&v)[K], double* acc) {
+  __shared__ double sh[K][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double w = warp_sum(v[k]);
+    if (lane == 0) sh[k][warp] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[threadIdx.x][w];
+    atomicAdd(acc + threadIdx.x, t);
+  }
+}
+
+// mode 0: sum (a-b)^2   mode 1: sum |a-b|   mode 2: sum (a-c)^2 (b unused, c = target constant)
+__global__ void __launch_bounds__(256) loss_pair_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                                                        int mode, float c, double* acc) {
+  double s[1] = {0.0};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float part = 0.f;
+  int cnt = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float x = __ldg(a + i);
+    const float d = x - (mode == 2 ? c : __ldg(b + i));
+    part += (mode == 1) ? fabsf(d) : d * d;
+    if (++cnt == 64) { s[0] += part; part = 0.f; cnt = 0; }   // bounded fp32 run, fp64 carry
+  }
+  s[0] += part;
+  block_accumulate<1>(s, acc);
+}
+
+// uvp [N,73,H,W]; dp_i int32 [N,H,W] in 0..24; dp_uv [N,2,H,W]
+// acc[0] += sum_fg |u_k - U| + |v_k - V| (k = ground-truth part)   acc[1] += #fg   acc[2] += sum CE
+__global__ void __launch_bounds__(256) loss_uv_prob_kernel(const float* __restrict__ uvp, const int32_t* __restrict__ dp_i,
+                                                           const float* __restrict__ dp_uv, int N, int64_t HW, double* acc) {
+  double s[3] = {0.0, 0.0, 0.0};
+  const int64_t total = (int64_t)N * HW;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / HW);
+    const int64_t pix = idx - (int64_t)n * HW;
+    const float* base = uvp + (int64_t)n * 73 * HW + pix;
+    const int part = dp_i[idx];
+    float lg[25], mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) { lg[k] = __ldg(base + (int64_t)k * HW); mx = fmaxf(mx, lg[k]); }
+    float den = 0.f, tgt = 0.f;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) { den += expf(lg[k] - mx); if (k == part) tgt = lg[k]; }
+    s[2] += (double)(logf(den) + mx - tgt);
+    if (part > 0) {
+      const float u = fminf(fmaxf(__ldg(base + (int64_t)(24 + part) * HW) * 0.5f + 0.5f, 0.f), 1.f);
+      const float v = fminf(fmaxf(__ldg(base + (int64_t)(48 + part) * HW) * 0.5f + 0.5f, 0.f), 1.f);
+      const float U = __ldg(dp_uv + (int64_t)n * 2 * HW + pix), V = __ldg(dp_uv + ((int64_t)n * 2 + 1) * HW + pix);
+      s[0] += (double)(fabsf(u - U) + fabsf(v - V));
+      s[1] += 1.0;
+    }
+  }
+  block_accumulate<3>(s, acc);
+}
+
+// acc[0] += sum |cur - warp(prev, flow)| over [N,C,H,W]; warp = bilinear sample of prev at (x+fx, y+fy),
+// border-clamped (grid_sample(padding_mode='border', align_corners=True) in pixel units)
+__global__ void __launch_bounds__(256) loss_temporal_kernel(const float* __restrict__ cur, const float* __restrict__ prev,
+                                                            const float* __restrict__ flow, int N, int C, int H, int W, double* acc) {
+  double s[1] = {0.0};
+  const int64_t HW = (int64_t)H * W;
+  const int64_t total = (int64_t)N * HW;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / HW);
+    const int64_t pix = idx - (int64_t)n * HW;
+    const int y = (int)(pix / W), x = (int)(pix - (int64_t)y * W);
+    float sx = (float)x + __ldg(flow + (int64_t)n * 2 * HW + pix);
+    float sy = (float)y + __ldg(flow + ((int64_t)n * 2 + 1) * HW + pix);
+    sx = fminf(fmaxf(sx, 0.f), (float)(W - 1));
+    sy = fminf(fmaxf(sy, 0.f), (float)(H - 1));
+    const float x0f = floorf(sx), y0f = floorf(sy);
+    const int x0 = (int)x0f, y0 = (int)y0f, x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+    const float wx = sx - x0f, wy = sy - y0f;
+    for (int c = 0; c < C; ++c) {
+      const float* p = prev + ((int64_t)n * C + c) * HW;
+      const float w = (1.f - wy) * ((1.f - wx) * __ldg(p + (int64_t)y0 * W + x0) + wx * __ldg(p + (int64_t)y0 * W + x1)) +
+                      wy * ((1.f - wx) * __ldg(p + (int64_t)y1 * W + x0) + wx * __ldg(p + (int64_t)y1 * W + x1));
+      s[0] += (double)fabsf(__ldg(cur + ((int64_t)n * C + c) * HW + pix) - w);
+    }
+  }
+  block_accumulate<1>(s, acc);
+}
+
+// AvgPool2d(kernel 3, stride 2, padding 1, count_include_pad=False) on NCHW fp32
+__global__ void __launch_bounds__(256) avgpool3s2_kernel(const float* __restrict__ in, int64_t planes, int H, int W, int Ho, int Wo,
+                                                         float* __restrict__ out) {
+  const int64_t total = planes * Ho * Wo;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int xo = (int)(idx % Wo);
+    const int yo = (int)((idx / Wo) % Ho);
+    const int64_t pl = idx / ((int64_t)Wo * Ho);
+    const float* p = in + pl * H * W;
+    float s = 0.f;
+    int cnt = 0;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int y = 2 * yo + dy;
+      if (y < 0 || y >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int x = 2 * xo + dx;
+        if (x < 0 || x >= W) continue;
+        s += __ldg(p + (int64_t)y * W + x);
+        ++cnt;
+      }
+    }
+    out[idx] = s / (float)cnt;
+  }
+}
+
+static inline int blocks_for(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 8)); }
+
+}  // namespace nhvr
+
+using namespace nhvr;
+
+#define NHVR_POST_LAUNCH()                                         \
+  count_launch();                                                  \
+  {                                                                \
+    cudaError_t e_ = cudaGetLastError();                           \
+    if (e_ != cudaSuccess) { note_cuda_error(e_); return NHVR_ERR_CUDA; } \
+  }                                                                \
+  return NHVR_OK
+
+extern "C" int nhvr_loss_sum_sq_diff(const float* a, const float* b, int64_t n, double* acc, void* stream) {
+  if (!a || !b || !acc) return NHVR_ERR_NULL;
+  if (n <= 0) return NHVR_ERR_SHAPE;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  loss_pair_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(a, b, n, 0, 0.f, acc);
+  NHVR_POST_LAUNCH();
+}
+extern "C" int nhvr_loss_sum_abs_diff(const float* a, const float* b, int64_t n, double* acc, void* stream) {
+  if (!a || !b || !acc) return NHVR_ERR_NULL;
+  if (n <= 0) return NHVR_ERR_SHAPE;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  loss_pair_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(a, b, n, 1, 0.f, acc);
+  NHVR_POST_LAUNCH();
+}
+extern "C" int nhvr_loss_sum_sq_const(const float* a, float target, int64_t n, double* acc, void* stream) {
+  if (!a || !acc) return NHVR_ERR_NULL;
+  if (n <= 0) return NHVR_ERR_SHAPE;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  loss_pair_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(a, nullptr, n, 2, target, acc);
+  NHVR_POST_LAUNCH();
+}
+extern "C" int nhvr_loss_uv_prob(const float* uvp, const int32_t* dp_i, const float* dp_uv, int32_t N, int32_t H, int32_t W,
+                                 double* acc3, void* stream) {
+  if (!uvp || !dp_i || !dp_uv || !acc3) return NHVR_ERR_NULL;
+  if (N <= 0 || H <= 0 || W <= 0) return NHVR_ERR_SHAPE;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  loss_uv_prob_kernel<<<blocks_for((int64_t)N * H * W), 256, 0, (cudaStream_t)stream>>>(uvp, dp_i, dp_uv, N, (int64_t)H * W, acc3);
+  NHVR_POST_LAUNCH();
+}
+extern "C" int nhvr_loss_temporal(const float* cur, const float* prev, const float* flow, int32_t N, int32_t C, int32_t H,
+                                  int32_t W, double* acc, void* stream) {
+  if (!cur || !prev || !flow || !acc) return NHVR_ERR_NULL;
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return NHVR_ERR_SHAPE;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  loss_temporal_kernel<<<blocks_for((int64_t)N * H * W), 256, 0, (cudaStream_t)stream>>>(cur, prev, flow, N, C, H, W, acc);
+  NHVR_POST_LAUNCH();
+}
+extern "C" int nhvr_avgpool3s2(const float* in, int32_t N, int32_t C, int32_t H, int32_t W, float* out, void* stream) {
+  if (!in || !out) return NHVR_ERR_NULL;
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return NHVR_ERR_SHAPE;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  avgpool3s2_kernel<<<blocks_for((int64_t)N * C * Ho * Wo), 256, 0, (cudaStream_t)stream>>>(in, (int64_t)N * C, H, W, Ho, Wo, out);
+  NHVR_POST_LAUNCH();
+}

@@ -1,0 +1,82 @@
+"""Training losses of the reference on the sm_100a reduction kernels (forward values; fp32 in, fp64 accumulate).
+
+Terms and weights are the reference's flags [REF train_start/pretrain_start.sh:31-37: --lambda_L2 500,
+--lambda_UV 1000, --lambda_Prob 10, --use_densepose_loss, --lambda_Temp 500] plus pix2pixHD's LSGAN and
+feature-matching terms [SURVEY Appendix C].  Same formulas as oracle/losses.py (SPEC D11, D13); parity bound
+1e-3 relative (BASELINE.json north_star).  Each function returns a 0-dim float64 CUDA tensor.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+
+from .capi import check, load, stream_ptr
+
+
+def _acc(dev, n=1):
+    return torch.zeros(n, dtype=torch.float64, device=dev)
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    assert t.is_cuda, "nhvr_b200 losses take CUDA tensors only (no CPU fallback)"
+    return t.detach().contiguous().float()
+
+
+def mse(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    a, b = _f32(a), _f32(b)
+    assert a.shape == b.shape
+    acc = _acc(a.device)
+    check(load().nhvr_loss_sum_sq_diff(a.data_ptr(), b.data_ptr(), a.numel(), acc.data_ptr(), stream_ptr()), "nhvr_loss_sum_sq_diff")
+    return acc[0] / a.numel()
+
+
+def l1(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    a, b = _f32(a), _f32(b)
+    assert a.shape == b.shape
+    acc = _acc(a.device)
+    check(load().nhvr_loss_sum_abs_diff(a.data_ptr(), b.data_ptr(), a.numel(), acc.data_ptr(), stream_ptr()), "nhvr_loss_sum_abs_diff")
+    return acc[0] / a.numel()
+
+
+def gan_loss(pred_scales: Sequence, target_is_real: bool) -> torch.Tensor:
+    """LSGAN: MSE vs 1/0 on the last map of each scale, summed over scales."""
+    total = None
+    for pred in pred_scales:
+        p = _f32(pred[-1] if isinstance(pred, (list, tuple)) else pred)
+        acc = _acc(p.device)
+        check(load().nhvr_loss_sum_sq_const(p.data_ptr(), 1.0 if target_is_real else 0.0, p.numel(), acc.data_ptr(), stream_ptr()),
+              "nhvr_loss_sum_sq_const")
+        term = acc[0] / p.numel()
+        total = term if total is None else total + term
+    return total
+
+
+def feature_matching_loss(pred_fake, pred_real, n_layers_D: int = 3, num_D: int = 2, lambda_feat: float = 10.0) -> torch.Tensor:
+    feat_w, d_w = 4.0 / (n_layers_D + 1), 1.0 / num_D
+    total = None
+    for i in range(num_D):
+        for j in range(len(pred_fake[i]) - 1):
+            term = l1(pred_fake[i][j], pred_real[i][j]) * (d_w * feat_w * lambda_feat)
+            total = term if total is None else total + term
+    return total
+
+
+def uv_prob_losses(uvp: torch.Tensor, dp_i: torch.Tensor, dp_uv: torch.Tensor):
+    """(uv_loss, prob_loss): masked L1 of the ground-truth part's (u,v) vs DensePose UV; 25-way part cross-entropy."""
+    uvp, dp_uv = _f32(uvp), _f32(dp_uv)
+    dp = dp_i.detach().contiguous().to(torch.int32)
+    N, _, H, W = uvp.shape
+    acc = _acc(uvp.device, 3)
+    check(load().nhvr_loss_uv_prob(uvp.data_ptr(), dp.data_ptr(), dp_uv.data_ptr(), N, H, W, acc.data_ptr(), stream_ptr()),
+          "nhvr_loss_uv_prob")
+    return acc[0] / torch.clamp(acc[1], min=1.0), acc[2] / (N * H * W)
+
+
+def temporal_loss(out_t: torch.Tensor, out_prev: torch.Tensor, flow_inv: torch.Tensor) -> torch.Tensor:
+    cur, prev, fl = _f32(out_t), _f32(out_prev), _f32(flow_inv)
+    N, C, H, W = cur.shape
+    acc = _acc(cur.device)
+    check(load().nhvr_loss_temporal(cur.data_ptr(), prev.data_ptr(), fl.data_ptr(), N, C, H, W, acc.data_ptr(), stream_ptr()),
+          "nhvr_loss_temporal")
+    return acc[0] / cur.numel()

@@ -81,9 +81,14 @@ class _ChainEngine:
         for i, L in enumerate(chain):
             last = i == len(chain) - 1
             p: _ConvParams = L["params"]
-            epi = capi.EPI_BIAS_ACT_F32 if last else capi.EPI_RAW_STATS
+            if last:
+                epi, act = capi.EPI_BIAS_ACT_F32, final_act
+            elif L.get("norm", True):
+                epi, act = capi.EPI_RAW_STATS, capi.ACT_NONE
+            else:
+                epi, act = capi.EPI_BIAS_ACT_P8, L["act"]        # conv + bias + activation, no norm (D layer 0)
             plan = ops.ConvPlan(capi.CONV_TRANSPOSE if p.transposed else capi.CONV, p.cin, p.cout, p.k, p.stride, p.pad,
-                                N, h, w, L["halo"], epi, final_act if last else capi.ACT_NONE)
+                                N, h, w, L["halo"], epi, act)
             self.plans.append(plan)
             h, w = plan.Ho, plan.Wo
         self.out = torch.empty(N, out_channels, h, w, dtype=torch.float32, device=device)
@@ -109,7 +114,7 @@ class _ChainEngine:
                 live = None                          # consumed by the apply that just wrote `chosen`
             if chain[i].get("res") == "save":
                 live = chosen
-            if i < len(self.plans) - 1:
+            if i < len(self.plans) - 1 and chain[i].get("norm", True):
                 rd = plan.raw_desc()
                 rkey = (rd.N, rd.C8, rd.H, rd.W)
                 if rkey not in self._raws:
@@ -118,7 +123,7 @@ class _ChainEngine:
             else:
                 self.raw_bufs.append(None)
         # InstanceNorm statistics: one zero-fill per forward
-        sizes = [N * pl.Cout8 * 8 * 2 for pl in self.plans[:-1]]
+        sizes = [N * pl.Cout8 * 8 * 2 if chain[i].get("norm", True) else 0 for i, pl in enumerate(self.plans[:-1])]
         self.stats_all = torch.zeros(max(1, sum(sizes)), dtype=torch.float32, device=device)
         self.stats: List[torch.Tensor] = []
         off = 0
@@ -142,6 +147,10 @@ class _ChainEngine:
         ops.pack_nchw(inputs, self.in_bufs[0])
         return self.run_packed()
 
+    def feature(self, i: int) -> torch.Tensor:
+        """Activation that feeds conv i (= output of layer i-1) as NCHW fp32 (D's intermediate features)."""
+        return ops.unpack_nchw(self.in_bufs[i], self.chain[i]["params"].cin)
+
     def run_packed(self) -> torch.Tensor:
         """Run the chain assuming in_bufs[0] already holds the packed input."""
         self.stats_all.zero_()
@@ -154,6 +163,10 @@ class _ChainEngine:
             if i == n - 1:
                 plan.forward(x, self.out.data_ptr(), bias=L["params"].bias)
                 break
+            if not L.get("norm", True):
+                nxt = self.in_bufs[i + 1]
+                plan.forward(x, nxt.ptr, bias=L["params"].bias, out_desc=nxt.desc)
+                continue
             raw = self.raw_bufs[i]
             plan.forward(x, raw.ptr, stats=self.stats[i])
             ops.in_apply(raw, self.stats[i], L["act"], self.in_bufs[i + 1],
@@ -252,6 +265,101 @@ def define_G(input_nc, output_nc, ngf, netG="global", n_downsample_global=3, n_b
     if final is None:
         raise NotImplementedError("generator [%s] not implemented" % netG)
     net = GlobalGeneratorB200(input_nc, output_nc, ngf, n_downsample_global, n_blocks_global, final=final)
+    if len(gpu_ids) > 0:
+        net.cuda(gpu_ids[0])
+    elif torch.cuda.is_available():
+        net.cuda()
+    return net
+
+
+# ----------------------------------------------------------------------------------------------
+# multiscale PatchGAN discriminator (training side)
+# ----------------------------------------------------------------------------------------------
+class MultiscaleDiscriminatorB200(nn.Module):
+    """pix2pixHD MultiscaleDiscriminator / NLayerDiscriminator (kw=4, padw=2) on the sm_100a kernels
+    [SURVEY §8 a8, Appendix C].  Parameter names equal upstream's: ``scale<i>_layer<j>.0.weight`` with
+    getIntermFeat, ``layer<i>.<idx>.weight`` without.  forward() returns the same nested lists."""
+
+    def __init__(self, input_nc, ndf=64, n_layers=3, use_sigmoid=False, num_D=3, getIntermFeat=False):
+        super().__init__()
+        if use_sigmoid:
+            raise NotImplementedError("use_sigmoid=True (the reference trains LSGAN: no sigmoid)")
+        self.input_nc, self.ndf, self.n_layers, self.num_D, self.getIntermFeat = input_nc, ndf, n_layers, num_D, getIntermFeat
+        for i in range(num_D):
+            seq = self._layers(input_nc, ndf, n_layers)
+            if getIntermFeat:
+                for j, grp in enumerate(seq):
+                    setattr(self, "scale%d_layer%d" % (i, j), nn.Sequential(*grp))
+            else:
+                setattr(self, "layer%d" % i, nn.Sequential(*[m for grp in seq for m in grp]))
+        self._engines: Dict[tuple, List[_ChainEngine]] = {}
+
+    @staticmethod
+    def _layers(input_nc, ndf, n_layers):
+        seq = [[_ConvParams(input_nc, ndf, 4, stride=2, pad=2), _Slot("LeakyReLU(0.2)")]]
+        nf = ndf
+        for _ in range(1, n_layers):
+            nf_prev, nf = nf, min(nf * 2, 512)
+            seq.append([_ConvParams(nf_prev, nf, 4, stride=2, pad=2), _Slot("InstanceNorm2d"), _Slot("LeakyReLU(0.2)")])
+        nf_prev, nf = nf, min(nf * 2, 512)
+        seq.append([_ConvParams(nf_prev, nf, 4, stride=1, pad=2), _Slot("InstanceNorm2d"), _Slot("LeakyReLU(0.2)")])
+        seq.append([_ConvParams(nf, 1, 4, stride=1, pad=2)])
+        return seq
+
+    def _convs(self, scale: int) -> List[_ConvParams]:
+        if self.getIntermFeat:
+            mods = [m for j in range(self.n_layers + 2) for m in getattr(self, "scale%d_layer%d" % (scale, j))]
+        else:
+            mods = list(getattr(self, "layer%d" % scale))
+        return [m for m in mods if isinstance(m, _ConvParams)]
+
+    def _chain(self, scale: int) -> List[dict]:
+        convs = self._convs(scale)
+        chain = []
+        for j, p in enumerate(convs):
+            chain.append(dict(params=p, halo=capi.HALO_ZERO, act=capi.ACT_LRELU02, res=None, norm=(0 < j < len(convs) - 1)))
+        return chain
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise NhvrError("nhvr_b200 modules take CUDA tensors only (no CPU fallback)")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NhvrError("backward through the sm_100a discriminator is not built yet (forward only); use torch.no_grad()")
+        x = x.contiguous().float()
+        N, C, H, W = x.shape
+        key = (N, H, W, x.device.index)
+        engs = self._engines.get(key)
+        if engs is None:
+            capi.require_device()
+            engs, h, w = [], H, W
+            for i in range(self.num_D):
+                engs.append(_ChainEngine(self._chain(self.num_D - 1 - i), N, h, w, x.device, capi.ACT_NONE, 1))
+                h, w = (h + 1) // 2, (w + 1) // 2
+            self._engines[key] = engs
+        result = []
+        xd = x
+        for i, eng in enumerate(engs):
+            eng.maybe_repack()
+            out = eng.run([xd]).clone()
+            if self.getIntermFeat:
+                feats = [eng.feature(j) for j in range(1, len(eng.plans))]
+                result.append(feats + [out])
+            else:
+                result.append([out])
+            if i != self.num_D - 1:
+                nxt = torch.empty(N, C, (xd.shape[2] + 1) // 2, (xd.shape[3] + 1) // 2, dtype=torch.float32, device=x.device)
+                capi.check(capi.load().nhvr_avgpool3s2(xd.data_ptr(), N, C, xd.shape[2], xd.shape[3], nxt.data_ptr(),
+                                                       capi.stream_ptr()), "nhvr_avgpool3s2")
+                xd = nxt
+        return result
+
+
+def define_D(input_nc, ndf, n_layers_D, norm="instance", use_sigmoid=False, num_D=1, getIntermFeat=False,
+             gpu_ids: Sequence[int] = ()):
+    """pix2pixHD ``define_D`` signature [SURVEY §8(b); named by BASELINE.json]."""
+    if norm != "instance":
+        raise NotImplementedError("only norm='instance' (the reference default) is built on sm_100a")
+    net = MultiscaleDiscriminatorB200(input_nc, ndf, n_layers_D, use_sigmoid, num_D, getIntermFeat)
     if len(gpu_ids) > 0:
         net.cuda(gpu_ids[0])
     elif torch.cuda.is_available():

@@ -225,3 +225,53 @@ def test_pipeline_lockstep_clips_equal_single(cuda_dev):
     for b in range(2):
         single = pipe.render_clip(poses[b])
         assert (both[b] - single).abs().max().item() <= 5e-3
+
+
+# ------------------------------------------------------------------ training side: discriminator + losses (forward)
+@pytest.mark.parametrize("getIntermFeat,num_D,size,batch", [(True, 2, 96, 2), (False, 2, 64, 1), (True, 3, 128, 1)])
+def test_discriminator_parity(cuda_dev, getIntermFeat, num_D, size, batch):
+    from nhvr_b200.networks import define_D
+    from oracle.networks import define_D as oracle_define_D
+    torch.manual_seed(21)
+    ref = oracle_define_D(6, 32, 3, "instance", False, num_D, getIntermFeat).to(cuda_dev).eval()
+    net = define_D(6, 32, 3, "instance", False, num_D, getIntermFeat)
+    net.load_state_dict(ref.state_dict())
+    x = torch.rand(batch, 6, size, size, device=cuda_dev) * 2 - 1
+    with torch.no_grad():
+        y, y_ref = net(x), ref(x)
+    assert len(y) == len(y_ref) == num_D
+    for a_scale, b_scale in zip(y, y_ref):
+        assert len(a_scale) == len(b_scale)
+        for a, b in zip(a_scale, b_scale):
+            assert a.shape == b.shape                      # odd PatchGAN sizes (size/2+1, ...) included
+            assert (a - b).abs().max().item() <= 2e-2 * max(1.0, b.abs().max().item())
+
+
+def test_losses_parity(cuda_dev):
+    """fp32 losses within 1e-3 relative of the oracle (BASELINE.json north_star)."""
+    from nhvr_b200 import losses as L
+    from oracle import losses as O
+    torch.manual_seed(23)
+    dev = cuda_dev
+    a, b = torch.rand(2, 3, 70, 90, device=dev) * 2 - 1, torch.rand(2, 3, 70, 90, device=dev) * 2 - 1
+
+    def close(x, y):
+        return abs(float(x) - float(y)) <= 1e-3 * max(abs(float(y)), 1e-6)
+    assert close(L.mse(a, b), O.l2_loss(a, b))
+    assert close(L.l1(a, b), torch.nn.functional.l1_loss(a, b))
+    preds = [[torch.randn(2, 8, 20, 20, device=dev), torch.randn(2, 1, 11, 11, device=dev)],
+             [torch.randn(2, 8, 10, 10, device=dev), torch.randn(2, 1, 6, 6, device=dev)]]
+    preds2 = [[torch.randn_like(t) for t in s] for s in preds]
+    for real in (True, False):
+        assert close(L.gan_loss(preds, real), O.gan_loss(preds, real))
+    assert close(L.feature_matching_loss(preds, preds2, 0, 2), O.feature_matching_loss(preds, preds2, 0, 2))
+    uvp = torch.randn(2, 73, 33, 47, device=dev) * 2
+    dp_i = torch.randint(0, 25, (2, 33, 47), device=dev)
+    dp_uv = torch.rand(2, 2, 33, 47, device=dev)
+    uv, prob = L.uv_prob_losses(uvp, dp_i, dp_uv)
+    assert close(uv, O.uv_loss(uvp, dp_i, dp_uv)) and close(prob, O.prob_loss(uvp, dp_i))
+    uv0, _ = L.uv_prob_losses(uvp, torch.zeros_like(dp_i), dp_uv)          # no foreground at all -> 0, not NaN
+    assert float(uv0) == 0.0
+    flow = torch.randn(2, 2, 70, 90, device=dev) * 3
+    assert close(L.temporal_loss(a, b, flow), O.temporal_loss(a, b, flow))
+    assert close(L.temporal_loss(a, a, torch.zeros_like(flow)), 0.0) or float(L.temporal_loss(a, a, torch.zeros_like(flow))) < 1e-7
