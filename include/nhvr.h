@@ -42,10 +42,12 @@ typedef enum nhvr_status {
 enum { NHVR_HALO_ZERO = 0, NHVR_HALO_REFLECT = 1 };
 enum { NHVR_ACT_NONE = 0, NHVR_ACT_RELU = 1, NHVR_ACT_LRELU02 = 2, NHVR_ACT_TANH = 3,
        NHVR_ACT_TANH_SIGMOID_LAST = 4 /* tanh on all channels but the last, sigmoid on the last */ };
-enum { NHVR_CONV = 0, NHVR_CONV_TRANSPOSE = 1 /* k3 s2 p1 output_padding 1 */ };
+enum { NHVR_CONV = 0, NHVR_CONV_TRANSPOSE = 1 /* k3 s2 p1 output_padding 1 */,
+       NHVR_CONV_DGRAD_S1 = 2 /* input-gradient of a stride-1 conv; the desc describes the FORWARD conv */ };
 enum { NHVR_EPI_RAW_STATS = 0,   /* bf16 P8 un-padded conv output + per-(n,c) sum / sum-of-squares */
        NHVR_EPI_BIAS_ACT_F32 = 1,/* bias + activation, fp32 NCHW output                            */
-       NHVR_EPI_BIAS_ACT_P8 = 2  /* bias + activation, bf16 P8 output in a consumer's format       */ };
+       NHVR_EPI_BIAS_ACT_P8 = 2, /* bias + activation, bf16 P8 output in a consumer's format       */
+       NHVR_EPI_RAW_P8 = 3       /* P8 un-padded output, no statistics (gradient convs)            */ };
 
 /* P8 activation descriptor (see header comment). */
 typedef struct nhvr_act_desc {
@@ -101,6 +103,9 @@ int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** out);
 void nhvr_conv_plan_destroy(nhvr_conv_plan* p);
 int nhvr_conv_input_desc(const nhvr_conv_plan* p, nhvr_act_desc* in_desc);   /* format the input must have */
 int nhvr_conv_output_dims(const nhvr_conv_plan* p, int32_t* Ho, int32_t* Wo, int32_t* Cout8);
+/* replace the plan's input descriptor by a layout-compatible one with a taller bottom halo (gradient buffers
+ * shared with a wgrad plan, see nhvr_wgrad_grad_desc) */
+int nhvr_conv_plan_set_input_desc(nhvr_conv_plan* p, const nhvr_act_desc* desc);
 size_t nhvr_conv_weight_bytes(const nhvr_conv_plan* p);
 double nhvr_conv_flops(const nhvr_conv_plan* p);     /* algorithmic 2*k*k*Cin*Cout*Ho*Wo*N, un-padded */
 /* tiling introspection: info[0..15] = kcp, nchunks, njobs, nruns, nacc, slab_units, Npad, bpb, nbstages,
@@ -142,6 +147,20 @@ int nhvr_texture_sample(const float* uvp, const float* atlas, int32_t N, int32_t
  * bg: float [3][H][W] (bg_batched==0, broadcast) or [N][3][H][W]; out: float [N][3][H][W]. */
 int nhvr_composite(const float* fgm, const float* bg, int32_t bg_batched, int32_t N, int32_t H, int32_t W,
                    float* out, void* stream);
+
+/* ---- weight gradient (tcgen05, MN-major operands straight from P8) ----
+ * fwd describes the FORWARD conv (NHVR_CONV any stride, or NHVR_CONV_TRANSPOSE).  x is the forward conv's
+ * P8 input (nhvr_conv_input_desc of the forward plan); g is the output gradient in the format
+ * nhvr_wgrad_grad_desc() returns, which is also the (bottom-extended) input format of the matching dgrad
+ * conv: NHVR_CONV_DGRAD_S1 for a stride-1 conv, NHVR_CONV_TRANSPOSE for a stride-2 conv, NHVR_CONV stride 2
+ * for a transposed conv.  dw has the forward weight's layout and receives (accumulate ? dw : 0) + scale * dW. */
+typedef struct nhvr_wgrad_plan nhvr_wgrad_plan;
+int nhvr_wgrad_plan_create(const nhvr_conv_desc* fwd, nhvr_wgrad_plan** out);
+void nhvr_wgrad_plan_destroy(nhvr_wgrad_plan* p);
+int nhvr_wgrad_grad_desc(const nhvr_wgrad_plan* p, nhvr_act_desc* g_desc);
+size_t nhvr_wgrad_workspace_bytes(const nhvr_wgrad_plan* p);
+int nhvr_wgrad(const nhvr_wgrad_plan* p, const void* x, const void* g, void* workspace, float* dw, float scale,
+               int32_t accumulate, void* stream);
 
 /* ---- training-side reductions (fp32 in, fp64 accumulate) ----
  * Each call ADDS partial sums into a caller-zeroed double accumulator; the host divides by the element

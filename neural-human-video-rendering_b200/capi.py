@@ -18,8 +18,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libnhvr_sm100.so")
 # enums (include/nhvr.h)
 HALO_ZERO, HALO_REFLECT = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU02, ACT_TANH, ACT_TANH_SIGMOID_LAST = 0, 1, 2, 3, 4
-CONV, CONV_TRANSPOSE = 0, 1
-EPI_RAW_STATS, EPI_BIAS_ACT_F32, EPI_BIAS_ACT_P8 = 0, 1, 2
+CONV, CONV_TRANSPOSE, CONV_DGRAD_S1 = 0, 1, 2
+EPI_RAW_STATS, EPI_BIAS_ACT_F32, EPI_BIAS_ACT_P8, EPI_RAW_P8 = 0, 1, 2, 3
 
 
 class ActDesc(C.Structure):
@@ -54,6 +54,12 @@ SYMBOLS = {
     "nhvr_conv_plan_destroy": (None, [_P]),
     "nhvr_conv_input_desc": (C.c_int, [_P, C.POINTER(ActDesc)]),
     "nhvr_conv_output_dims": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "nhvr_conv_plan_set_input_desc": (C.c_int, [_P, C.POINTER(ActDesc)]),
+    "nhvr_wgrad_plan_create": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(_P)]),
+    "nhvr_wgrad_plan_destroy": (None, [_P]),
+    "nhvr_wgrad_grad_desc": (C.c_int, [_P, C.POINTER(ActDesc)]),
+    "nhvr_wgrad_workspace_bytes": (C.c_size_t, [_P]),
+    "nhvr_wgrad": (C.c_int, [_P, _P, _P, _P, _P, C.c_float, C.c_int32, _P]),
     "nhvr_conv_weight_bytes": (C.c_size_t, [_P]),
     "nhvr_conv_flops": (C.c_double, [_P]),
     "nhvr_conv_plan_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_int32]),

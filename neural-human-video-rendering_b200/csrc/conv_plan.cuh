@@ -1,0 +1,80 @@
+// Shared between the forward/dgrad conv kernel and the wgrad kernel: the "shift program" of one conv.
+#pragma once
+#include "common.cuh"
+#include "p8.cuh"
+
+namespace nhvr {
+
+constexpr int kMaxJobs = 52;
+constexpr int kMaxMma = 208;   // jobs x k-steps per chunk
+constexpr int kMaxRuns = 8;
+constexpr int kTileM = 128;
+
+struct ConvJob {
+  int32_t a_off;   // shift (16-B units) inside a plane slab
+  int16_t acc;     // accumulator index
+  int16_t first;   // first job of its accumulator (overwrites instead of accumulating)
+};
+struct ConvMma {     // one tcgen05.mma of a chunk: precomputed so the issue loop has no arithmetic chains
+  int32_t a_off;     // (job shift + k-step plane offset) in 16-B units inside the chunk slab
+  uint16_t acc_col;  // accumulator column offset in TMEM
+  uint16_t first;    // overwrites its accumulator when executed in the first chunk
+};
+struct ConvRun {
+  int32_t g_off;   // offset (units) from the plane base + q0
+  int32_t len;     // units
+  int32_t s_off;   // offset (units) inside the plane slab
+};
+
+struct ConvKParams {
+  const uint4* in;
+  const uint4* w;
+  const float* bias;
+  void* out;
+  float* stats;
+  int64_t in_plane_units;
+  int64_t w_split_units;   // packed-weight units per N-split
+  int32_t C8in, kcp, nchunks, njobs, nruns, nacc;
+  int32_t slab_units, Npad, bpb, nbstages, nblocks;
+  int32_t SA, SB;
+  int32_t Wrow, Hv, Wv, oys, oxs;
+  int32_t oy[4], ox[4];
+  int32_t Ho, Wo, Cout, Cout8;
+  int32_t epilogue, act;
+  int32_t tmem_cols;
+  int32_t f16;             // operand element type: 0 bf16, 1 fp16
+  int32_t debug;           // NHVR_CONV_DEBUG experiments (results are wrong when set): 1 no MMA, 2 unshifted A, 4 double issue
+  ActGeom og;              // BIAS_ACT_P8 destination
+  int32_t mmas_per_chunk, stages_per_chunk;
+  ConvRun runs[kMaxRuns];
+  ConvMma mma[kMaxMma];
+};
+
+
+}  // namespace nhvr
+
+// weight packing parameters (conv_pack_weights_kernel)
+namespace nhvr {
+struct PackParams {
+  const float* w;
+  uint4* dst;
+  int32_t Cin, Cout, kh, kw, transposed;
+  int32_t kcp, nchunks, njobs, Npad, nsplit, nblocks_padded;
+  int32_t f16;
+  int32_t flip;                // dgrad of a stride-1 conv: taps mirrored (r,s) -> (kh-1-r, kw-1-s)
+  int16_t job_tap[kMaxJobs];   // r*kw + s of each job
+};
+}  // namespace nhvr
+
+struct nhvr_conv_plan {
+  nhvr_conv_desc d;
+  nhvr_act_desc in_desc;
+  nhvr::ConvKParams kp;          // pointers filled at launch
+  nhvr::PackParams pp;
+  int32_t Ho, Wo, Cout8, nsplit, tiles_per_img;
+  size_t smem_bytes;
+  size_t weight_bytes;
+  // host copies of the shift program (wgrad reuses them)
+  int32_t njobs_h;
+  nhvr::ConvJob jobs_h[nhvr::kMaxJobs];
+};

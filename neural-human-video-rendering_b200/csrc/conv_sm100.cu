@@ -15,8 +15,7 @@
 // Roles (384 threads): warp0 = slab producer, warp1 = weight producer, warp2 = MMA issuer (one
 // thread), warp3 = TMEM allocator, warps 4-11 = epilogue (TMEM -> registers -> global, InstanceNorm
 // statistics by warp-shuffle column reduction, or bias + activation).
-#include "common.cuh"
-#include "p8.cuh"
+#include "conv_plan.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -29,51 +28,6 @@ extern void note_cuda_error(cudaError_t e);
 extern void count_launch();
 extern int arch_ok_cached();
 extern int operand_f16();
-
-constexpr int kMaxJobs = 52;
-constexpr int kMaxMma = 208;   // jobs x k-steps per chunk
-constexpr int kMaxRuns = 8;
-constexpr int kTileM = 128;
-
-struct ConvJob {
-  int32_t a_off;   // shift (16-B units) inside a plane slab
-  int16_t acc;     // accumulator index
-  int16_t first;   // first job of its accumulator (overwrites instead of accumulating)
-};
-struct ConvMma {     // one tcgen05.mma of a chunk: precomputed so the issue loop has no arithmetic chains
-  int32_t a_off;     // (job shift + k-step plane offset) in 16-B units inside the chunk slab
-  uint16_t acc_col;  // accumulator column offset in TMEM
-  uint16_t first;    // overwrites its accumulator when executed in the first chunk
-};
-struct ConvRun {
-  int32_t g_off;   // offset (units) from the plane base + q0
-  int32_t len;     // units
-  int32_t s_off;   // offset (units) inside the plane slab
-};
-
-struct ConvKParams {
-  const uint4* in;
-  const uint4* w;
-  const float* bias;
-  void* out;
-  float* stats;
-  int64_t in_plane_units;
-  int64_t w_split_units;   // packed-weight units per N-split
-  int32_t C8in, kcp, nchunks, njobs, nruns, nacc;
-  int32_t slab_units, Npad, bpb, nbstages, nblocks;
-  int32_t SA, SB;
-  int32_t Wrow, Hv, Wv, oys, oxs;
-  int32_t oy[4], ox[4];
-  int32_t Ho, Wo, Cout, Cout8;
-  int32_t epilogue, act;
-  int32_t tmem_cols;
-  int32_t f16;             // operand element type: 0 bf16, 1 fp16
-  int32_t debug;           // NHVR_CONV_DEBUG experiments (results are wrong when set): 1 no MMA, 2 unshifted A, 4 double issue
-  ActGeom og;              // BIAS_ACT_P8 destination
-  int32_t mmas_per_chunk, stages_per_chunk;
-  ConvRun runs[kMaxRuns];
-  ConvMma mma[kMaxMma];
-};
 
 // -------------------------------------------------------------------------------------------------
 // warp-level column sums: every lane holds 16 values (one row, 16 columns); on return lane l holds
@@ -286,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(vr[i]);
         const int c0 = cout_off + g * 16;
 
-        if (P.epilogue == NHVR_EPI_RAW_STATS) {
+        if (P.epilogue == NHVR_EPI_RAW_STATS || P.epilogue == NHVR_EPI_RAW_P8) {
           if (valid) {
             uint4* o = reinterpret_cast<uint4*>(P.out);
             const int64_t u0 = (((int64_t)n * P.Cout8 + (c0 >> 3)) * P.Ho + Y) * P.Wo + X;
@@ -299,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
             if ((c0 >> 3) < P.Cout8) o[u0] = lo;
             if ((c0 >> 3) + 1 < P.Cout8) o[u0 + pstride] = hi;
           }
-          if (!(P.debug & 16)) {
+          if (P.epilogue == NHVR_EPI_RAW_STATS && !(P.debug & 16)) {
           float s[16], ss[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) { s[i] = valid ? v[i] : 0.f; ss[i] = s[i] * s[i]; }
@@ -362,15 +316,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
 // -------------------------------------------------------------------------------------------------
 // weight packing: OIHW (or IOHW for transposed) fp32 -> per-MMA blocks [2][Npad][8] bf16 in
 // consumption order (chunk, job, k-step); see header comment.
-struct PackParams {
-  const float* w;
-  uint4* dst;
-  int32_t Cin, Cout, kh, kw, transposed;
-  int32_t kcp, nchunks, njobs, Npad, nsplit, nblocks_padded;
-  int32_t f16;
-  int16_t job_tap[kMaxJobs];   // r*kw + s of each job
-};
-
 __global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
   const int64_t total = (int64_t)P.nsplit * P.nblocks_padded * 2 * P.Npad;
   const int qsteps = P.kcp >> 1;
@@ -386,7 +331,7 @@ __global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
       const int qq = blk % qsteps;
       const int j = (blk / qsteps) % P.njobs;
       const int c = blk / (qsteps * P.njobs);
-      const int tap = P.job_tap[j];
+      const int tap = P.flip ? (P.kh * P.kw - 1 - P.job_tap[j]) : P.job_tap[j];
       const int co = z * P.Npad + nrow;
       float vals[8];
 #pragma unroll
@@ -414,16 +359,6 @@ __global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
 // =================================================================================================
 using namespace nhvr;
 
-struct nhvr_conv_plan {
-  nhvr_conv_desc d;
-  nhvr_act_desc in_desc;
-  ConvKParams kp;          // pointers filled at launch
-  PackParams pp;
-  int32_t Ho, Wo, Cout8, nsplit, tiles_per_img;
-  size_t smem_bytes;
-  size_t weight_bytes;
-};
-
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline int next_pow2_cols(int c) { int p = 32; while (p < c) p <<= 1; return p; }
 
@@ -434,7 +369,9 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   std::memset(p, 0, sizeof(*p));
   p->d = *d;
   ConvKParams& K = p->kp;
-  const int C8 = round_up((d->Cin + 7) / 8, 2);   // K = 16 per MMA -> an even number of planes
+  int gemm_k = d->Cin, gemm_n = d->Cout;          // dgrad swaps them
+  if (d->kind == NHVR_CONV_DGRAD_S1) { gemm_k = d->Cout; gemm_n = d->Cin; }
+  const int C8 = round_up((gemm_k + 7) / 8, 2);   // K = 16 per MMA -> an even number of planes
   K.C8in = C8;
   nhvr_act_desc& in = p->in_desc;
   in.N = d->N; in.C8 = C8; in.H = d->H; in.W = d->W; in.halo = d->halo; in.split = 0;
@@ -455,6 +392,23 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
     for (int r = 0; r < d->kh; ++r)
       for (int s = 0; s < d->kw; ++s) taps.push_back({r, s, 0, r * d->kw + s});
     K.Wrow = Wp; K.Hv = Ho; K.Wv = Wo; K.oys = K.oxs = 1;
+  } else if (d->kind == NHVR_CONV_DGRAD_S1) {
+    // d describes the FORWARD conv (Cin, Cout, k, pad, input H x W).  dX over the padded input extent is the
+    // correlation of the output gradient (stored with k-1 zero rows above/below and k-1 zero columns LEFT of
+    // every row: consecutive rows share that gap in the linearised image) with the mirrored, transposed taps.
+    if (d->stride != 1) { delete p; return NHVR_ERR_UNSUPPORTED; }
+    const int Hof = d->H + 2 * d->pad - d->kh + 1, Wof = d->W + 2 * d->pad - d->kw + 1;
+    if (Hof <= 0 || Wof <= 0) { delete p; return NHVR_ERR_SHAPE; }
+    in.H = Hof; in.W = Wof;
+    in.C8 = round_up((d->Cout + 7) / 8, 2);
+    in.pad_t = in.pad_b = d->kh - 1; in.pad_l = d->kw - 1; in.pad_r = 0;
+    in.halo = NHVR_HALO_ZERO;
+    const int Wpi = Wof + d->kw - 1;                 // == W + 2*pad: same pitch as the forward input
+    Ho = d->H + 2 * d->pad; Wo = d->W + 2 * d->pad;  // gradient w.r.t. the PADDED forward input
+    for (int r = 0; r < d->kh; ++r) run_specs.push_back({r * Wpi, kTileM + d->kw - 1});
+    for (int r = 0; r < d->kh; ++r)
+      for (int s = 0; s < d->kw; ++s) taps.push_back({r, s, 0, r * d->kw + s});
+    K.Wrow = Wpi; K.Hv = Ho; K.Wv = Wo; K.oys = K.oxs = 1;
   } else if (d->kind == NHVR_CONV && d->stride == 2) {
     in.pad_t = in.pad_b = in.pad_l = in.pad_r = d->pad;
     in.split = 1;
@@ -540,12 +494,14 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
     p->pp.job_tap[j] = (int16_t)taps[j].tap;
   }
   K.nacc = nacc;
+  p->njobs_h = K.njobs;
+  for (int j = 0; j < K.njobs; ++j) p->jobs_h[j] = jobs[j];
 
   // ---- N (Cout) tiling
-  int Npad = round_up(d->Cout, 16);
+  int Npad = round_up(gemm_n, 16);
   int nsplit = 1;
   const int max_n = 256 / (nacc > 2 ? 2 : 1) / (nacc > 1 ? 2 : 1);   // nacc*Npad <= 512 and Npad <= 256
-  while (Npad > std::min(256, 512 / nacc)) { nsplit *= 2; Npad = round_up((d->Cout + nsplit - 1) / nsplit, 16); }
+  while (Npad > std::min(256, 512 / nacc)) { nsplit *= 2; Npad = round_up((gemm_n + nsplit - 1) / nsplit, 16); }
   (void)max_n;
   K.Npad = Npad;
   K.tmem_cols = next_pow2_cols(nacc * Npad);
@@ -553,8 +509,8 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   p->Ho = Ho; p->Wo = Wo;
   // P8 outputs carry an even number of planes (zero channels beyond Cout) so that they can feed the next
   // conv directly: one MMA consumes K = 16 channels = 2 planes
-  p->Cout8 = round_up((d->Cout + 7) / 8, 2);
-  K.Ho = Ho; K.Wo = Wo; K.Cout = d->Cout; K.Cout8 = p->Cout8;
+  p->Cout8 = round_up((gemm_n + 7) / 8, 2);
+  K.Ho = Ho; K.Wo = Wo; K.Cout = gemm_n; K.Cout8 = p->Cout8;
   K.epilogue = d->epilogue; K.act = d->act;
 
   // ---- shared-memory budget: prefer two co-resident CTAs per SM (<= ~100 KB, <= 256 TMEM columns)
@@ -619,8 +575,11 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   p->tiles_per_img = (int)((last_q + kTileM - 1) / kTileM);
 
   PackParams& PP = p->pp;
-  PP.Cin = d->Cin; PP.Cout = d->Cout; PP.kh = d->kh; PP.kw = d->kw;
-  PP.transposed = d->kind == NHVR_CONV_TRANSPOSE;
+  PP.Cin = gemm_k; PP.Cout = gemm_n; PP.kh = d->kh; PP.kw = d->kw;
+  // weight tensor layout [GEMM-K channel][GEMM-N channel][kh][kw]: ConvTranspose2d weights, and the forward
+  // Conv2d weight [Cout][Cin] seen from its dgrad (K = Cout, N = Cin)
+  PP.transposed = (d->kind == NHVR_CONV_TRANSPOSE || d->kind == NHVR_CONV_DGRAD_S1);
+  PP.flip = (d->kind == NHVR_CONV_DGRAD_S1);
   PP.kcp = kcp; PP.nchunks = K.nchunks; PP.njobs = K.njobs; PP.Npad = Npad; PP.nsplit = nsplit;
   PP.nblocks_padded = nblocks_padded;
   *out = p;
@@ -634,6 +593,20 @@ extern "C" int nhvr_conv_input_desc(const nhvr_conv_plan* p, nhvr_act_desc* in_d
   *in_desc = p->in_desc;
   return NHVR_OK;
 }
+// Accept a caller-supplied input descriptor that is layout-compatible with the plan's own (same pitch, top /
+// left halo, split and channel planes) but taller at the bottom: gradient buffers shared with a wgrad plan carry
+// extra zero rows (see nhvr_wgrad_grad_desc).  Only the plane stride changes.
+extern "C" int nhvr_conv_plan_set_input_desc(nhvr_conv_plan* p, const nhvr_act_desc* desc) {
+  if (!p || !desc) return NHVR_ERR_NULL;
+  const ActGeom a = make_geom(p->in_desc), b = make_geom(*desc);
+  if (a.N != b.N || a.C8 != b.C8 || a.Wp != b.Wp || a.pad_t != b.pad_t || a.pad_l != b.pad_l || a.split != b.split ||
+      a.H != b.H || a.W != b.W || b.Hp < a.Hp)
+    return NHVR_ERR_SHAPE;
+  p->in_desc = *desc;
+  p->kp.in_plane_units = b.plane_units;
+  return NHVR_OK;
+}
+
 extern "C" int nhvr_conv_output_dims(const nhvr_conv_plan* p, int32_t* Ho, int32_t* Wo, int32_t* Cout8) {
   if (!p) return NHVR_ERR_NULL;
   if (Ho) *Ho = p->Ho;
@@ -645,7 +618,9 @@ extern "C" size_t nhvr_conv_weight_bytes(const nhvr_conv_plan* p) { return p ? p
 extern "C" double nhvr_conv_flops(const nhvr_conv_plan* p) {
   if (!p) return 0.0;
   const nhvr_conv_desc& d = p->d;
-  const double px = d.kind == NHVR_CONV_TRANSPOSE ? (double)d.H * d.W : (double)p->Ho * p->Wo;
+  const double px = d.kind == NHVR_CONV_TRANSPOSE ? (double)d.H * d.W
+                    : d.kind == NHVR_CONV_DGRAD_S1 ? (double)(d.H + 2 * d.pad - d.kh + 1) * (d.W + 2 * d.pad - d.kw + 1)
+                                                   : (double)p->Ho * p->Wo;
   return 2.0 * d.kh * d.kw * d.Cin * d.Cout * px * d.N;
 }
 // introspection used by tests / DESIGN.md tables
