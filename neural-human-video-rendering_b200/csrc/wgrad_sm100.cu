@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     tc_fence_after();
     if (c_end > c_begin) {
       for (int t = 0; t < ntaps; ++t) {
-        float* dst = P.ws + ((int64_t)(tap0 + t) * P.CoutP + co) * P.CinP + ci_blk * P.nci;
+        float* dst = P.ws + ((int64_t)P.taps[tap0 + t].tap * P.CoutP + co) * P.CinP + ci_blk * P.nci;   // filter-tap order
         for (int gcol = 0; gcol < P.nci; gcol += 16) {
           uint32_t vr[16];
           tmem_ld16(t_lane + (uint32_t)(t * P.nci + gcol), vr);

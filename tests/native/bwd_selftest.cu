@@ -106,6 +106,14 @@ static int run_case(const Case& c) {
     if (e > werr || std::isnan(got[i])) werr = std::isnan(got[i]) ? 1e30 : e;
   }
 
+  if (getenv("BWD_VERBOSE")) {
+    const int kk = c.k * c.k;
+    for (int tap = 0; tap < kk; ++tap) {
+      double te = 0, tr = 0;
+      for (size_t i = tap; i < wn; i += kk) { te = fmax(te, fabs(got[i] - ref[i])); tr = fmax(tr, fabs(ref[i])); }
+      printf("   tap %d (ky=%d kx=%d): max_err %.3e  max|ref| %.2f   got[0]=%.4f ref[0]=%.4f\n", tap, tap / c.k, tap % c.k, te, tr, got[tap], ref[tap]);
+    }
+  }
   // ---- dgrad of a stride-1 conv from the same gradient buffer
   double derr = 0, dmax = 0; size_t dbad = 0;
   if (c.kind == NHVR_CONV && c.stride == 1) {
