@@ -162,6 +162,26 @@ size_t nhvr_wgrad_workspace_bytes(const nhvr_wgrad_plan* p);
 int nhvr_wgrad(const nhvr_wgrad_plan* p, const void* x, const void* g, void* workspace, float* dw, float scale,
                int32_t accumulate, void* stream);
 
+/* ---- backward of  x_next = pad(act(InstanceNorm(raw)) [+ residual]) ----
+ * dx: gradient w.r.t. the PADDED x_next as an un-padded P8 buffer [N][C8][dx_H][dx_W] (the dgrad conv's
+ * RAW_P8 output); the interior starts at (pad_t, pad_l); reflect != 0 folds the mirrored halo gradients
+ * back (ReflectionPad2d), 0 drops them (zero padding).  skip (nullable): extra gradient of the un-padded
+ * output (ResnetBlock skip path), P8 [N][C8][H][W].  raw / stats: the forward RAW_STATS outputs.
+ * Writes g (gradient w.r.t. raw) in g_desc's format, halo zeroed; dy_out (nullable) receives the folded
+ * total gradient of the un-padded output; sums is a float [N][C8*8][2] scratch. */
+int nhvr_in_bwd(const void* dx, int32_t dx_H, int32_t dx_W, int32_t pad_t, int32_t pad_l, int32_t reflect,
+                const void* skip, const void* raw, const nhvr_act_desc* raw_desc, const float* stats, float eps,
+                int32_t act, float* sums, void* g, const nhvr_act_desc* g_desc, void* dy_out, void* stream);
+/* folded gradient of a chain input -> float [N][C][H][W] * scale (interior_desc: un-padded P8 of the input) */
+int nhvr_fold_unpack(const void* dx, int32_t dx_H, int32_t dx_W, int32_t pad_t, int32_t pad_l, int32_t reflect,
+                     const nhvr_act_desc* interior_desc, float* dst, int32_t C, float scale, void* stream);
+/* output layer (bias + activation, no norm): g_pre = grad_out * act'(out) * scale, all float [N][C][H][W] */
+int nhvr_head_bwd(const float* out, const float* grad_out, int32_t N, int32_t C, int32_t H, int32_t W, int32_t act,
+                  float scale, float* g_pre, void* stream);
+/* db[c] = (accumulate ? db[c] : 0) + scale * sum over n,h,w of g[n][c][h][w] */
+int nhvr_bias_grad(const float* g, int32_t N, int32_t C, int32_t H, int32_t W, float scale, int32_t accumulate, float* db,
+                   void* stream);
+
 /* ---- training-side reductions (fp32 in, fp64 accumulate) ----
  * Each call ADDS partial sums into a caller-zeroed double accumulator; the host divides by the element
  * count to get the mean the reference's torch losses return (pretrain_start.sh:31-37 --lambda_L2 /

@@ -70,6 +70,12 @@ SYMBOLS = {
     "nhvr_texture_sample": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P,
                                       _P, _P]),
     "nhvr_composite": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "nhvr_in_bwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.POINTER(ActDesc), _P, C.c_float,
+                            C.c_int32, _P, _P, C.POINTER(ActDesc), _P, _P]),
+    "nhvr_fold_unpack": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ActDesc), _P, C.c_int32,
+                                 C.c_float, _P]),
+    "nhvr_head_bwd": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P]),
+    "nhvr_bias_grad": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P, _P]),
     "nhvr_loss_sum_sq_diff": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "nhvr_loss_sum_abs_diff": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "nhvr_loss_sum_sq_const": (C.c_int, [_P, C.c_float, C.c_int64, _P, _P]),

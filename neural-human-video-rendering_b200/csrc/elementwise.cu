@@ -232,3 +232,306 @@ extern "C" int nhvr_in_apply(const void* raw, const nhvr_act_desc* raw_desc, con
   if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
   return NHVR_OK;
 }
+
+// =================================================================================================
+// backward of  x_next = pad( act( InstanceNorm(raw) ) [+ residual] )
+// =================================================================================================
+// dX is the gradient w.r.t. the PADDED tensor x_next (un-padded P8 buffer whose logical size is the padded
+// extent, as written by the dgrad conv), `fold` describes that padding: the gradient of an interior pixel is
+// the sum of dX over every padded position that mirrors it (ReflectionPad2d) or just its own (zero padding).
+// Pass 1 reduces  s1 = sum g_z,  s2 = sum g_z * z  per (n, c);  pass 2 writes
+//   g_raw = rstd * (g_z - s1/HW - z * s2/HW)      with  z = (raw - mean) * rstd,  g_z = dY * act'(z)
+// into the gradient format shared by this layer's dgrad and wgrad (zero halo), and optionally the folded
+// total dY (needed later as the skip-connection gradient of a ResnetBlock).
+namespace nhvr {
+
+struct FoldGeom {
+  int32_t H, W;            // interior size
+  int32_t pad_t, pad_l;    // interior origin inside dX
+  int32_t Hp, Wp;          // dX logical size
+  int32_t reflect;         // 1: mirror halo contributes, 0: zero padding (halo gradient dropped)
+};
+
+struct InBwdParams {
+  const uint4* dx;         // P8 [N][C8][Hp][Wp] un-padded buffer
+  const uint4* skip;       // nullable, P8 [N][C8][H][W]
+  const uint4* raw;        // P8 [N][C8][H][W]
+  const float* stats;      // [N][C8*8][2] forward sums
+  float* sums;             // [N][C8*8][2] backward sums (pass 1 out, pass 2 in)
+  uint4* g;                // pass 2 out: gradient format
+  uint4* dy_out;           // pass 2 out (nullable): folded dY, P8 [N][C8][H][W]
+  FoldGeom f;
+  ActGeom gg;              // gradient format geometry
+  int32_t N, C8;
+  float eps, inv_hw;
+  int32_t act, f16;
+};
+
+NHVR_DEVINL void unpack8(const uint4& u, float (&v)[8], int f16) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = (e & 1) ? unpack_hi(w[e >> 1], f16) : unpack_lo(w[e >> 1], f16);
+}
+NHVR_DEVINL uint4 pack8(const float (&v)[8], int f16) {
+  uint4 o;
+  o.x = pack2(v[0], v[1], f16); o.y = pack2(v[2], v[3], f16);
+  o.z = pack2(v[4], v[5], f16); o.w = pack2(v[6], v[7], f16);
+  return o;
+}
+
+// folded gradient of interior pixel (y, x) of plane np
+NHVR_DEVINL void fold_load(const InBwdParams& P, int64_t np, int y, int x, float (&dy)[8]) {
+  const FoldGeom& f = P.f;
+  int ys[2], xs[2], ny = 1, nx = 1;
+  ys[0] = y + f.pad_t; xs[0] = x + f.pad_l;
+  if (f.reflect) {
+    // padded rows that mirror row y: pad_t - y (top halo, 1 <= y <= pad_t) and 2(H-1) - y + pad_t (bottom halo)
+    if (y >= 1 && y <= f.pad_t) ys[ny++] = f.pad_t - y;
+    else { const int yb = 2 * (f.H - 1) - y + f.pad_t; if (y <= f.H - 2 && yb < f.Hp) ys[ny++] = yb; }
+    if (x >= 1 && x <= f.pad_l) xs[nx++] = f.pad_l - x;
+    else { const int xb = 2 * (f.W - 1) - x + f.pad_l; if (x <= f.W - 2 && xb < f.Wp) xs[nx++] = xb; }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) dy[e] = 0.f;
+  const uint4* base = P.dx + np * (int64_t)f.Hp * f.Wp;
+  for (int a = 0; a < ny; ++a)
+    for (int b = 0; b < nx; ++b) {
+      float t[8];
+      unpack8(base[(int64_t)ys[a] * f.Wp + xs[b]], t, P.f16);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dy[e] += t[e];
+    }
+  if (P.skip) {
+    float t[8];
+    unpack8(P.skip[np * (int64_t)f.H * f.W + (int64_t)y * f.W + x], t, P.f16);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dy[e] += t[e];
+  }
+}
+
+NHVR_DEVINL void fwd_norm_params(const InBwdParams& P, int64_t np, float (&scale)[8], float (&shift)[8]) {
+  const float* st = P.stats + np * 16;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float mean = st[2 * e] * P.inv_hw;
+    const float var = fmaxf(st[2 * e + 1] * P.inv_hw - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + P.eps);
+    scale[e] = rstd;
+    shift[e] = -mean * rstd;
+  }
+}
+
+NHVR_DEVINL float act_grad(float z, int act) {
+  if (act == NHVR_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  if (act == NHVR_ACT_LRELU02) return z > 0.f ? 1.f : 0.2f;
+  return 1.f;
+}
+
+__global__ void __launch_bounds__(256) in_bwd_reduce_kernel(const __grid_constant__ InBwdParams P) {
+  const int64_t np = blockIdx.y;
+  float scale[8], shift[8];
+  fwd_norm_params(P, np, scale, shift);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
+  const int total = P.f.H * P.f.W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int y = i / P.f.W, x = i - y * P.f.W;
+    float dy[8], r[8];
+    fold_load(P, np, y, x, dy);
+    unpack8(P.raw[np * (int64_t)total + i], r, P.f16);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float z = fmaf(r[e], scale[e], shift[e]);
+      const float gz = dy[e] * act_grad(z, P.act);
+      s1[e] += gz;
+      s2[e] += gz * z;
+    }
+  }
+  __shared__ float sh[16][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float a = s1[e], b = s2[e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if (lane == 0) { sh[2 * e][warp] = a; sh[2 * e + 1][warp] = b; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[threadIdx.x][w];
+    atomicAdd(P.sums + np * 16 + threadIdx.x, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) in_bwd_apply_kernel(const __grid_constant__ InBwdParams P) {
+  const int64_t np = blockIdx.y;
+  const int n = (int)(np / P.C8), p = (int)(np - (int64_t)n * P.C8);
+  float scale[8], shift[8], m1[8], m2[8];
+  fwd_norm_params(P, np, scale, shift);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { m1[e] = P.sums[np * 16 + 2 * e] * P.inv_hw; m2[e] = P.sums[np * 16 + 2 * e + 1] * P.inv_hw; }
+  const ActGeom& g = P.gg;
+  const int total = g.Hp * g.Wp;       // every position of the gradient format is written (halo = 0)
+  const int HW = P.f.H * P.f.W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int yy = i / g.Wp, xx = i - yy * g.Wp;
+    const int y = yy - g.pad_t, x = xx - g.pad_l;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < P.f.H && x >= 0 && x < P.f.W) {
+      float dy[8], r[8], v[8];
+      fold_load(P, np, y, x, dy);
+      unpack8(P.raw[np * (int64_t)HW + (int64_t)y * P.f.W + x], r, P.f16);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float z = fmaf(r[e], scale[e], shift[e]);
+        const float gz = dy[e] * act_grad(z, P.act);
+        v[e] = scale[e] * (gz - m1[e] - z * m2[e]);
+      }
+      o = pack8(v, P.f16);
+      if (P.dy_out) P.dy_out[np * (int64_t)HW + (int64_t)y * P.f.W + x] = pack8(dy, P.f16);
+    }
+    P.g[((int64_t)n * g.C8 + p) * g.plane_units + plane_unit(g, yy, xx)] = o;
+  }
+}
+
+// g_pre = grad_out * act'(out) * scale  (fp32 NCHW), the output layer has no norm
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ out, const float* __restrict__ gout, int64_t n_per_c,
+                                                       int C, int64_t total, int act, float scale, float* __restrict__ gpre) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i / n_per_c) % C);
+    const float o = out[i];
+    float d = 1.f;
+    if (act == NHVR_ACT_TANH || (act == NHVR_ACT_TANH_SIGMOID_LAST && c != C - 1)) d = 1.f - o * o;
+    else if (act == NHVR_ACT_TANH_SIGMOID_LAST) d = o * (1.f - o);
+    else if (act == NHVR_ACT_RELU) d = o > 0.f ? 1.f : 0.f;
+    else if (act == NHVR_ACT_LRELU02) d = o > 0.f ? 1.f : 0.2f;
+    gpre[i] = gout[i] * d * scale;
+  }
+}
+
+// db[c] (+)= scale * sum_{n,h,w} g[n][c][h][w]
+__global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ g, int N, int C, int64_t HW, float scale, int accumulate,
+                                                        float* __restrict__ db) {
+  const int c = blockIdx.x;
+  double s = 0.0;
+  for (int n = 0; n < N; ++n) {
+    const float* p = g + ((int64_t)n * C + c) * HW;
+    float part = 0.f;
+    for (int64_t i = threadIdx.x; i < HW; i += blockDim.x) part += p[i];
+    s += (double)part;
+  }
+  __shared__ double sh[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    const float v = (float)(t * (double)scale);
+    db[c] = accumulate ? db[c] + v : v;
+  }
+}
+
+// folded input gradient -> NCHW fp32 (first C channels), scaled: the chain's dL/d(input)
+__global__ void __launch_bounds__(256) fold_unpack_kernel(const __grid_constant__ InBwdParams P, float* __restrict__ dst, int C, float scale) {
+  const int64_t np = blockIdx.y;
+  const int n = (int)(np / P.C8), p = (int)(np - (int64_t)n * P.C8);
+  const int total = P.f.H * P.f.W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int y = i / P.f.W, x = i - y * P.f.W;
+    float dy[8];
+    fold_load(P, np, y, x, dy);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = p * 8 + e;
+      if (c < C) dst[((int64_t)n * C + c) * total + i] = dy[e] * scale;
+    }
+  }
+}
+
+}  // namespace nhvr
+
+static int make_in_bwd(InBwdParams& P, const void* dx, int32_t dx_H, int32_t dx_W, int32_t pad_t, int32_t pad_l, int32_t reflect,
+                       const void* skip, const void* raw, const nhvr_act_desc* raw_desc, const float* stats, float* sums, float eps,
+                       int32_t act) {
+  if (!dx || !raw_desc) return NHVR_ERR_NULL;
+  const ActGeom rg = make_geom(*raw_desc);
+  if (rg.pad_t || rg.pad_l || rg.Hp != rg.H || rg.Wp != rg.W || rg.split) return NHVR_ERR_SHAPE;   // raw / skip are un-padded
+  if (dx_H < rg.H + pad_t || dx_W < rg.W + pad_l) return NHVR_ERR_SHAPE;
+  P.dx = reinterpret_cast<const uint4*>(dx);
+  P.skip = reinterpret_cast<const uint4*>(skip);
+  P.raw = reinterpret_cast<const uint4*>(raw);
+  P.stats = stats; P.sums = sums;
+  P.g = nullptr; P.dy_out = nullptr;
+  P.f.H = rg.H; P.f.W = rg.W; P.f.pad_t = pad_t; P.f.pad_l = pad_l; P.f.Hp = dx_H; P.f.Wp = dx_W; P.f.reflect = reflect;
+  P.N = rg.N; P.C8 = rg.C8;
+  P.eps = eps; P.inv_hw = 1.0f / ((float)rg.H * (float)rg.W);
+  P.act = act; P.f16 = operand_f16();
+  return NHVR_OK;
+}
+
+#define NHVR_POST(...)                                                    \
+  count_launch();                                                         \
+  {                                                                       \
+    cudaError_t e_ = cudaGetLastError();                                  \
+    if (e_ != cudaSuccess) { note_cuda_error(e_); return NHVR_ERR_CUDA; } \
+  }
+
+extern "C" int nhvr_in_bwd(const void* dx, int32_t dx_H, int32_t dx_W, int32_t pad_t, int32_t pad_l, int32_t reflect,
+                           const void* skip, const void* raw, const nhvr_act_desc* raw_desc, const float* stats, float eps,
+                           int32_t act, float* sums, void* g, const nhvr_act_desc* g_desc, void* dy_out, void* stream) {
+  if (!raw || !stats || !sums || !g || !g_desc) return NHVR_ERR_NULL;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  InBwdParams P;
+  int st = make_in_bwd(P, dx, dx_H, dx_W, pad_t, pad_l, reflect, skip, raw, raw_desc, stats, sums, eps, act);
+  if (st != NHVR_OK) return st;
+  P.gg = make_geom(*g_desc);
+  if (P.gg.N != P.N || P.gg.C8 != P.C8 || P.gg.H != P.f.H || P.gg.W != P.f.W) return NHVR_ERR_SHAPE;
+  P.g = reinterpret_cast<uint4*>(g);
+  P.dy_out = reinterpret_cast<uint4*>(dy_out);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int planes = P.N * P.C8;
+  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)planes * 16 * sizeof(float), s);
+  if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
+  in_bwd_reduce_kernel<<<dim3(grid_x_for((int64_t)P.f.H * P.f.W, planes), planes), 256, 0, s>>>(P);
+  NHVR_POST();
+  in_bwd_apply_kernel<<<dim3(grid_x_for((int64_t)P.gg.Hp * P.gg.Wp, planes), planes), 256, 0, s>>>(P);
+  NHVR_POST();
+  return NHVR_OK;
+}
+
+extern "C" int nhvr_fold_unpack(const void* dx, int32_t dx_H, int32_t dx_W, int32_t pad_t, int32_t pad_l, int32_t reflect,
+                                const nhvr_act_desc* interior_desc, float* dst, int32_t C, float scale, void* stream) {
+  if (!dst) return NHVR_ERR_NULL;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  InBwdParams P;
+  int st = make_in_bwd(P, dx, dx_H, dx_W, pad_t, pad_l, reflect, nullptr, dx, interior_desc, nullptr, nullptr, 0.f, 0);
+  if (st != NHVR_OK) return st;
+  const int planes = P.N * P.C8;
+  fold_unpack_kernel<<<dim3(grid_x_for((int64_t)P.f.H * P.f.W, planes), planes), 256, 0, (cudaStream_t)stream>>>(P, dst, C, scale);
+  NHVR_POST();
+  return NHVR_OK;
+}
+
+extern "C" int nhvr_head_bwd(const float* out, const float* grad_out, int32_t N, int32_t C, int32_t H, int32_t W, int32_t act,
+                             float scale, float* g_pre, void* stream) {
+  if (!out || !grad_out || !g_pre) return NHVR_ERR_NULL;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  const int64_t total = (int64_t)N * C * H * W;
+  head_bwd_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(out, grad_out, (int64_t)H * W, C,
+                                                                                                          total, act, scale, g_pre);
+  NHVR_POST();
+  return NHVR_OK;
+}
+
+extern "C" int nhvr_bias_grad(const float* g, int32_t N, int32_t C, int32_t H, int32_t W, float scale, int32_t accumulate, float* db,
+                              void* stream) {
+  if (!g || !db) return NHVR_ERR_NULL;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  bias_grad_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(g, N, C, (int64_t)H * W, scale, accumulate, db);
+  NHVR_POST();
+  return NHVR_OK;
+}

@@ -72,8 +72,9 @@ class _ChainEngine:
     The last layer has norm=False and writes fp32 NCHW with bias + ``final_act``.
     """
 
-    def __init__(self, chain: List[dict], N: int, H: int, W: int, device, final_act: int, out_channels: int):
+    def __init__(self, chain: List[dict], N: int, H: int, W: int, device, final_act: int, out_channels: int, train: bool = False):
         self.N, self.H, self.W = N, H, W
+        self.train, self.final_act, self._bwd, self.busy = train, final_act, None, False
         self.device = device
         self.chain = chain
         self.plans: List[ops.ConvPlan] = []
@@ -105,7 +106,7 @@ class _ChainEngine:
             # in_bufs[i] is written by the apply after conv i-1 (pack for i == 0): it must not be the live
             # residual source nor the buffer conv i-1 reads
             prev = self.in_bufs[-1] if self.in_bufs else None
-            chosen = next((b for b in pool if b is not live and b is not prev), None)
+            chosen = None if train else next((b for b in pool if b is not live and b is not prev), None)
             if chosen is None:
                 chosen = ops.P8Buffer(d.copy(), device)
                 pool.append(chosen)
@@ -117,6 +118,9 @@ class _ChainEngine:
             if i < len(self.plans) - 1 and chain[i].get("norm", True):
                 rd = plan.raw_desc()
                 rkey = (rd.N, rd.C8, rd.H, rd.W)
+                if train:                                   # backward re-reads every layer's raw output
+                    self.raw_bufs.append(ops.P8Buffer(rd, device))
+                    continue
                 if rkey not in self._raws:
                     self._raws[rkey] = ops.P8Buffer(rd, device)
                 self.raw_bufs.append(self._raws[rkey])
@@ -147,6 +151,105 @@ class _ChainEngine:
         ops.pack_nchw(inputs, self.in_bufs[0])
         return self.run_packed()
 
+    # ------------------------------------------------------------------ backward (training engines only)
+    def _build_backward(self) -> None:
+        L = len(self.plans)
+        dev = self.device
+        B = {"wplans": [], "dplans": [None] * L, "G": [None] * L, "dX": [None] * L, "fold": [None] * L}
+        gpool: Dict[tuple, ops.P8Buffer] = {}
+        xpool: Dict[tuple, ops.P8Buffer] = {}
+
+        def key_of(d):
+            return tuple(getattr(d, f) for f, _ in capi.ActDesc._fields_)
+        ws_bytes = 0
+        for i, (Lr, plan) in enumerate(zip(self.chain, self.plans)):
+            wp = ops.WgradPlan(plan)
+            B["wplans"].append(wp)
+            ws_bytes = max(ws_bytes, wp.ws_bytes)
+            k = key_of(wp.g_desc)
+            if k not in gpool:
+                gpool[k] = ops.P8Buffer(wp.g_desc.copy(), dev)
+            B["G"][i] = gpool[k]
+            p: _ConvParams = Lr["params"]
+            d = plan.desc
+            if p.transposed:          # dgrad of a transposed conv = the stride-2 conv of the gradient
+                dp = ops.ConvPlan(capi.CONV, p.cout, p.cin, p.k, 2, p.pad, self.N, plan.Ho, plan.Wo, capi.HALO_ZERO, capi.EPI_RAW_P8)
+                fold = (0, 0, False)
+            elif p.stride == 2:       # dgrad of a stride-2 conv = the transposed conv of the gradient
+                if p.k != 3 or p.pad != 1 or (d.H % 2) or (d.W % 2):
+                    raise NhvrError("backward of a stride-2 conv is built for k3 p1 on even sizes only")
+                dp = ops.ConvPlan(capi.CONV_TRANSPOSE, p.cout, p.cin, 3, 2, 1, self.N, plan.Ho, plan.Wo, capi.HALO_ZERO, capi.EPI_RAW_P8)
+                fold = (0, 0, False)
+            else:                     # stride-1: gradient over the padded input extent, halo folded afterwards
+                dp = ops.ConvPlan(capi.CONV_DGRAD_S1, p.cin, p.cout, p.k, 1, p.pad, self.N, d.H, d.W, capi.HALO_ZERO, capi.EPI_RAW_P8)
+                fold = (p.pad, p.pad, Lr["halo"] == capi.HALO_REFLECT)
+            ops.conv_set_input_desc(dp, wp.g_desc)
+            B["dplans"][i] = dp
+            B["fold"][i] = fold
+            xd = ops.make_desc(self.N, dp.Cout8, dp.Ho, dp.Wo)
+            k = key_of(xd)
+            if k not in xpool:
+                xpool[k] = ops.P8Buffer(xd, dev)
+            B["dX"][i] = xpool[k]
+        B["ws"] = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        maxc8 = max(pl.Cout8 for pl in self.plans)
+        B["sums"] = torch.zeros(self.N * maxc8 * 16, dtype=torch.float32, device=dev)
+        B["dy"] = {}
+        self._bwd = B
+        self._bwd_versions = None
+
+    def backward(self, grad_out: torch.Tensor, need_input_grad: bool, in_channels: int):
+        """Gradients of the chain: (input_grad NCHW fp32 or None, [dW per layer], db of the output layer)."""
+        assert self.train, "backward needs a training engine"
+        if self._bwd is None:
+            self._build_backward()
+        B = self._bwd
+        ver = tuple(Lr["params"].weight._version for Lr in self.chain)
+        if ver != self._bwd_versions:                       # dgrad convs read the same weights, differently packed
+            for Lr, dp in zip(self.chain, B["dplans"]):
+                dp.pack_weights(Lr["params"].weight)
+            self._bwd_versions = ver
+        L = len(self.plans)
+        grad_out = grad_out.contiguous().float()
+        # static gradient scale: keeps 16-bit gradient operands in range (fp16), exact power of two
+        amax = float(grad_out.abs().max())
+        S = 1.0 if amax == 0.0 or not (amax == amax) else 2.0 ** round(__import__("math").log2(64.0 / amax))
+        inv_S = 1.0 / S
+        g_pre = ops.head_bwd(self.out, grad_out, self.final_act, S)
+        db_last = ops.bias_grad(g_pre, inv_S)
+        ops.pack_nchw([g_pre], B["G"][L - 1])
+        dWs: List[Optional[torch.Tensor]] = [None] * L
+        dy_total: Dict[int, ops.P8Buffer] = {}
+        input_grad = None
+        for i in range(L - 1, -1, -1):
+            Lr, plan = self.chain[i], self.plans[i]
+            dW = torch.empty_like(Lr["params"].weight, dtype=torch.float32)
+            B["wplans"][i].run(self.in_bufs[i], B["G"][i], B["ws"], dW, inv_S)
+            dWs[i] = dW
+            if i == 0 and not need_input_grad:
+                break
+            dX = B["dX"][i]
+            B["dplans"][i].forward(B["G"][i], dX.ptr)
+            pt, pl_, refl = B["fold"][i]
+            if i == 0:
+                d0 = self.plans[0].desc
+                input_grad = ops.fold_unpack(dX, pt, pl_, refl, self.N, B["dplans"][0].Cout8, d0.H, d0.W, in_channels, inv_S)
+                break
+            prev = self.chain[i - 1]
+            skip = dy_total.get(i + 1) if Lr.get("res") == "save" else None
+            dy_out = None
+            if prev.get("res") == "add":
+                rd = self.plans[i - 1].raw_desc()
+                slot = (i // 2) % 2                          # two live skip-gradient buffers alternate
+                key = (slot, rd.C8, rd.H, rd.W)
+                if key not in B["dy"]:
+                    B["dy"][key] = ops.P8Buffer(rd, self.device)
+                dy_out = B["dy"][key]
+                dy_total[i - 1] = dy_out
+            ops.in_bwd(dX, pt, pl_, refl, self.raw_bufs[i - 1], self.stats[i - 1], prev["act"], B["sums"], B["G"][i - 1],
+                       skip=skip, dy_out=dy_out)
+        return input_grad, dWs, db_last
+
     def feature(self, i: int) -> torch.Tensor:
         """Activation that feeds conv i (= output of layer i-1) as NCHW fp32 (D's intermediate features)."""
         return ops.unpack_nchw(self.in_bufs[i], self.chain[i]["params"].cin)
@@ -174,6 +277,38 @@ class _ChainEngine:
             if L.get("res") == "add":
                 res_src = None
         return self.out
+
+
+class _ChainFunction(torch.autograd.Function):
+    """Differentiable wrapper of a conv chain: forward and backward both run on the sm_100a kernels."""
+
+    @staticmethod
+    def forward(ctx, eng: "_ChainEngine", n_inputs: int, *tensors):
+        inputs, params = tensors[:n_inputs], tensors[n_inputs:]
+        ctx.eng, ctx.n_inputs = eng, n_inputs
+        ctx.in_channels = [t.shape[1] for t in inputs]
+        ctx.need_in = any(t.requires_grad for t in inputs)
+        out = eng.run([t.detach().float() for t in inputs])
+        return out.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        eng = ctx.eng
+        gin, dWs, db_last = eng.backward(grad_out, ctx.need_in, sum(ctx.in_channels))
+        eng.busy = False
+        grads_in = [None] * ctx.n_inputs
+        if gin is not None:
+            off = 0
+            for k, c in enumerate(ctx.in_channels):
+                grads_in[k] = gin[:, off:off + c].contiguous()
+                off += c
+        grads_p = []
+        L = len(eng.chain)
+        for i, Lr in enumerate(eng.chain):
+            grads_p.append(dWs[i])
+            # a bias in front of an affine-free InstanceNorm has exactly zero gradient; only the output layer's counts
+            grads_p.append(db_last if i == L - 1 else torch.zeros_like(Lr["params"].bias))
+        return (None, None) + tuple(grads_in) + tuple(grads_p)
 
 
 class GlobalGeneratorB200(nn.Module):
@@ -221,15 +356,29 @@ class GlobalGeneratorB200(nn.Module):
     def _final_act(self) -> int:
         return {"tanh": capi.ACT_TANH, "none": capi.ACT_NONE, "tanh_sigmoid_last": capi.ACT_TANH_SIGMOID_LAST}[self.final]
 
-    def engine(self, N: int, H: int, W: int) -> _ChainEngine:
+    def engine(self, N: int, H: int, W: int, train: bool = False) -> _ChainEngine:
         dev = self.model[1].weight.device
-        key = (N, H, W, dev.index)
+        if train:
+            # a training engine holds the activations its backward needs: one engine per forward call still
+            # waiting for its backward (e.g. two frames of one step), recycled afterwards
+            pool = self._engines.setdefault((N, H, W, dev.index, "train"), [])
+            eng = next((e for e in pool if not e.busy), None)
+            if eng is None:
+                if len(pool) >= 8:
+                    raise NhvrError("more than 8 forward passes of one module are waiting for backward")
+                capi.require_device()
+                eng = _ChainEngine(self._chain(), N, H, W, dev, self._final_act(), self.output_nc, train=True)
+                pool.append(eng)
+            eng.busy = True
+            eng.maybe_repack()
+            return eng
+        key = (N, H, W, dev.index, train)
         eng = self._engines.get(key)
         if eng is None:
             capi.require_device()
             if dev.type != "cuda":
                 raise NhvrError("GlobalGeneratorB200 parameters must live on a CUDA device (call .cuda()); no CPU path")
-            eng = _ChainEngine(self._chain(), N, H, W, dev, self._final_act(), self.output_nc)
+            eng = _ChainEngine(self._chain(), N, H, W, dev, self._final_act(), self.output_nc, train=train)
             self._engines[key] = eng
         eng.maybe_repack()
         return eng
@@ -237,10 +386,6 @@ class GlobalGeneratorB200(nn.Module):
     def forward(self, x, *more):
         """x (and optional further tensors, concatenated along C): NCHW fp32 CUDA -> NCHW fp32 CUDA."""
         xs = (x,) + tuple(more)
-        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or any(
-                t.requires_grad for t in xs)):
-            raise NhvrError("backward through the sm_100a conv chain is not built yet (forward/inference only); "
-                            "wrap the call in torch.no_grad()")
         for t in xs:
             if not t.is_cuda:
                 raise NhvrError("nhvr_b200 modules take CUDA tensors only (no CPU fallback)")
@@ -248,6 +393,12 @@ class GlobalGeneratorB200(nn.Module):
         if cin != self.input_nc:
             raise NhvrError("expected %d input channels, got %d" % (self.input_nc, cin))
         N, _, H, W = x.shape
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or any(t.requires_grad for t in xs)):
+            eng = self.engine(N, H, W, train=True)
+            params = []
+            for Lr in eng.chain:
+                params += [Lr["params"].weight, Lr["params"].bias]
+            return _ChainFunction.apply(eng, len(xs), *xs, *params)
         eng = self.engine(N, H, W)
         out = eng.run([t.float() for t in xs])
         return out

@@ -149,6 +149,72 @@ class ConvPlan:
                   "nhvr_conv_forward")
 
 
+class WgradPlan:
+    """Weight-gradient plan of one forward conv (nhvr_wgrad_*): dW from the forward's P8 input and the output
+    gradient stored in ``g_desc`` (which the matching dgrad conv also reads)."""
+
+    def __init__(self, fwd: "ConvPlan"):
+        h = C.c_void_p()
+        check(load().nhvr_wgrad_plan_create(C.byref(fwd.desc), C.byref(h)), "nhvr_wgrad_plan_create")
+        self.handle = h
+        self.g_desc = ActDesc()
+        check(load().nhvr_wgrad_grad_desc(h, C.byref(self.g_desc)), "nhvr_wgrad_grad_desc")
+        self.ws_bytes = load().nhvr_wgrad_workspace_bytes(h)
+        self.flops = fwd.flops
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                load().nhvr_wgrad_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def run(self, x: P8Buffer, g: P8Buffer, ws: torch.Tensor, dw: torch.Tensor, scale: float, accumulate: bool = False) -> None:
+        assert dw.dtype == torch.float32 and dw.is_contiguous() and ws.numel() >= self.ws_bytes
+        with _prof("wgrad", self.flops):
+            check(load().nhvr_wgrad(self.handle, x.ptr, g.ptr, ws.data_ptr(), dw.data_ptr(), scale, int(accumulate), stream_ptr()),
+                  "nhvr_wgrad")
+
+
+def conv_set_input_desc(plan: "ConvPlan", desc: ActDesc) -> None:
+    check(load().nhvr_conv_plan_set_input_desc(plan.handle, C.byref(desc)), "nhvr_conv_plan_set_input_desc")
+    plan.in_desc = desc.copy()
+
+
+def in_bwd(dx: P8Buffer, pad_t: int, pad_l: int, reflect: bool, raw: P8Buffer, stats: torch.Tensor, act: int, sums: torch.Tensor,
+           g: P8Buffer, skip: Optional[P8Buffer] = None, dy_out: Optional[P8Buffer] = None, eps: float = 1e-5) -> None:
+    work = _act_interior_bytes(raw.desc) * (4.0 + (1.0 if skip is not None else 0.0))
+    with _prof("in_bwd", work):
+        check(load().nhvr_in_bwd(dx.ptr, dx.desc.H, dx.desc.W, pad_t, pad_l, int(reflect), skip.ptr if skip is not None else None,
+                                 raw.ptr, C.byref(raw.desc), stats.data_ptr(), eps, act, sums.data_ptr(), g.ptr, C.byref(g.desc),
+                                 dy_out.ptr if dy_out is not None else None, stream_ptr()), "nhvr_in_bwd")
+
+
+def fold_unpack(dx: P8Buffer, pad_t: int, pad_l: int, reflect: bool, N: int, C8: int, H: int, W: int, channels: int,
+                scale: float) -> torch.Tensor:
+    out = torch.empty(N, channels, H, W, dtype=torch.float32, device=dx.mem.device)
+    d = make_desc(N, C8, H, W)
+    check(load().nhvr_fold_unpack(dx.ptr, dx.desc.H, dx.desc.W, pad_t, pad_l, int(reflect), C.byref(d), out.data_ptr(), channels,
+                                  scale, stream_ptr()), "nhvr_fold_unpack")
+    return out
+
+
+def head_bwd(out: torch.Tensor, grad_out: torch.Tensor, act: int, scale: float) -> torch.Tensor:
+    N, Cc, H, W = out.shape
+    g = torch.empty_like(out)
+    check(load().nhvr_head_bwd(out.data_ptr(), grad_out.data_ptr(), N, Cc, H, W, act, scale, g.data_ptr(), stream_ptr()),
+          "nhvr_head_bwd")
+    return g
+
+
+def bias_grad(g: torch.Tensor, scale: float) -> torch.Tensor:
+    N, Cc, H, W = g.shape
+    db = torch.empty(Cc, dtype=torch.float32, device=g.device)
+    check(load().nhvr_bias_grad(g.data_ptr(), N, Cc, H, W, scale, 0, db.data_ptr(), stream_ptr()), "nhvr_bias_grad")
+    return db
+
+
 def in_apply(raw: P8Buffer, stats: torch.Tensor, act: int, dst: P8Buffer, residual: Optional[P8Buffer] = None,
              eps: float = 1e-5) -> None:
     # algorithmic bytes: read raw (+ residual), write the interior once
