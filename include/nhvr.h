@@ -69,6 +69,7 @@ typedef struct nhvr_conv_desc {
   int32_t halo;          /* NHVR_HALO_* the input must carry (reflect for ReflectionPad2d, zero for padding=) */
   int32_t epilogue;      /* NHVR_EPI_* */
   int32_t act;           /* NHVR_ACT_* (epilogues 1, 2) */
+  int32_t in_extra_rows; /* extra zero rows below the input's bottom halo (gradient buffers shared with wgrad) */
 } nhvr_conv_desc;
 
 typedef struct nhvr_conv_plan nhvr_conv_plan;   /* opaque, host memory only */
@@ -194,6 +195,10 @@ int nhvr_loss_sum_sq_const(const float* a, float target, int64_t n, double* acc,
  * acc3[1] += foreground pixel count; acc3[2] += sum of 25-way cross-entropy of the part logits. */
 int nhvr_loss_uv_prob(const float* uvp, const int32_t* dp_i, const float* dp_uv, int32_t N, int32_t H, int32_t W,
                       double* acc3, void* stream);
+/* d(w_uv*uv_loss + w_prob*prob_loss)/d uvp -> grad float [N][73][H][W], times *grad_scale (device scalar, nullable);
+ * acc3 = the forward's sums (device): the foreground count is read on the device, no host round trip. */
+int nhvr_loss_uv_prob_bwd(const float* uvp, const int32_t* dp_i, const float* dp_uv, int32_t N, int32_t H, int32_t W,
+                          const double* acc3, float w_uv, float w_prob, const float* grad_scale, float* grad, void* stream);
 /* acc += sum |cur - warp(prev, flow)|, flow float [N][2][H][W] in pixels (dx, dy), bilinear, border clamp. */
 int nhvr_loss_temporal(const float* cur, const float* prev, const float* flow, int32_t N, int32_t C, int32_t H,
                        int32_t W, double* acc, void* stream);

@@ -34,7 +34,7 @@ class ActDesc(C.Structure):
 
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
-                ("kind", "Cin", "Cout", "kh", "kw", "stride", "pad", "N", "H", "W", "halo", "epilogue", "act")]
+                ("kind", "Cin", "Cout", "kh", "kw", "stride", "pad", "N", "H", "W", "halo", "epilogue", "act", "in_extra_rows")]
 
 
 # every symbol include/nhvr.h declares: name -> (restype, argtypes)
@@ -80,6 +80,7 @@ SYMBOLS = {
     "nhvr_loss_sum_abs_diff": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "nhvr_loss_sum_sq_const": (C.c_int, [_P, C.c_float, C.c_int64, _P, _P]),
     "nhvr_loss_uv_prob": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "nhvr_loss_uv_prob_bwd": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_float, C.c_float, _P, _P, _P]),
     "nhvr_loss_temporal": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "nhvr_avgpool3s2": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
 }

@@ -411,6 +411,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
     K.Wrow = Wpi; K.Hv = Ho; K.Wv = Wo; K.oys = K.oxs = 1;
   } else if (d->kind == NHVR_CONV && d->stride == 2) {
     in.pad_t = in.pad_b = in.pad_l = in.pad_r = d->pad;
+    in.pad_b += d->in_extra_rows;
     in.split = 1;
     ActGeom g = make_geom(in);
     const int Hq = g.Hp / 2, Wq = g.Wp / 2;
@@ -569,6 +570,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   p->smem_bytes = (size_t)SA * kcp * slab * 16 + (size_t)SB * bpb * b_block + (size_t)(2 * SA + 2 * SB + 1) * 8 + 8 +
                   (size_t)Npad * 8 + 128;
 
+  if (!(d->kind == NHVR_CONV && d->stride == 2)) in.pad_b += d->in_extra_rows;   // plain formats: only the plane stride grows
   ActGeom gin = make_geom(in);
   K.in_plane_units = gin.plane_units;
   const int64_t last_q = (int64_t)(K.Hv - 1) * K.Wrow + K.Wv;   // one past the last valid linear position
@@ -602,6 +604,7 @@ extern "C" int nhvr_conv_plan_set_input_desc(nhvr_conv_plan* p, const nhvr_act_d
   if (a.N != b.N || a.C8 != b.C8 || a.Wp != b.Wp || a.pad_t != b.pad_t || a.pad_l != b.pad_l || a.split != b.split ||
       a.H != b.H || a.W != b.W || b.Hp < a.Hp)
     return NHVR_ERR_SHAPE;
+  if (a.split && b.Hp != a.Hp) return NHVR_ERR_SHAPE;   // parity-plane offsets depend on Hp: create the plan with in_extra_rows
   p->in_desc = *desc;
   p->kp.in_plane_units = b.plane_units;
   return NHVR_OK;

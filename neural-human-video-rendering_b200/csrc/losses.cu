@@ -114,6 +114,47 @@ __global__ void __launch_bounds__(256) loss_temporal_kernel(const float* __restr
   block_accumulate<1>(s, acc);
 }
 
+// gradient of  w_uv * uv_loss + w_prob * prob_loss  w.r.t. uvp (all 73 channels written), times *gscale.
+// acc3 are the forward sums (acc3[1] = foreground count) so no host round trip is needed.
+__global__ void __launch_bounds__(256) loss_uv_prob_bwd_kernel(const float* __restrict__ uvp, const int32_t* __restrict__ dp_i,
+                                                               const float* __restrict__ dp_uv, int N, int64_t HW, const double* acc3,
+                                                               float w_uv, float w_prob, const float* gscale, float* __restrict__ grad) {
+  const int64_t total = (int64_t)N * HW;
+  const float gs = gscale ? *gscale : 1.f;
+  const float cuv = gs * w_uv / (float)fmax(acc3[1], 1.0);
+  const float cpr = gs * w_prob / (float)total;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / HW);
+    const int64_t pix = idx - (int64_t)n * HW;
+    const float* base = uvp + (int64_t)n * 73 * HW + pix;
+    float* gb = grad + (int64_t)n * 73 * HW + pix;
+    const int part = dp_i[idx];
+    float lg[25], mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) { lg[k] = __ldg(base + (int64_t)k * HW); mx = fmaxf(mx, lg[k]); }
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) { lg[k] = expf(lg[k] - mx); den += lg[k]; }
+    const float inv = 1.f / den;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) gb[(int64_t)k * HW] = cpr * (lg[k] * inv - (k == part ? 1.f : 0.f));
+    for (int k = 1; k <= 24; ++k) {
+      float gu = 0.f, gv = 0.f;
+      if (k == part) {
+        const float xu = __ldg(base + (int64_t)(24 + k) * HW), xv = __ldg(base + (int64_t)(48 + k) * HW);
+        const float tu = xu * 0.5f + 0.5f, tv = xv * 0.5f + 0.5f;
+        const float u = fminf(fmaxf(tu, 0.f), 1.f), v = fminf(fmaxf(tv, 0.f), 1.f);
+        const float du = u - __ldg(dp_uv + (int64_t)n * 2 * HW + pix), dv = v - __ldg(dp_uv + ((int64_t)n * 2 + 1) * HW + pix);
+        // d|t|/dt = sign(t) (0 at 0); clamp passes the gradient on the closed interval, as torch.clamp does
+        if (tu >= 0.f && tu <= 1.f) gu = 0.5f * cuv * (du > 0.f ? 1.f : (du < 0.f ? -1.f : 0.f));
+        if (tv >= 0.f && tv <= 1.f) gv = 0.5f * cuv * (dv > 0.f ? 1.f : (dv < 0.f ? -1.f : 0.f));
+      }
+      gb[(int64_t)(24 + k) * HW] = gu;
+      gb[(int64_t)(48 + k) * HW] = gv;
+    }
+  }
+}
+
 // AvgPool2d(kernel 3, stride 2, padding 1, count_include_pad=False) on NCHW fp32
 __global__ void __launch_bounds__(256) avgpool3s2_kernel(const float* __restrict__ in, int64_t planes, int H, int W, int Ho, int Wo,
                                                          float* __restrict__ out) {
@@ -182,6 +223,16 @@ extern "C" int nhvr_loss_uv_prob(const float* uvp, const int32_t* dp_i, const fl
   if (N <= 0 || H <= 0 || W <= 0) return NHVR_ERR_SHAPE;
   if (!arch_ok_cached()) return NHVR_ERR_ARCH;
   loss_uv_prob_kernel<<<blocks_for((int64_t)N * H * W), 256, 0, (cudaStream_t)stream>>>(uvp, dp_i, dp_uv, N, (int64_t)H * W, acc3);
+  NHVR_POST_LAUNCH();
+}
+extern "C" int nhvr_loss_uv_prob_bwd(const float* uvp, const int32_t* dp_i, const float* dp_uv, int32_t N, int32_t H, int32_t W,
+                                     const double* acc3, float w_uv, float w_prob, const float* grad_scale, float* grad,
+                                     void* stream) {
+  if (!uvp || !dp_i || !dp_uv || !acc3 || !grad) return NHVR_ERR_NULL;
+  if (N <= 0 || H <= 0 || W <= 0) return NHVR_ERR_SHAPE;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  loss_uv_prob_bwd_kernel<<<blocks_for((int64_t)N * H * W), 256, 0, (cudaStream_t)stream>>>(uvp, dp_i, dp_uv, N, (int64_t)H * W, acc3,
+                                                                                            w_uv, w_prob, grad_scale, grad);
   NHVR_POST_LAUNCH();
 }
 extern "C" int nhvr_loss_temporal(const float* cur, const float* prev, const float* flow, int32_t N, int32_t C, int32_t H,

@@ -80,3 +80,35 @@ def temporal_loss(out_t: torch.Tensor, out_prev: torch.Tensor, flow_inv: torch.T
     check(load().nhvr_loss_temporal(cur.data_ptr(), prev.data_ptr(), fl.data_ptr(), N, C, H, W, acc.data_ptr(), stream_ptr()),
           "nhvr_loss_temporal")
     return acc[0] / cur.numel()
+
+
+class _UVProbLoss(torch.autograd.Function):
+    """lambda_UV * uv_loss + lambda_Prob * prob_loss with its gradient w.r.t. the UV-generator output, both on
+    the sm_100a reduction kernels (the UV-generator pre-train objective, REF pretrainTrans.sh; pretrain_start.sh:32-33)."""
+
+    @staticmethod
+    def forward(ctx, uvp, dp_i, dp_uv, w_uv, w_prob):
+        u, d = _f32(uvp), _f32(dp_uv)
+        dp = dp_i.detach().contiguous().to(torch.int32)
+        N, _, H, W = u.shape
+        acc = _acc(u.device, 3)
+        check(load().nhvr_loss_uv_prob(u.data_ptr(), dp.data_ptr(), d.data_ptr(), N, H, W, acc.data_ptr(), stream_ptr()),
+              "nhvr_loss_uv_prob")
+        ctx.saved = (u, dp, d, acc, float(w_uv), float(w_prob))
+        loss = w_uv * acc[0] / torch.clamp(acc[1], min=1.0) + w_prob * acc[2] / (N * H * W)
+        return loss.float()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        u, dp, d, acc, w_uv, w_prob = ctx.saved
+        N, _, H, W = u.shape
+        grad = torch.empty_like(u)
+        gs = grad_out.detach().reshape(1).float().contiguous()
+        check(load().nhvr_loss_uv_prob_bwd(u.data_ptr(), dp.data_ptr(), d.data_ptr(), N, H, W, acc.data_ptr(), w_uv, w_prob,
+                                           gs.data_ptr(), grad.data_ptr(), stream_ptr()), "nhvr_loss_uv_prob_bwd")
+        return grad, None, None, None, None
+
+
+def uv_prob_objective(uvp, dp_i, dp_uv, lambda_uv: float = 1000.0, lambda_prob: float = 10.0) -> torch.Tensor:
+    """Differentiable  lambda_UV * uv_loss + lambda_Prob * prob_loss  (0-dim fp32 CUDA tensor)."""
+    return _UVProbLoss.apply(uvp, dp_i, dp_uv, lambda_uv, lambda_prob)

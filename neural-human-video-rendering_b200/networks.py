@@ -166,14 +166,15 @@ class _ChainEngine:
             wp = ops.WgradPlan(plan)
             B["wplans"].append(wp)
             ws_bytes = max(ws_bytes, wp.ws_bytes)
-            k = key_of(wp.g_desc)
+            k = key_of(wp.g_desc) + ((i,) if __import__("os").environ.get("NHVR_DEBUG_KEEP") else ())
             if k not in gpool:
                 gpool[k] = ops.P8Buffer(wp.g_desc.copy(), dev)
             B["G"][i] = gpool[k]
             p: _ConvParams = Lr["params"]
             d = plan.desc
             if p.transposed:          # dgrad of a transposed conv = the stride-2 conv of the gradient
-                dp = ops.ConvPlan(capi.CONV, p.cout, p.cin, p.k, 2, p.pad, self.N, plan.Ho, plan.Wo, capi.HALO_ZERO, capi.EPI_RAW_P8)
+                dp = ops.ConvPlan(capi.CONV, p.cout, p.cin, p.k, 2, p.pad, self.N, plan.Ho, plan.Wo, capi.HALO_ZERO, capi.EPI_RAW_P8,
+                                  in_extra_rows=wp.g_desc.pad_b - p.pad)
                 fold = (0, 0, False)
             elif p.stride == 2:       # dgrad of a stride-2 conv = the transposed conv of the gradient
                 if p.k != 3 or p.pad != 1 or (d.H % 2) or (d.W % 2):
@@ -215,6 +216,7 @@ class _ChainEngine:
         amax = float(grad_out.abs().max())
         S = 1.0 if amax == 0.0 or not (amax == amax) else 2.0 ** round(__import__("math").log2(64.0 / amax))
         inv_S = 1.0 / S
+        self._last_S = S
         g_pre = ops.head_bwd(self.out, grad_out, self.final_act, S)
         db_last = ops.bias_grad(g_pre, inv_S)
         ops.pack_nchw([g_pre], B["G"][L - 1])

@@ -93,8 +93,9 @@ def unpack_nchw(src: P8Buffer, channels: int, out: Optional[torch.Tensor] = None
 class ConvPlan:
     """One conv layer lowered to the tcgen05 shift-GEMM kernel (nhvr_conv_plan_*)."""
 
-    def __init__(self, kind, Cin, Cout, k, stride, pad, N, H, W, halo, epilogue, act=capi.ACT_NONE):
+    def __init__(self, kind, Cin, Cout, k, stride, pad, N, H, W, halo, epilogue, act=capi.ACT_NONE, in_extra_rows=0):
         d = ConvDesc()
+        d.in_extra_rows = in_extra_rows
         d.kind, d.Cin, d.Cout, d.kh, d.kw, d.stride, d.pad = kind, Cin, Cout, k, k, stride, pad
         d.N, d.H, d.W, d.halo, d.epilogue, d.act = N, H, W, halo, epilogue, act
         self.desc = d
