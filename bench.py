@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--clips", type=int, default=4, help="independent clips advanced in lock-step per GPU")
     ap.add_argument("--impl", type=str, default="b200")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_train", action="store_true", help="skip the configs[1] training leg")
+    ap.add_argument("--train_batch", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -286,6 +288,38 @@ def main():
                                  "frac": w / s / 1e9 / pk["hbm_gbs"], "launches_per_step": n // 3,
                                  "ms_per_step": 1e3 * s / 3}
 
+    # ---------------------------------------------------------------- training leg: configs[1] UV-generator pre-train
+    train = None
+    if not args.no_train:
+        from nhvr_b200.networks import define_G
+        from nhvr_b200.train import UVPretrainer, synthetic_densepose
+        del step, pipe, flush
+        torch.cuda.empty_cache()
+        TB, TS = args.train_batch, 256
+        netT = define_G(3, 73, 64, "translate", 2, 5, gpu_ids=[local])
+        trainer = UVPretrainer(netT, distributed=world > 1)
+        pose, dp_i, dp_uv = synthetic_densepose(TB, TS, TS, dev, seed=rank)
+        for _ in range(3):
+            trainer.step(pose, dp_i, dp_uv)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        KT = max(5, min(K, 20))
+        t0.record()
+        for _ in range(KT):
+            last = trainer.step(pose, dp_i, dp_uv)
+        t1.record()
+        barrier()
+        tt = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tms = float(tt.item()) / KT
+        eng = [e for v in netT._engines.values() if isinstance(v, list) for e in v][0]
+        fwd_flops = eng.flops
+        train = {"workload": "configs[1]: UV generator pre-train fwd+bwd+Adam, %dx%d, batch %d/GPU, synthetic DensePose targets%s"
+                             % (TS, TS, TB, ", NCCL gradient all-reduce" if world > 1 else ""),
+                 "steps_per_s": 1000.0 / tms, "ms_per_step": tms, "samples_per_s": world * TB * 1000.0 / tms,
+                 "conv_tflops_fwd_dgrad_wgrad": 3.0 * fwd_flops / (tms * 1e-3) / 1e12, "final_loss": float(last)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         fps, n, cores = cpu_oracle_fps(15.0)
@@ -300,7 +334,7 @@ def main():
                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "frames_checksum": checksum},
                "gpu_launches": int(step.launches_per_step * K), "roofline": roof, "roofline_memory_kernels": kernels,
-               "cpu_baseline": cpu}
+               "cpu_baseline": cpu, "train": train}
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
