@@ -290,9 +290,11 @@ def main():
 
     # ---------------------------------------------------------------- training leg: configs[1] UV-generator pre-train
     train = None
+    launches_per_step = step.launches_per_step
     if not args.no_train:
         from nhvr_b200.networks import define_G
         from nhvr_b200.train import UVPretrainer, synthetic_densepose
+        launches_per_step = step.launches_per_step
         del step, pipe, flush
         torch.cuda.empty_cache()
         TB, TS = args.train_batch, 256
@@ -333,7 +335,7 @@ def main():
                "config": workload_config(B), "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "frames_checksum": checksum},
-               "gpu_launches": int(step.launches_per_step * K), "roofline": roof, "roofline_memory_kernels": kernels,
+               "gpu_launches": int(launches_per_step * K), "roofline": roof, "roofline_memory_kernels": kernels,
                "cpu_baseline": cpu, "train": train}
         print(json.dumps(out))
     if dist is not None:

@@ -286,7 +286,7 @@ def test_generator_backward_parity(cuda_dev, netG, cin, cout, ngf, nd, nb, size,
     is exact for the forward that was executed; against the fp32 oracle the difference is dominated by ReLU
     masks that flip where |z| is below the 16-bit rounding of the stored conv output (a fraction f of the
     pixels gives a relative gradient error of sqrt(f)); measured on the full 26-conv generator: cosine 0.996-1.0,
-    max error 6-14 % of each tensor's max (profiles/r01_grad_probe.log).  Bounds here: cosine >= 0.995, 25 %."""
+    max error 6-14 % of each tensor's max (profiles/r01_grad_probe.log).  Bounds: cosine >= 0.995, relative L2 <= 10 %."""
     net, ref = _pair_G(cuda_dev, cin, cout, ngf, netG, nd, nb, seed=31)
     torch.manual_seed(32)
     x = (torch.rand(batch, cin, size, size, device=cuda_dev) * 2 - 1).requires_grad_(True)
@@ -309,8 +309,10 @@ def test_generator_backward_parity(cuda_dev, netG, cin, cout, ngf, nd, nb, size,
         cos = torch.nn.functional.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0).item()
         if name.endswith(".bias") and name != list(dict(net.named_parameters()))[-1]:
             continue                                         # oracle's IN-cancelled bias grads are round-off noise
-        assert err <= 2.5e-1 * scale + 1e-12, (name, err, scale)
+        rel_l2 = ((a - b).double().norm() / b.double().norm().clamp(min=1e-30)).item()
+        assert rel_l2 <= 1.0e-1, (name, rel_l2)
         assert cos >= 0.995, (name, cos)
+        assert err <= 5e-1 * scale + 1e-12, (name, err, scale)     # sparse mask flips: loose on the max norm
 
 
 def test_generator_two_forwards_one_backward(cuda_dev):
