@@ -163,6 +163,15 @@ size_t nhvr_wgrad_workspace_bytes(const nhvr_wgrad_plan* p);
 int nhvr_wgrad(const nhvr_wgrad_plan* p, const void* x, const void* g, void* workspace, float* dw, float scale,
                int32_t accumulate, void* stream);
 
+/* ---- backward of the texture lookup (use_mask_texture variant) and of the composite ----
+ * grad_uvp float [N][73][H][W] is fully written; grad_atlas float [24][S][S][Ct4] (channels-last, zeroed by the
+ * caller) receives vector reductions. */
+int nhvr_texture_sample_bwd(const float* uvp, const float* atlas, const float* grad_tex, int32_t N, int32_t H, int32_t W,
+                            int32_t S, int32_t Ctex, float* grad_uvp, float* grad_atlas, void* stream);
+/* grad_fgm float [N][4][H][W]; grad_bg float [3][H][W] (summed over the batch) or [N][3][H][W] if bg_batched */
+int nhvr_composite_bwd(const float* fgm, const float* bg, int32_t bg_batched, const float* grad_out, int32_t N, int32_t H,
+                       int32_t W, float* grad_fgm, float* grad_bg, void* stream);
+
 /* ---- backward of  x_next = pad(act(InstanceNorm(raw)) [+ residual]) ----
  * dx: gradient w.r.t. the PADDED x_next as an un-padded P8 buffer [N][C8][dx_H][dx_W] (the dgrad conv's
  * RAW_P8 output); the interior starts at (pad_t, pad_l); reflect != 0 folds the mirrored halo gradients
@@ -195,6 +204,12 @@ int nhvr_loss_sum_sq_const(const float* a, float target, int64_t n, double* acc,
  * acc3[1] += foreground pixel count; acc3[2] += sum of 25-way cross-entropy of the part logits. */
 int nhvr_loss_uv_prob(const float* uvp, const int32_t* dp_i, const float* dp_uv, int32_t N, int32_t H, int32_t W,
                       double* acc3, void* stream);
+/* gradient w.r.t. a of  coef * mean(...)  for mode 0: (a-b)^2, 1: |a-b|, 2: (a-target)^2; times *grad_scale (device
+ * scalar, nullable); grad_a = (accumulate ? grad_a : 0) + ... */
+int nhvr_loss_pair_bwd(const float* a, const float* b, int64_t n, int32_t mode, float target, float coef,
+                       const float* grad_scale, int32_t accumulate, float* grad_a, void* stream);
+int nhvr_avgpool3s2_bwd(const float* grad_out, int32_t N, int32_t C, int32_t H, int32_t W, int32_t accumulate, float* grad_in,
+                        void* stream);
 /* d(w_uv*uv_loss + w_prob*prob_loss)/d uvp -> grad float [N][73][H][W], times *grad_scale (device scalar, nullable);
  * acc3 = the forward's sums (device): the foreground count is read on the device, no host round trip. */
 int nhvr_loss_uv_prob_bwd(const float* uvp, const int32_t* dp_i, const float* dp_uv, int32_t N, int32_t H, int32_t W,

@@ -155,6 +155,39 @@ __global__ void __launch_bounds__(256) loss_uv_prob_bwd_kernel(const float* __re
   }
 }
 
+// gradient of the mean reductions w.r.t. a:  mode 0: 2(a-b)/n   mode 1: sign(a-b)/n   mode 2: 2(a-c)/n ; times coef * *gscale
+__global__ void __launch_bounds__(256) loss_pair_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, int mode,
+                                                            float c, float coef, const float* gscale, int accumulate, float* __restrict__ ga) {
+  const float k = coef * (gscale ? *gscale : 1.f) / (float)n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = a[i] - (mode == 2 ? c : b[i]);
+    const float g = (mode == 1) ? (d > 0.f ? k : (d < 0.f ? -k : 0.f)) : 2.f * k * d;
+    ga[i] = accumulate ? ga[i] + g : g;
+  }
+}
+
+// backward of AvgPool2d(3, s2, p1, count_include_pad=False): gin (+)= sum over the windows containing the pixel of gout / count
+__global__ void __launch_bounds__(256) avgpool3s2_bwd_kernel(const float* __restrict__ gout, int64_t planes, int H, int W, int Ho, int Wo,
+                                                             int accumulate, float* __restrict__ gin) {
+  const int64_t total = planes * H * W;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % W);
+    const int y = (int)((idx / W) % H);
+    const int64_t pl = idx / ((int64_t)W * H);
+    float s = 0.f;
+    // windows (yo, xo) with |2*yo - y| <= 1
+    const int yo0 = max((y - 1 + 1) / 2, 0), yo1 = min((y + 1) / 2, Ho - 1);
+    const int xo0 = max((x - 1 + 1) / 2, 0), xo1 = min((x + 1) / 2, Wo - 1);
+    for (int yo = yo0; yo <= yo1; ++yo)
+      for (int xo = xo0; xo <= xo1; ++xo) {
+        const int cy = min(2 * yo + 1, H - 1) - max(2 * yo - 1, 0) + 1;
+        const int cx = min(2 * xo + 1, W - 1) - max(2 * xo - 1, 0) + 1;
+        s += gout[(pl * Ho + yo) * Wo + xo] / (float)(cy * cx);
+      }
+    gin[idx] = accumulate ? gin[idx] + s : s;
+  }
+}
+
 // AvgPool2d(kernel 3, stride 2, padding 1, count_include_pad=False) on NCHW fp32
 __global__ void __launch_bounds__(256) avgpool3s2_kernel(const float* __restrict__ in, int64_t planes, int H, int W, int Ho, int Wo,
                                                          float* __restrict__ out) {
@@ -241,6 +274,24 @@ extern "C" int nhvr_loss_temporal(const float* cur, const float* prev, const flo
   if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return NHVR_ERR_SHAPE;
   if (!arch_ok_cached()) return NHVR_ERR_ARCH;
   loss_temporal_kernel<<<blocks_for((int64_t)N * H * W), 256, 0, (cudaStream_t)stream>>>(cur, prev, flow, N, C, H, W, acc);
+  NHVR_POST_LAUNCH();
+}
+extern "C" int nhvr_loss_pair_bwd(const float* a, const float* b, int64_t n, int32_t mode, float target, float coef,
+                                  const float* grad_scale, int32_t accumulate, float* grad_a, void* stream) {
+  if (!a || !grad_a || (mode != 2 && !b)) return NHVR_ERR_NULL;
+  if (n <= 0 || mode < 0 || mode > 2) return NHVR_ERR_SHAPE;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  loss_pair_bwd_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(a, b, n, mode, target, coef, grad_scale, accumulate, grad_a);
+  NHVR_POST_LAUNCH();
+}
+extern "C" int nhvr_avgpool3s2_bwd(const float* grad_out, int32_t N, int32_t C, int32_t H, int32_t W, int32_t accumulate, float* grad_in,
+                                   void* stream) {
+  if (!grad_out || !grad_in) return NHVR_ERR_NULL;
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return NHVR_ERR_SHAPE;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  avgpool3s2_bwd_kernel<<<blocks_for((int64_t)N * C * H * W), 256, 0, (cudaStream_t)stream>>>(grad_out, (int64_t)N * C, H, W, Ho, Wo,
+                                                                                              accumulate, grad_in);
   NHVR_POST_LAUNCH();
 }
 extern "C" int nhvr_avgpool3s2(const float* in, int32_t N, int32_t C, int32_t H, int32_t W, float* out, void* stream) {

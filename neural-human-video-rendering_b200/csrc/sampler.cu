@@ -194,3 +194,160 @@ extern "C" int nhvr_composite(const float* fgm, const float* bg, int32_t bg_batc
   if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
   return NHVR_OK;
 }
+
+// =================================================================================================
+// backward of the texture lookup (use_mask_texture variant) and of the composite
+// =================================================================================================
+namespace nhvr {
+
+// tex_c = sum_{k>=1} P_k * s_kc,  s_kc = bilinear(T_k; fx_k, fy_k)
+//   d tex_c / d logit_j = P_j * (s_jc [j>=1] - tex_c)
+//   d tex_c / d U_k     = P_k * ds_kc/dfx * (S-1)/2 * [0 <= U/2+1/2 <= 1]          (same for V)
+//   d tex_c / d T_k[corner] = P_k * w_corner
+// Atlas gradient: vector reductions into a channels-last fp32 buffer [24][S][S][4G] (zeroed by the caller).
+template <int G>
+__global__ void __launch_bounds__(128) texture_sample_bwd_kernel(const float* __restrict__ uvp, const float4* __restrict__ atlas,
+                                                                 const float* __restrict__ gtex, int N, int H, int W, int S, int Ctex,
+                                                                 float* __restrict__ guvp, float* __restrict__ gatlas) {
+  const int64_t HW = (int64_t)H * W;
+  const int64_t total = (int64_t)N * HW;
+  const float sm1 = (float)(S - 1);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / HW);
+    const int64_t pix = idx - (int64_t)n * HW;
+    const float* base = uvp + (int64_t)n * 73 * HW + pix;
+    float* gb = guvp + (int64_t)n * 73 * HW + pix;
+    float g[4 * G];
+#pragma unroll
+    for (int c = 0; c < 4 * G; ++c) g[c] = c < Ctex ? __ldg(gtex + ((int64_t)n * Ctex + c) * HW + pix) : 0.f;
+
+    float lg[25], mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) { lg[k] = __ldg(base + (int64_t)k * HW); mx = fmaxf(mx, lg[k]); }
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) { lg[k] = __expf(lg[k] - mx); den += lg[k]; }
+    const float inv_den = 1.f / den;
+    float tdot = 0.f;           // sum_c g_c * tex_c = sum_k P_k a_k
+    float a[25];
+    a[0] = 0.f;
+#pragma unroll
+    for (int k = 1; k <= kParts; ++k) {
+      const float tu = __fadd_rn(__fmul_rn(__ldg(base + (int64_t)(24 + k) * HW), 0.5f), 0.5f);
+      const float tv = __fadd_rn(__fmul_rn(__ldg(base + (int64_t)(48 + k) * HW), 0.5f), 0.5f);
+      const float u = fminf(fmaxf(tu, 0.f), 1.f), v = fminf(fmaxf(tv, 0.f), 1.f);
+      const float fx = __fmul_rn(u, sm1), fy = __fmul_rn(v, sm1);
+      const float x0f = floorf(fx), y0f = floorf(fy);
+      const int x0 = (int)x0f, y0 = (int)y0f;
+      const int x1 = min(x0 + 1, S - 1), y1 = min(y0 + 1, S - 1);
+      const float wx = fx - x0f, wy = fy - y0f;
+      const float pk = lg[k] * inv_den;
+      const int64_t tb = (int64_t)(k - 1) * S * S;
+      const int64_t i00 = (tb + (int64_t)y0 * S + x0) * G, i01 = (tb + (int64_t)y0 * S + x1) * G;
+      const int64_t i10 = (tb + (int64_t)y1 * S + x0) * G, i11 = (tb + (int64_t)y1 * S + x1) * G;
+      const float w00 = (1.f - wy) * (1.f - wx), w01 = (1.f - wy) * wx, w10 = wy * (1.f - wx), w11 = wy * wx;
+      float ak = 0.f, dfx = 0.f, dfy = 0.f;
+#pragma unroll
+      for (int q = 0; q < G; ++q) {
+        const float4 A = __ldg(atlas + i00 + q), B = __ldg(atlas + i01 + q), Cc = __ldg(atlas + i10 + q), D = __ldg(atlas + i11 + q);
+        const float av[4] = {A.x, A.y, A.z, A.w}, bv[4] = {B.x, B.y, B.z, B.w}, cv[4] = {Cc.x, Cc.y, Cc.z, Cc.w}, dv[4] = {D.x, D.y, D.z, D.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float gc = g[q * 4 + e];
+          ak += gc * (w00 * av[e] + w01 * bv[e] + w10 * cv[e] + w11 * dv[e]);
+          dfx += gc * ((1.f - wy) * (bv[e] - av[e]) + wy * (dv[e] - cv[e]));
+          dfy += gc * ((1.f - wx) * (cv[e] - av[e]) + wx * (dv[e] - bv[e]));
+        }
+        // atlas gradient (vector reduction per corner)
+        const float s00 = pk * w00, s01 = pk * w01, s10 = pk * w10, s11 = pk * w11;
+        float* ga = gatlas;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ga + (i00 + q) * 4), "f"(s00 * g[q * 4]), "f"(s00 * g[q * 4 + 1]),
+                     "f"(s00 * g[q * 4 + 2]), "f"(s00 * g[q * 4 + 3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ga + (i01 + q) * 4), "f"(s01 * g[q * 4]), "f"(s01 * g[q * 4 + 1]),
+                     "f"(s01 * g[q * 4 + 2]), "f"(s01 * g[q * 4 + 3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ga + (i10 + q) * 4), "f"(s10 * g[q * 4]), "f"(s10 * g[q * 4 + 1]),
+                     "f"(s10 * g[q * 4 + 2]), "f"(s10 * g[q * 4 + 3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ga + (i11 + q) * 4), "f"(s11 * g[q * 4]), "f"(s11 * g[q * 4 + 1]),
+                     "f"(s11 * g[q * 4 + 2]), "f"(s11 * g[q * 4 + 3]) : "memory");
+      }
+      a[k] = ak;
+      tdot += pk * ak;
+      const float cu = (tu >= 0.f && tu <= 1.f) ? 0.5f * sm1 * pk : 0.f;
+      const float cv2 = (tv >= 0.f && tv <= 1.f) ? 0.5f * sm1 * pk : 0.f;
+      gb[(int64_t)(24 + k) * HW] = cu * dfx;
+      gb[(int64_t)(48 + k) * HW] = cv2 * dfy;
+    }
+#pragma unroll
+    for (int k = 0; k < 25; ++k) gb[(int64_t)k * HW] = lg[k] * inv_den * (a[k] - tdot);
+  }
+}
+
+// out = m*fg + (1-m)*bg :  g_fg = m*g,  g_m = sum_c g_c (fg_c - bg_c),  g_bg = (1-m)*g (summed over the batch when bg is shared)
+__global__ void __launch_bounds__(256) composite_bwd_kernel(const float* __restrict__ fgm, const float* __restrict__ bg, int bg_batched,
+                                                            const float* __restrict__ gout, int N, int64_t HW, float* __restrict__ gfgm,
+                                                            float* __restrict__ gbg) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int n = 0; n < N; ++n) {
+      const float m = fgm[((int64_t)n * 4 + 3) * HW + p];
+      float gm = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float go = gout[((int64_t)n * 3 + c) * HW + p];
+        const float fg = fgm[((int64_t)n * 4 + c) * HW + p];
+        const float bb = bg[((bg_batched ? (int64_t)n * 3 : 0) + c) * HW + p];
+        gfgm[((int64_t)n * 4 + c) * HW + p] = m * go;
+        gm += go * (fg - bb);
+        if (bg_batched) gbg[((int64_t)n * 3 + c) * HW + p] = (1.f - m) * go;
+        else acc[c] += (1.f - m) * go;
+      }
+      gfgm[((int64_t)n * 4 + 3) * HW + p] = gm;
+    }
+    if (!bg_batched) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gbg[(int64_t)c * HW + p] = acc[c];
+    }
+  }
+}
+
+}  // namespace nhvr
+
+extern "C" int nhvr_texture_sample_bwd(const float* uvp, const float* atlas, const float* grad_tex, int32_t N, int32_t H, int32_t W,
+                                       int32_t S, int32_t Ctex, float* grad_uvp, float* grad_atlas, void* stream) {
+  if (!uvp || !atlas || !grad_tex || !grad_uvp || !grad_atlas) return NHVR_ERR_NULL;
+  if (N <= 0 || H <= 0 || W <= 0 || S < 2 || Ctex <= 0 || Ctex > 20) return NHVR_ERR_SHAPE;
+  if ((((uintptr_t)atlas | (uintptr_t)grad_atlas) & 15) != 0) return NHVR_ERR_ALIGN;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  const int G = (Ctex + 3) / 4;
+  const int64_t total = (int64_t)N * H * W;
+  const int blocks = (int)std::min<int64_t>((total + 127) / 128, (int64_t)148 * 16 * 8);
+  const float4* a4 = reinterpret_cast<const float4*>(atlas);
+  cudaStream_t st = (cudaStream_t)stream;
+#define NHVR_LAUNCH_SBWD(GG) texture_sample_bwd_kernel<GG><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, grad_uvp, grad_atlas)
+  switch (G) {
+    case 1: NHVR_LAUNCH_SBWD(1); break;
+    case 2: NHVR_LAUNCH_SBWD(2); break;
+    case 3: NHVR_LAUNCH_SBWD(3); break;
+    case 4: NHVR_LAUNCH_SBWD(4); break;
+    default: NHVR_LAUNCH_SBWD(5); break;
+  }
+#undef NHVR_LAUNCH_SBWD
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
+  return NHVR_OK;
+}
+
+extern "C" int nhvr_composite_bwd(const float* fgm, const float* bg, int32_t bg_batched, const float* grad_out, int32_t N, int32_t H,
+                                  int32_t W, float* grad_fgm, float* grad_bg, void* stream) {
+  if (!fgm || !bg || !grad_out || !grad_fgm || !grad_bg) return NHVR_ERR_NULL;
+  if (N <= 0 || H <= 0 || W <= 0) return NHVR_ERR_SHAPE;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  const int64_t HW = (int64_t)H * W;
+  composite_bwd_kernel<<<(int)std::min<int64_t>((HW + 255) / 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(fgm, bg, bg_batched, grad_out, N,
+                                                                                                          HW, grad_fgm, grad_bg);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
+  return NHVR_OK;
+}

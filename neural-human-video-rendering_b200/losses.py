@@ -112,3 +112,58 @@ class _UVProbLoss(torch.autograd.Function):
 def uv_prob_objective(uvp, dp_i, dp_uv, lambda_uv: float = 1000.0, lambda_prob: float = 10.0) -> torch.Tensor:
     """Differentiable  lambda_UV * uv_loss + lambda_Prob * prob_loss  (0-dim fp32 CUDA tensor)."""
     return _UVProbLoss.apply(uvp, dp_i, dp_uv, lambda_uv, lambda_prob)
+
+
+class _PairLoss(torch.autograd.Function):
+    """coef * mean(f(a, b)) with gradient w.r.t. a (b is a target / detached): mode 0 MSE, 1 L1, 2 MSE vs constant."""
+
+    @staticmethod
+    def forward(ctx, a, b, mode, target, coef):
+        x = _f32(a)
+        y = _f32(b) if b is not None else None
+        acc = _acc(x.device)
+        lib = load()
+        if mode == 0:
+            check(lib.nhvr_loss_sum_sq_diff(x.data_ptr(), y.data_ptr(), x.numel(), acc.data_ptr(), stream_ptr()), "nhvr_loss_sum_sq_diff")
+        elif mode == 1:
+            check(lib.nhvr_loss_sum_abs_diff(x.data_ptr(), y.data_ptr(), x.numel(), acc.data_ptr(), stream_ptr()), "nhvr_loss_sum_abs_diff")
+        else:
+            check(lib.nhvr_loss_sum_sq_const(x.data_ptr(), float(target), x.numel(), acc.data_ptr(), stream_ptr()), "nhvr_loss_sum_sq_const")
+        ctx.saved = (x, y, int(mode), float(target), float(coef))
+        return (coef * acc[0] / x.numel()).float()
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, y, mode, target, coef = ctx.saved
+        g = torch.empty_like(x)
+        gs = gout.detach().reshape(1).float().contiguous()
+        check(load().nhvr_loss_pair_bwd(x.data_ptr(), y.data_ptr() if y is not None else None, x.numel(), mode, target, coef,
+                                        gs.data_ptr(), 0, g.data_ptr(), stream_ptr()), "nhvr_loss_pair_bwd")
+        return g, None, None, None, None
+
+
+def mse_diff(a, b, coef: float = 1.0):
+    return _PairLoss.apply(a, b.detach(), 0, 0.0, coef)
+
+
+def l1_diff(a, b, coef: float = 1.0):
+    return _PairLoss.apply(a, b.detach(), 1, 0.0, coef)
+
+
+def lsgan_diff(pred_scales, target_is_real: bool, coef: float = 1.0):
+    total = None
+    for pred in pred_scales:
+        p = pred[-1] if isinstance(pred, (list, tuple)) else pred
+        term = _PairLoss.apply(p, None, 2, 1.0 if target_is_real else 0.0, coef)
+        total = term if total is None else total + term
+    return total
+
+
+def feature_matching_diff(pred_fake, pred_real, n_layers_D: int = 3, num_D: int = 2, lambda_feat: float = 10.0):
+    feat_w, d_w = 4.0 / (n_layers_D + 1), 1.0 / num_D
+    total = None
+    for i in range(num_D):
+        for j in range(len(pred_fake[i]) - 1):
+            term = l1_diff(pred_fake[i][j], pred_real[i][j], d_w * feat_w * lambda_feat)
+            total = term if total is None else total + term
+    return total

@@ -266,3 +266,62 @@ def composite(fgm: torch.Tensor, bg: torch.Tensor, out: Optional[torch.Tensor] =
         check(load().nhvr_composite(fgm.data_ptr(), bg.data_ptr(), batched, N, H, W, out.data_ptr(), stream_ptr()),
               "nhvr_composite")
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# differentiable wrappers (training): forward and backward both on the sm_100a kernels
+# ----------------------------------------------------------------------------------------------
+class _TextureSampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, uvp, atlas, use_mask_texture):
+        if not use_mask_texture:
+            raise capi.NhvrError("texture lookup backward is built for --use_mask_texture (the reference's setting) only")
+        u = uvp.detach().contiguous().float()
+        acl = atlas_to_channels_last(atlas)
+        tex, _, _ = texture_sample(u, acl, atlas.shape[1], True, want_indices=False)
+        ctx.saved = (u, acl, atlas.shape)
+        return tex
+
+    @staticmethod
+    def backward(ctx, gtex):
+        u, acl, ashape = ctx.saved
+        N, _, H, W = u.shape
+        P, Ct, S, _ = ashape
+        gtex = gtex.contiguous().float()
+        guvp = torch.empty_like(u)
+        gacl = torch.zeros_like(acl)
+        with _prof("sampler_bwd", float(N) * H * W * (73 * 2 + Ct) * 4.0):
+            check(load().nhvr_texture_sample_bwd(u.data_ptr(), acl.data_ptr(), gtex.data_ptr(), N, H, W, S, Ct, guvp.data_ptr(),
+                                                 gacl.data_ptr(), stream_ptr()), "nhvr_texture_sample_bwd")
+        gatlas = gacl[..., :Ct].permute(0, 3, 1, 2).contiguous()
+        return guvp, gatlas, None
+
+
+def texture_sample_diff(uvp: torch.Tensor, atlas: torch.Tensor, use_mask_texture: bool = True) -> torch.Tensor:
+    """Differentiable texture lookup: tex [N,Ctex,H,W]; gradients flow to uvp and to the atlas parameter."""
+    return _TextureSampleFn.apply(uvp, atlas, use_mask_texture)
+
+
+class _CompositeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fgm, bg):
+        f = fgm.detach().contiguous().float()
+        b = bg.detach().contiguous().float()
+        ctx.saved = (f, b)
+        return composite(f, b)
+
+    @staticmethod
+    def backward(ctx, gout):
+        f, b = ctx.saved
+        N, _, H, W = f.shape
+        batched = int(b.dim() == 4 and b.shape[0] == N and N > 1)
+        gout = gout.contiguous().float()
+        gf = torch.empty_like(f)
+        gb = torch.empty_like(b)
+        check(load().nhvr_composite_bwd(f.data_ptr(), b.data_ptr(), batched, gout.data_ptr(), N, H, W, gf.data_ptr(), gb.data_ptr(),
+                                        stream_ptr()), "nhvr_composite_bwd")
+        return gf, gb
+
+
+def composite_diff(fgm: torch.Tensor, bg: torch.Tensor) -> torch.Tensor:
+    return _CompositeFn.apply(fgm, bg)

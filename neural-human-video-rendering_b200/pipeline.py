@@ -68,6 +68,16 @@ class RenderPipeline(nn.Module):
         out = ops.composite(fgm, bg_refined)
         return {"out": out, "fgm": fgm, "tex": tex, "uvp": uvp, "part": part, "texel": texel}
 
+    def forward_train(self, pose: torch.Tensor, prev: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Differentiable frame: every stage runs forward AND backward on the sm_100a kernels (autograd only
+        routes the gradients).  `prev` is the (detached) previous composited frame."""
+        uvp = self.netTransG(pose)
+        tex = ops.texture_sample_diff(uvp, self.atlas, self.use_mask_texture)
+        fgm = self.netG(tex, pose, prev.detach())
+        bg_refined = self.netBG(self.bg.unsqueeze(0))[0]
+        out = ops.composite_diff(fgm, bg_refined)
+        return {"out": out, "fgm": fgm, "tex": tex, "uvp": uvp, "bg": bg_refined}
+
     @torch.no_grad()
     def render_clip(self, poses: torch.Tensor, use_graph: bool = True) -> torch.Tensor:
         """poses [T, pose_nc, H, W] (CUDA fp32) -> frames [T, 3, H, W]."""

@@ -352,3 +352,60 @@ def test_uv_pretrain_objective_and_step(cuda_dev):
         opt.step()
         vals.append(l.item())
     assert vals[-1] < vals[0], vals
+
+
+def test_pipeline_backward_parity(cuda_dev):
+    """One differentiable frame of the whole path (UV generator -> lookup -> temporal generator -> bg net ->
+    composite) with the G-side objective lambda_L2*L2 + lambda_UV*UV + lambda_Prob*Prob: gradients of every
+    parameter group (three networks, atlas, background image) against torch autograd on the oracle."""
+    from nhvr_b200 import losses as L
+    from oracle import losses as O
+    from oracle.texture import texture_sample, composite
+    pipe, ref = _pair_pipeline(cuda_dev, _small_kw(), seed=61)
+    torch.manual_seed(62)
+    pose = torch.rand(2, 3, 64, 64, device=cuda_dev) * 2 - 1
+    prev = torch.rand(2, 3, 64, 64, device=cuda_dev) * 2 - 1
+    real = torch.rand(2, 3, 64, 64, device=cuda_dev) * 2 - 1
+    dp_i = torch.randint(0, 25, (2, 64, 64), device=cuda_dev)
+    dp_uv = torch.rand(2, 2, 64, 64, device=cuda_dev)
+    r = pipe.forward_train(pose, prev)
+    loss = L.mse_diff(r["out"], real, 500.0) + L.uv_prob_objective(r["uvp"], dp_i, dp_uv, 1000.0, 10.0)
+    loss.backward()
+    uvp = ref.netTransG(pose)
+    tex, _, _ = texture_sample(uvp, ref.atlas, True)
+    fgm = ref.netG(torch.cat([tex, pose, prev], 1))
+    out = composite(fgm, ref.netBG(ref.bg.unsqueeze(0))[0])
+    loss_r = 500.0 * O.l2_loss(out, real) + 1000.0 * O.uv_loss(uvp, dp_i, dp_uv) + 10.0 * O.prob_loss(uvp, dp_i)
+    loss_r.backward()
+    assert abs(loss.item() - loss_r.item()) <= 5e-3 * abs(loss_r.item())
+    checked = 0
+    for (k, p), (_, q) in zip(sorted(pipe.named_parameters()), sorted(ref.named_parameters())):
+        if k.endswith(".bias") and q.grad.abs().max().item() < 1e-7:
+            continue
+        assert p.grad is not None, k
+        cos = torch.nn.functional.cosine_similarity(p.grad.flatten().double(), q.grad.flatten().double(), dim=0).item()
+        assert cos >= 0.99, (k, cos)
+        checked += 1
+    assert checked >= 20
+
+
+def test_sampler_and_composite_backward_exact(cuda_dev):
+    """The two memory-bound stages' gradients against torch autograd on identical fp32 inputs (tight bounds)."""
+    from nhvr_b200 import ops
+    from oracle.texture import texture_sample, composite
+    torch.manual_seed(71)
+    uvp = (torch.randn(2, 73, 20, 24, device=cuda_dev)).requires_grad_(True)
+    atlas = smooth_atlas(3, 16, cuda_dev).requires_grad_(True)
+    u2, a2 = uvp.detach().clone().requires_grad_(True), atlas.detach().clone().requires_grad_(True)
+    w = torch.randn(2, 3, 20, 24, device=cuda_dev)
+    (ops.texture_sample_diff(uvp, atlas, True) * w).sum().backward()
+    (texture_sample(u2, a2, True)[0] * w).sum().backward()
+    assert (uvp.grad - u2.grad).abs().max().item() <= 1e-3 * u2.grad.abs().max().item()
+    assert (atlas.grad - a2.grad).abs().max().item() <= 1e-3 * a2.grad.abs().max().item()
+    fgm = torch.rand(3, 4, 10, 12, device=cuda_dev).requires_grad_(True)
+    bg = torch.rand(3, 10, 12, device=cuda_dev).requires_grad_(True)
+    f2, b2 = fgm.detach().clone().requires_grad_(True), bg.detach().clone().requires_grad_(True)
+    w = torch.randn(3, 3, 10, 12, device=cuda_dev)
+    (ops.composite_diff(fgm, bg) * w).sum().backward()
+    (composite(f2, b2) * w).sum().backward()
+    assert (fgm.grad - f2.grad).abs().max().item() <= 1e-5 and (bg.grad - b2.grad).abs().max().item() <= 1e-5
