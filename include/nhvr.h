@@ -42,7 +42,7 @@ typedef enum nhvr_status {
 enum { NHVR_HALO_ZERO = 0, NHVR_HALO_REFLECT = 1 };
 enum { NHVR_ACT_NONE = 0, NHVR_ACT_RELU = 1, NHVR_ACT_LRELU02 = 2, NHVR_ACT_TANH = 3,
        NHVR_ACT_TANH_SIGMOID_LAST = 4 /* tanh on all channels but the last, sigmoid on the last */ };
-enum { NHVR_CONV = 0, NHVR_CONV_TRANSPOSE = 1 /* k3 s2 p1 output_padding 1 */,
+enum { NHVR_CONV = 0, NHVR_CONV_TRANSPOSE = 1 /* stride 2: k3 p1 output_padding 1, or k4 p2 (input-gradient of a 4x4 s2 p2 conv) */,
        NHVR_CONV_DGRAD_S1 = 2 /* input-gradient of a stride-1 conv; the desc describes the FORWARD conv */ };
 enum { NHVR_EPI_RAW_STATS = 0,   /* bf16 P8 un-padded conv output + per-(n,c) sum / sum-of-squares */
        NHVR_EPI_BIAS_ACT_F32 = 1,/* bias + activation, fp32 NCHW output                            */
@@ -70,6 +70,8 @@ typedef struct nhvr_conv_desc {
   int32_t epilogue;      /* NHVR_EPI_* */
   int32_t act;           /* NHVR_ACT_* (epilogues 1, 2) */
   int32_t in_extra_rows; /* extra zero rows below the input's bottom halo (gradient buffers shared with wgrad) */
+  int32_t in_extra_cols; /* extra zero columns right of the input's right halo (same purpose)                 */
+  int32_t out_h, out_w;  /* NHVR_CONV_TRANSPOSE only: output size override (0 = 2H x 2W for k3, 2H-2 for k4)  */
 } nhvr_conv_desc;
 
 typedef struct nhvr_conv_plan nhvr_conv_plan;   /* opaque, host memory only */
@@ -182,6 +184,11 @@ int nhvr_composite_bwd(const float* fgm, const float* bg, int32_t bg_batched, co
 int nhvr_in_bwd(const void* dx, int32_t dx_H, int32_t dx_W, int32_t pad_t, int32_t pad_l, int32_t reflect,
                 const void* skip, const void* raw, const nhvr_act_desc* raw_desc, const float* stats, float eps,
                 int32_t act, float* sums, void* g, const nhvr_act_desc* g_desc, void* dy_out, void* stream);
+/* same for a layer WITHOUT normalisation (conv + bias + activation): g = dY * act'(y), y read from the stored
+ * activation yact (P8 in y_desc's format); dbias float [C8*8] (zeroed by the caller) += per-channel sums of g */
+int nhvr_act_bwd(const void* dx, int32_t dx_H, int32_t dx_W, int32_t pad_t, int32_t pad_l, int32_t reflect,
+                 const void* skip, const void* yact, const nhvr_act_desc* y_desc, int32_t act, void* g,
+                 const nhvr_act_desc* g_desc, float* dbias, void* stream);
 /* folded gradient of a chain input -> float [N][C][H][W] * scale (interior_desc: un-padded P8 of the input) */
 int nhvr_fold_unpack(const void* dx, int32_t dx_H, int32_t dx_W, int32_t pad_t, int32_t pad_l, int32_t reflect,
                      const nhvr_act_desc* interior_desc, float* dst, int32_t C, float scale, void* stream);

@@ -34,7 +34,7 @@ class ActDesc(C.Structure):
 
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
-                ("kind", "Cin", "Cout", "kh", "kw", "stride", "pad", "N", "H", "W", "halo", "epilogue", "act", "in_extra_rows")]
+                ("kind", "Cin", "Cout", "kh", "kw", "stride", "pad", "N", "H", "W", "halo", "epilogue", "act", "in_extra_rows", "in_extra_cols", "out_h", "out_w")]
 
 
 # every symbol include/nhvr.h declares: name -> (restype, argtypes)
@@ -76,6 +76,8 @@ SYMBOLS = {
     "nhvr_avgpool3s2_bwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "nhvr_in_bwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.POINTER(ActDesc), _P, C.c_float,
                             C.c_int32, _P, _P, C.POINTER(ActDesc), _P, _P]),
+    "nhvr_act_bwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.POINTER(ActDesc), C.c_int32, _P,
+                             C.POINTER(ActDesc), _P, _P]),
     "nhvr_fold_unpack": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ActDesc), _P, C.c_int32,
                                  C.c_float, _P]),
     "nhvr_head_bwd": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P]),

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
     const int64_t q = q0 + m;
     const int y = (int)(q / P.Wrow);
     const int x = (int)(q - (int64_t)y * P.Wrow);
-    const bool valid = (y < P.Hv) && (x < P.Wv);
+    const bool valid_m = (y < P.Hv) && (x < P.Wv);
     const uint32_t t_lane = tmem_base + ((uint32_t)(we * 32) << 16);
     const int cout_off = split * P.Npad;
     const int ngroups = P.Npad >> 4;
@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
     for (int a = 0; a < ((P.debug & 8) ? 0 : P.nacc); ++a) {
       const int Y = y * P.oys + P.oy[a];
       const int X = x * P.oxs + P.ox[a];
+      const bool valid = valid_m && Y < P.Ho && X < P.Wo;
       for (int g = half; g < ngroups; g += 2) {
         uint32_t vr[16];
         tmem_ld16(t_lane + (uint32_t)(a * P.Npad + g * 16), vr);
@@ -429,24 +430,30 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
       }
     K.Wrow = Wq; K.Hv = Ho; K.Wv = Wo; K.oys = K.oxs = 1;
   } else if (d->kind == NHVR_CONV_TRANSPOSE) {
-    if (d->kh != 3 || d->kw != 3 || d->stride != 2 || d->pad != 1) { delete p; return NHVR_ERR_UNSUPPORTED; }
-    in.pad_t = in.pad_l = 0; in.pad_b = in.pad_r = 1;
+    const bool k3 = (d->kh == 3 && d->kw == 3 && d->pad == 1), k4 = (d->kh == 4 && d->kw == 4 && d->pad == 2);
+    if (d->stride != 2 || !(k3 || k4)) { delete p; return NHVR_ERR_UNSUPPORTED; }
+    in.pad_t = in.pad_l = 0; in.pad_b = 1; in.pad_r = 1 + d->in_extra_cols;
     in.halo = NHVR_HALO_ZERO;
-    const int Wp = d->W + 1;
-    Ho = 2 * d->H; Wo = 2 * d->W;
+    const int Wp = d->W + in.pad_r;
+    // out[2i - pad + ky] += x[i] * w[ky]:  k3 p1 -> 2H (output_padding 1);  k4 p2 -> 2H-2 (+ output_padding via out_h)
+    Ho = d->out_h > 0 ? d->out_h : (k3 ? 2 * d->H : 2 * d->H - 2);
+    Wo = d->out_w > 0 ? d->out_w : (k3 ? 2 * d->W : 2 * d->W - 2);
+    if (Ho < 1 || Wo < 1 || Ho > 2 * d->H || Wo > 2 * d->W) { delete p; return NHVR_ERR_SHAPE; }
     run_specs.push_back({0, kTileM + 1});
     run_specs.push_back({Wp, kTileM + 1});
     nacc = 4;
-    // out[2i-1+ky][2j-1+kx] += x[i][j] * w[ky][kx]; phase a (row parity): a=0 -> (di=0,ky=1); a=1 -> (0,2),(1,0)
-    const int n_opt[2] = {1, 2};
-    const int o_d[2][2] = {{0, 0}, {0, 1}};
-    const int o_k[2][2] = {{1, 1}, {2, 0}};
+    // phase a (output row parity), M index t <-> output row 2t+a, input row t+di:
+    //   k3 p1: a=0 -> (di 0, ky 1);          a=1 -> (0, 2), (1, 0)
+    //   k4 p2: a=0 -> (di 1, ky 0), (0, 2);  a=1 -> (1, 1), (0, 3)
+    int n_opt[2], o_d[2][2], o_k[2][2];
+    if (k3) { n_opt[0] = 1; n_opt[1] = 2; o_d[0][0] = 0; o_k[0][0] = 1; o_d[0][1] = 0; o_k[0][1] = 1; o_d[1][0] = 0; o_k[1][0] = 2; o_d[1][1] = 1; o_k[1][1] = 0; }
+    else    { n_opt[0] = 2; n_opt[1] = 2; o_d[0][0] = 1; o_k[0][0] = 0; o_d[0][1] = 0; o_k[0][1] = 2; o_d[1][0] = 1; o_k[1][0] = 1; o_d[1][1] = 0; o_k[1][1] = 3; }
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b)
         for (int ia = 0; ia < n_opt[a]; ++ia)
           for (int ib = 0; ib < n_opt[b]; ++ib)
-            taps.push_back({o_d[a][ia], o_d[b][ib], a * 2 + b, o_k[a][ia] * 3 + o_k[b][ib]});
-    K.Wrow = Wp; K.Hv = d->H; K.Wv = d->W; K.oys = K.oxs = 2;
+            taps.push_back({o_d[a][ia], o_d[b][ib], a * 2 + b, o_k[a][ia] * d->kw + o_k[b][ib]});
+    K.Wrow = Wp; K.Hv = (Ho + 1) / 2; K.Wv = (Wo + 1) / 2; K.oys = K.oxs = 2;
     for (int a = 0; a < 4; ++a) { K.oy[a] = a >> 1; K.ox[a] = a & 1; }
   } else {
     delete p; return NHVR_ERR_UNSUPPORTED;

@@ -396,6 +396,53 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const __grid_constant
   }
 }
 
+// backward of  x_next = pad(act(conv + bias))  (a layer WITHOUT normalisation, e.g. the discriminator's first):
+// g = dY * act'(y) with y read back from the stored activation; dbias[c] += sum g  (scaled like g)
+struct ActBwdExtra {
+  const uint4* yact;   // stored activation, P8 in the consumer's format
+  ActGeom yg;
+  float* dbias;        // [C8*8], zeroed by the caller
+};
+
+__global__ void __launch_bounds__(256) act_bwd_kernel(const __grid_constant__ InBwdParams P, const __grid_constant__ ActBwdExtra X) {
+  const int64_t np = blockIdx.y;
+  const int n = (int)(np / P.C8), p = (int)(np - (int64_t)n * P.C8);
+  const ActGeom& g = P.gg;
+  const int total = g.Hp * g.Wp;
+  float bs[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) bs[e] = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int yy = i / g.Wp, xx = i - yy * g.Wp;
+    const int y = yy - g.pad_t, x = xx - g.pad_l;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < P.f.H && x >= 0 && x < P.f.W) {
+      float dy[8], a[8], v[8];
+      fold_load(P, np, y, x, dy);
+      unpack8(X.yact[act_unit(X.yg, n, p, y + X.yg.pad_t, x + X.yg.pad_l)], a, P.f16);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { v[e] = dy[e] * act_grad(a[e], P.act); bs[e] += v[e]; }
+      o = pack8(v, P.f16);
+    }
+    P.g[((int64_t)n * g.C8 + p) * g.plane_units + plane_unit(g, yy, xx)] = o;
+  }
+  __shared__ float sh[8][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float t = bs[e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) sh[e][warp] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[threadIdx.x][w];
+    atomicAdd(X.dbias + p * 8 + threadIdx.x, t);
+  }
+}
+
 // g_pre = grad_out * act'(out) * scale  (fp32 NCHW), the output layer has no norm
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ out, const float* __restrict__ gout, int64_t n_per_c,
                                                        int C, int64_t total, int act, float scale, float* __restrict__ gpre) {
@@ -499,6 +546,29 @@ extern "C" int nhvr_in_bwd(const void* dx, int32_t dx_H, int32_t dx_W, int32_t p
   in_bwd_reduce_kernel<<<dim3(grid_x_for((int64_t)P.f.H * P.f.W, planes), planes), 256, 0, s>>>(P);
   NHVR_POST();
   in_bwd_apply_kernel<<<dim3(grid_x_for((int64_t)P.gg.Hp * P.gg.Wp, planes), planes), 256, 0, s>>>(P);
+  NHVR_POST();
+  return NHVR_OK;
+}
+
+extern "C" int nhvr_act_bwd(const void* dx, int32_t dx_H, int32_t dx_W, int32_t pad_t, int32_t pad_l, int32_t reflect,
+                            const void* skip, const void* yact, const nhvr_act_desc* y_desc, int32_t act, void* g,
+                            const nhvr_act_desc* g_desc, float* dbias, void* stream) {
+  if (!yact || !y_desc || !g || !g_desc || !dbias) return NHVR_ERR_NULL;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  InBwdParams P;
+  ActBwdExtra X;
+  X.yact = reinterpret_cast<const uint4*>(yact);
+  X.yg = make_geom(*y_desc);
+  X.dbias = dbias;
+  nhvr_act_desc interior = *y_desc;
+  interior.pad_t = interior.pad_l = interior.pad_b = interior.pad_r = 0; interior.split = 0;
+  int st = make_in_bwd(P, dx, dx_H, dx_W, pad_t, pad_l, reflect, skip, yact, &interior, nullptr, nullptr, 0.f, act);
+  if (st != NHVR_OK) return st;
+  P.gg = make_geom(*g_desc);
+  if (P.gg.N != P.N || P.gg.C8 != P.C8 || P.gg.H != P.f.H || P.gg.W != P.f.W) return NHVR_ERR_SHAPE;
+  P.g = reinterpret_cast<uint4*>(g);
+  const int planes = P.N * P.C8;
+  act_bwd_kernel<<<dim3(grid_x_for((int64_t)P.gg.Hp * P.gg.Wp, planes), planes), 256, 0, (cudaStream_t)stream>>>(P, X);
   NHVR_POST();
   return NHVR_OK;
 }

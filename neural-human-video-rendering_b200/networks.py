@@ -177,9 +177,10 @@ class _ChainEngine:
                                   in_extra_rows=wp.g_desc.pad_b - p.pad)
                 fold = (0, 0, False)
             elif p.stride == 2:       # dgrad of a stride-2 conv = the transposed conv of the gradient
-                if p.k != 3 or p.pad != 1 or (d.H % 2) or (d.W % 2):
-                    raise NhvrError("backward of a stride-2 conv is built for k3 p1 on even sizes only")
-                dp = ops.ConvPlan(capi.CONV_TRANSPOSE, p.cout, p.cin, 3, 2, 1, self.N, plan.Ho, plan.Wo, capi.HALO_ZERO, capi.EPI_RAW_P8)
+                if (p.k, p.pad) not in ((3, 1), (4, 2)):
+                    raise NhvrError("backward of a stride-2 conv is built for k3 p1 and k4 p2 only")
+                dp = ops.ConvPlan(capi.CONV_TRANSPOSE, p.cout, p.cin, p.k, 2, p.pad, self.N, plan.Ho, plan.Wo, capi.HALO_ZERO,
+                                  capi.EPI_RAW_P8, in_extra_cols=wp.g_desc.pad_r - 1, out_hw=(d.H, d.W))
                 fold = (0, 0, False)
             else:                     # stride-1: gradient over the padded input extent, halo folded afterwards
                 dp = ops.ConvPlan(capi.CONV_DGRAD_S1, p.cin, p.cout, p.k, 1, p.pad, self.N, d.H, d.W, capi.HALO_ZERO, capi.EPI_RAW_P8)
@@ -199,26 +200,34 @@ class _ChainEngine:
         self._bwd = B
         self._bwd_versions = None
 
-    def backward(self, grad_out: torch.Tensor, need_input_grad: bool, in_channels: int):
-        """Gradients of the chain: (input_grad NCHW fp32 or None, [dW per layer], db of the output layer)."""
+    def backward(self, grad_out: Optional[torch.Tensor], need_input_grad: bool, in_channels: int,
+                 extra_grads: Optional[Dict[int, torch.Tensor]] = None):
+        """Gradients of the chain: (input_grad NCHW fp32 or None, [dW per layer], [db per layer or None]).
+
+        extra_grads[i] (i >= 1): additional gradient w.r.t. the activation that feeds conv i (the discriminator's
+        intermediate features used by the feature-matching loss), NCHW fp32."""
         assert self.train, "backward needs a training engine"
         if self._bwd is None:
             self._build_backward()
         B = self._bwd
+        extra_grads = {k: v for k, v in (extra_grads or {}).items() if v is not None}
         ver = tuple(Lr["params"].weight._version for Lr in self.chain)
         if ver != self._bwd_versions:                       # dgrad convs read the same weights, differently packed
             for Lr, dp in zip(self.chain, B["dplans"]):
                 dp.pack_weights(Lr["params"].weight)
             self._bwd_versions = ver
         L = len(self.plans)
+        if grad_out is None:
+            grad_out = torch.zeros_like(self.out)
         grad_out = grad_out.contiguous().float()
         # static gradient scale: keeps 16-bit gradient operands in range (fp16), exact power of two
-        amax = float(grad_out.abs().max())
+        amax = float(max([grad_out.abs().max()] + [g.abs().max() for g in extra_grads.values()]))
         S = 1.0 if amax == 0.0 or not (amax == amax) else 2.0 ** round(__import__("math").log2(64.0 / amax))
         inv_S = 1.0 / S
         self._last_S = S
         g_pre = ops.head_bwd(self.out, grad_out, self.final_act, S)
-        db_last = ops.bias_grad(g_pre, inv_S)
+        dbs: List[Optional[torch.Tensor]] = [None] * L
+        dbs[L - 1] = ops.bias_grad(g_pre, inv_S)
         ops.pack_nchw([g_pre], B["G"][L - 1])
         dWs: List[Optional[torch.Tensor]] = [None] * L
         dy_total: Dict[int, ops.P8Buffer] = {}
@@ -239,6 +248,14 @@ class _ChainEngine:
                 break
             prev = self.chain[i - 1]
             skip = dy_total.get(i + 1) if Lr.get("res") == "save" else None
+            if i in extra_grads:                             # external gradient of this activation (D features)
+                assert skip is None
+                rd = self.plans[i - 1].raw_desc()
+                key = ("extra", rd.C8, rd.H, rd.W)
+                if key not in B["dy"]:
+                    B["dy"][key] = ops.P8Buffer(rd, self.device)
+                skip = B["dy"][key]
+                ops.pack_nchw([extra_grads[i].contiguous().float() * S], skip)
             dy_out = None
             if prev.get("res") == "add":
                 rd = self.plans[i - 1].raw_desc()
@@ -248,9 +265,14 @@ class _ChainEngine:
                     B["dy"][key] = ops.P8Buffer(rd, self.device)
                 dy_out = B["dy"][key]
                 dy_total[i - 1] = dy_out
-            ops.in_bwd(dX, pt, pl_, refl, self.raw_bufs[i - 1], self.stats[i - 1], prev["act"], B["sums"], B["G"][i - 1],
-                       skip=skip, dy_out=dy_out)
-        return input_grad, dWs, db_last
+            if prev.get("norm", True):
+                ops.in_bwd(dX, pt, pl_, refl, self.raw_bufs[i - 1], self.stats[i - 1], prev["act"], B["sums"], B["G"][i - 1],
+                           skip=skip, dy_out=dy_out)
+            else:                                            # conv + bias + activation without norm
+                dbias = torch.zeros(self.plans[i - 1].Cout8 * 8, dtype=torch.float32, device=self.device)
+                ops.act_bwd(dX, pt, pl_, refl, self.in_bufs[i], prev["act"], B["G"][i - 1], dbias, skip=skip)
+                dbs[i - 1] = dbias[:prev["params"].cout] * inv_S
+        return input_grad, dWs, dbs
 
     def feature(self, i: int) -> torch.Tensor:
         """Activation that feeds conv i (= output of layer i-1) as NCHW fp32 (D's intermediate features)."""
@@ -282,21 +304,25 @@ class _ChainEngine:
 
 
 class _ChainFunction(torch.autograd.Function):
-    """Differentiable wrapper of a conv chain: forward and backward both run on the sm_100a kernels."""
+    """Differentiable wrapper of a conv chain: forward and backward both run on the sm_100a kernels.
+    With n_feats > 0 the intermediate activations feeding convs 1..n_feats are returned too (discriminator)."""
 
     @staticmethod
-    def forward(ctx, eng: "_ChainEngine", n_inputs: int, *tensors):
-        inputs, params = tensors[:n_inputs], tensors[n_inputs:]
-        ctx.eng, ctx.n_inputs = eng, n_inputs
+    def forward(ctx, eng: "_ChainEngine", n_inputs: int, n_feats: int, *tensors):
+        inputs = tensors[:n_inputs]
+        ctx.eng, ctx.n_inputs, ctx.n_feats = eng, n_inputs, n_feats
         ctx.in_channels = [t.shape[1] for t in inputs]
         ctx.need_in = any(t.requires_grad for t in inputs)
-        out = eng.run([t.detach().float() for t in inputs])
-        return out.clone()
+        out = eng.run([t.detach().float() for t in inputs]).clone()
+        if n_feats == 0:
+            return out
+        return tuple(eng.feature(j) for j in range(1, n_feats + 1)) + (out,)
 
     @staticmethod
-    def backward(ctx, grad_out):
+    def backward(ctx, *grads):
         eng = ctx.eng
-        gin, dWs, db_last = eng.backward(grad_out, ctx.need_in, sum(ctx.in_channels))
+        extra = {j + 1: g for j, g in enumerate(grads[:-1])}
+        gin, dWs, dbs = eng.backward(grads[-1], ctx.need_in, sum(ctx.in_channels), extra)
         eng.busy = False
         grads_in = [None] * ctx.n_inputs
         if gin is not None:
@@ -305,12 +331,11 @@ class _ChainFunction(torch.autograd.Function):
                 grads_in[k] = gin[:, off:off + c].contiguous()
                 off += c
         grads_p = []
-        L = len(eng.chain)
         for i, Lr in enumerate(eng.chain):
             grads_p.append(dWs[i])
-            # a bias in front of an affine-free InstanceNorm has exactly zero gradient; only the output layer's counts
-            grads_p.append(db_last if i == L - 1 else torch.zeros_like(Lr["params"].bias))
-        return (None, None) + tuple(grads_in) + tuple(grads_p)
+            # a bias in front of an affine-free InstanceNorm has exactly zero gradient
+            grads_p.append(dbs[i] if dbs[i] is not None else torch.zeros_like(Lr["params"].bias))
+        return (None, None, None) + tuple(grads_in) + tuple(grads_p)
 
 
 class GlobalGeneratorB200(nn.Module):
@@ -400,7 +425,7 @@ class GlobalGeneratorB200(nn.Module):
             params = []
             for Lr in eng.chain:
                 params += [Lr["params"].weight, Lr["params"].bias]
-            return _ChainFunction.apply(eng, len(xs), *xs, *params)
+            return _ChainFunction.apply(eng, len(xs), 0, *xs, *params)
         eng = self.engine(N, H, W)
         out = eng.run([t.float() for t in xs])
         return out
@@ -473,37 +498,54 @@ class MultiscaleDiscriminatorB200(nn.Module):
             chain.append(dict(params=p, halo=capi.HALO_ZERO, act=capi.ACT_LRELU02, res=None, norm=(0 < j < len(convs) - 1)))
         return chain
 
+    def _scale_engines(self, N, H, W, dev, train: bool) -> List[_ChainEngine]:
+        if train:
+            pool = self._engines.setdefault((N, H, W, dev.index, "train"), [])
+            engs = next((e for e in pool if not any(x.busy for x in e)), None)
+            if engs is None:
+                if len(pool) >= 8:
+                    raise NhvrError("more than 8 forward passes of one module are waiting for backward")
+                engs = self._make_engines(N, H, W, dev, True)
+                pool.append(engs)
+            for e in engs:
+                e.busy = True
+            return engs
+        key = (N, H, W, dev.index)
+        if key not in self._engines:
+            self._engines[key] = self._make_engines(N, H, W, dev, False)
+        return self._engines[key]
+
+    def _make_engines(self, N, H, W, dev, train):
+        capi.require_device()
+        engs, h, w = [], H, W
+        for i in range(self.num_D):
+            engs.append(_ChainEngine(self._chain(self.num_D - 1 - i), N, h, w, dev, capi.ACT_NONE, 1, train=train))
+            h, w = (h + 1) // 2, (w + 1) // 2
+        return engs
+
     def forward(self, x):
         if not x.is_cuda:
             raise NhvrError("nhvr_b200 modules take CUDA tensors only (no CPU fallback)")
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NhvrError("backward through the sm_100a discriminator is not built yet (forward only); use torch.no_grad()")
         x = x.contiguous().float()
         N, C, H, W = x.shape
-        key = (N, H, W, x.device.index)
-        engs = self._engines.get(key)
-        if engs is None:
-            capi.require_device()
-            engs, h, w = [], H, W
-            for i in range(self.num_D):
-                engs.append(_ChainEngine(self._chain(self.num_D - 1 - i), N, h, w, x.device, capi.ACT_NONE, 1))
-                h, w = (h + 1) // 2, (w + 1) // 2
-            self._engines[key] = engs
+        train = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        engs = self._scale_engines(N, H, W, x.device, train)
         result = []
         xd = x
         for i, eng in enumerate(engs):
             eng.maybe_repack()
-            out = eng.run([xd]).clone()
-            if self.getIntermFeat:
-                feats = [eng.feature(j) for j in range(1, len(eng.plans))]
-                result.append(feats + [out])
+            n_feats = len(eng.plans) - 1 if self.getIntermFeat else 0
+            if train:
+                params = []
+                for Lr in eng.chain:
+                    params += [Lr["params"].weight, Lr["params"].bias]
+                outs = _ChainFunction.apply(eng, 1, n_feats, xd, *params)
+                result.append(list(outs) if n_feats else [outs])
             else:
-                result.append([out])
+                out = eng.run([xd]).clone()
+                result.append([eng.feature(j) for j in range(1, n_feats + 1)] + [out])
             if i != self.num_D - 1:
-                nxt = torch.empty(N, C, (xd.shape[2] + 1) // 2, (xd.shape[3] + 1) // 2, dtype=torch.float32, device=x.device)
-                capi.check(capi.load().nhvr_avgpool3s2(xd.data_ptr(), N, C, xd.shape[2], xd.shape[3], nxt.data_ptr(),
-                                                       capi.stream_ptr()), "nhvr_avgpool3s2")
-                xd = nxt
+                xd = ops.avgpool3s2(xd)
         return result
 
 

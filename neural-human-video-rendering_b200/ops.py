@@ -93,9 +93,11 @@ def unpack_nchw(src: P8Buffer, channels: int, out: Optional[torch.Tensor] = None
 class ConvPlan:
     """One conv layer lowered to the tcgen05 shift-GEMM kernel (nhvr_conv_plan_*)."""
 
-    def __init__(self, kind, Cin, Cout, k, stride, pad, N, H, W, halo, epilogue, act=capi.ACT_NONE, in_extra_rows=0):
+    def __init__(self, kind, Cin, Cout, k, stride, pad, N, H, W, halo, epilogue, act=capi.ACT_NONE, in_extra_rows=0,
+                 in_extra_cols=0, out_hw=(0, 0)):
         d = ConvDesc()
-        d.in_extra_rows = in_extra_rows
+        d.in_extra_rows, d.in_extra_cols = in_extra_rows, in_extra_cols
+        d.out_h, d.out_w = out_hw
         d.kind, d.Cin, d.Cout, d.kh, d.kw, d.stride, d.pad = kind, Cin, Cout, k, k, stride, pad
         d.N, d.H, d.W, d.halo, d.epilogue, d.act = N, H, W, halo, epilogue, act
         self.desc = d
@@ -190,6 +192,37 @@ def in_bwd(dx: P8Buffer, pad_t: int, pad_l: int, reflect: bool, raw: P8Buffer, s
         check(load().nhvr_in_bwd(dx.ptr, dx.desc.H, dx.desc.W, pad_t, pad_l, int(reflect), skip.ptr if skip is not None else None,
                                  raw.ptr, C.byref(raw.desc), stats.data_ptr(), eps, act, sums.data_ptr(), g.ptr, C.byref(g.desc),
                                  dy_out.ptr if dy_out is not None else None, stream_ptr()), "nhvr_in_bwd")
+
+
+def act_bwd(dx: P8Buffer, pad_t: int, pad_l: int, reflect: bool, yact: P8Buffer, act: int, g: P8Buffer, dbias: torch.Tensor,
+            skip: Optional[P8Buffer] = None) -> None:
+    check(load().nhvr_act_bwd(dx.ptr, dx.desc.H, dx.desc.W, pad_t, pad_l, int(reflect), skip.ptr if skip is not None else None,
+                              yact.ptr, C.byref(yact.desc), act, g.ptr, C.byref(g.desc), dbias.data_ptr(), stream_ptr()), "nhvr_act_bwd")
+
+
+class _AvgPoolFn(torch.autograd.Function):
+    """AvgPool2d(3, 2, 1, count_include_pad=False) between discriminator scales, forward and backward native."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous().float()
+        N, Cc, H, W = x.shape
+        out = torch.empty(N, Cc, (H + 1) // 2, (W + 1) // 2, dtype=torch.float32, device=x.device)
+        check(load().nhvr_avgpool3s2(x.data_ptr(), N, Cc, H, W, out.data_ptr(), stream_ptr()), "nhvr_avgpool3s2")
+        ctx.shape = (N, Cc, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        N, Cc, H, W = ctx.shape
+        g = g.contiguous().float()
+        gin = torch.empty(N, Cc, H, W, dtype=torch.float32, device=g.device)
+        check(load().nhvr_avgpool3s2_bwd(g.data_ptr(), N, Cc, H, W, 0, gin.data_ptr(), stream_ptr()), "nhvr_avgpool3s2_bwd")
+        return gin
+
+
+def avgpool3s2(x: torch.Tensor) -> torch.Tensor:
+    return _AvgPoolFn.apply(x)
 
 
 def fold_unpack(dx: P8Buffer, pad_t: int, pad_l: int, reflect: bool, N: int, C8: int, H: int, W: int, channels: int,

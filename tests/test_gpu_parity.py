@@ -409,3 +409,36 @@ def test_sampler_and_composite_backward_exact(cuda_dev):
     (ops.composite_diff(fgm, bg) * w).sum().backward()
     (composite(f2, b2) * w).sum().backward()
     assert (fgm.grad - f2.grad).abs().max().item() <= 1e-5 and (bg.grad - b2.grad).abs().max().item() <= 1e-5
+
+
+def test_discriminator_backward_parity(cuda_dev):
+    """D and G objectives through the multiscale PatchGAN (LSGAN + feature matching): gradients w.r.t. the
+    discriminator's parameters and w.r.t. its input image (what the generator receives) vs torch autograd."""
+    from nhvr_b200.networks import define_D
+    from nhvr_b200 import losses as L
+    from oracle.networks import define_D as oracle_define_D
+    from oracle import losses as O
+    torch.manual_seed(81)
+    ref = oracle_define_D(6, 16, 3, "instance", False, 2, True).to(cuda_dev)
+    net = define_D(6, 16, 3, "instance", False, 2, True)
+    net.load_state_dict(ref.state_dict())
+    fake = (torch.rand(2, 6, 66, 66, device=cuda_dev) * 2 - 1).requires_grad_(True)
+    real = torch.rand(2, 6, 66, 66, device=cuda_dev) * 2 - 1
+    fake_r = fake.detach().clone().requires_grad_(True)
+    with torch.no_grad():
+        pr = net(real)
+        pr_r = ref(real)
+    pf = net(fake)
+    loss = L.lsgan_diff(pf, True) + L.feature_matching_diff(pf, pr, 3, 2, 10.0)
+    loss.backward()
+    pf_r = ref(fake_r)
+    loss_r = O.gan_loss(pf_r, True) + O.feature_matching_loss(pf_r, pr_r, 3, 2, 10.0)
+    loss_r.backward()
+    assert abs(loss.item() - loss_r.item()) <= 2e-2 * abs(loss_r.item())
+    rows = [("input", fake.grad, fake_r.grad)] + [(k, p.grad, q.grad) for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters())]
+    for name, a, b in rows:
+        assert a is not None, name
+        if name.endswith(".bias") and a.abs().max().item() == 0.0:
+            continue
+        cos = torch.nn.functional.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0).item()
+        assert cos >= 0.99, (name, cos)
