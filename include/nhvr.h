@@ -224,6 +224,9 @@ int nhvr_loss_uv_prob_bwd(const float* uvp, const int32_t* dp_i, const float* dp
 /* acc += sum |cur - warp(prev, flow)|, flow float [N][2][H][W] in pixels (dx, dy), bilinear, border clamp. */
 int nhvr_loss_temporal(const float* cur, const float* prev, const float* flow, int32_t N, int32_t C, int32_t H,
                        int32_t W, double* acc, void* stream);
+/* gradient of coef * mean|cur - warp(prev, flow)| w.r.t. cur (prev = detached previous frame) */
+int nhvr_loss_temporal_bwd(const float* cur, const float* prev, const float* flow, int32_t N, int32_t C, int32_t H,
+                           int32_t W, float coef, const float* grad_scale, float* grad_cur, void* stream);
 /* AvgPool2d(3, stride 2, padding 1, count_include_pad=False) between discriminator scales (pix2pixHD
  * MultiscaleDiscriminator.downsample): in float [N][C][H][W] -> out float [N][C][(H+1)/2][(W+1)/2]. */
 int nhvr_avgpool3s2(const float* in, int32_t N, int32_t C, int32_t H, int32_t W, float* out, void* stream);

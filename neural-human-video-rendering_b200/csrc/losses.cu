@@ -155,6 +155,34 @@ __global__ void __launch_bounds__(256) loss_uv_prob_bwd_kernel(const float* __re
   }
 }
 
+// gradient of coef * mean|cur - warp(prev, flow)| w.r.t. cur (prev is the detached previous frame)
+__global__ void __launch_bounds__(256) loss_temporal_bwd_kernel(const float* __restrict__ cur, const float* __restrict__ prev,
+                                                                const float* __restrict__ flow, int N, int C, int H, int W, float coef,
+                                                                const float* gscale, float* __restrict__ gcur) {
+  const int64_t HW = (int64_t)H * W;
+  const int64_t total = (int64_t)N * HW;
+  const float k = coef * (gscale ? *gscale : 1.f) / (float)(total * C);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / HW);
+    const int64_t pix = idx - (int64_t)n * HW;
+    const int y = (int)(pix / W), x = (int)(pix - (int64_t)y * W);
+    float sx = (float)x + __ldg(flow + (int64_t)n * 2 * HW + pix);
+    float sy = (float)y + __ldg(flow + ((int64_t)n * 2 + 1) * HW + pix);
+    sx = fminf(fmaxf(sx, 0.f), (float)(W - 1));
+    sy = fminf(fmaxf(sy, 0.f), (float)(H - 1));
+    const float x0f = floorf(sx), y0f = floorf(sy);
+    const int x0 = (int)x0f, y0 = (int)y0f, x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+    const float wx = sx - x0f, wy = sy - y0f;
+    for (int c = 0; c < C; ++c) {
+      const float* p = prev + ((int64_t)n * C + c) * HW;
+      const float w = (1.f - wy) * ((1.f - wx) * __ldg(p + (int64_t)y0 * W + x0) + wx * __ldg(p + (int64_t)y0 * W + x1)) +
+                      wy * ((1.f - wx) * __ldg(p + (int64_t)y1 * W + x0) + wx * __ldg(p + (int64_t)y1 * W + x1));
+      const float d = __ldg(cur + ((int64_t)n * C + c) * HW + pix) - w;
+      gcur[((int64_t)n * C + c) * HW + pix] = d > 0.f ? k : (d < 0.f ? -k : 0.f);
+    }
+  }
+}
+
 // gradient of the mean reductions w.r.t. a:  mode 0: 2(a-b)/n   mode 1: sign(a-b)/n   mode 2: 2(a-c)/n ; times coef * *gscale
 __global__ void __launch_bounds__(256) loss_pair_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, int mode,
                                                             float c, float coef, const float* gscale, int accumulate, float* __restrict__ ga) {
@@ -274,6 +302,15 @@ extern "C" int nhvr_loss_temporal(const float* cur, const float* prev, const flo
   if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return NHVR_ERR_SHAPE;
   if (!arch_ok_cached()) return NHVR_ERR_ARCH;
   loss_temporal_kernel<<<blocks_for((int64_t)N * H * W), 256, 0, (cudaStream_t)stream>>>(cur, prev, flow, N, C, H, W, acc);
+  NHVR_POST_LAUNCH();
+}
+extern "C" int nhvr_loss_temporal_bwd(const float* cur, const float* prev, const float* flow, int32_t N, int32_t C, int32_t H,
+                                      int32_t W, float coef, const float* grad_scale, float* grad_cur, void* stream) {
+  if (!cur || !prev || !flow || !grad_cur) return NHVR_ERR_NULL;
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return NHVR_ERR_SHAPE;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  loss_temporal_bwd_kernel<<<blocks_for((int64_t)N * H * W), 256, 0, (cudaStream_t)stream>>>(cur, prev, flow, N, C, H, W, coef, grad_scale,
+                                                                                             grad_cur);
   NHVR_POST_LAUNCH();
 }
 extern "C" int nhvr_loss_pair_bwd(const float* a, const float* b, int64_t n, int32_t mode, float target, float coef,

@@ -167,3 +167,31 @@ def feature_matching_diff(pred_fake, pred_real, n_layers_D: int = 3, num_D: int 
             term = l1_diff(pred_fake[i][j], pred_real[i][j], d_w * feat_w * lambda_feat)
             total = term if total is None else total + term
     return total
+
+
+class _TemporalLoss(torch.autograd.Function):
+    """coef * L1(out_t - warp(out_{t-1}.detach(), flow_inv_t))  [REF pretrain_start.sh:21-22,37 --lambda_Temp; SPEC D11]."""
+
+    @staticmethod
+    def forward(ctx, cur, prev, flow, coef):
+        c, p, f = _f32(cur), _f32(prev), _f32(flow)
+        N, Cc, H, W = c.shape
+        acc = _acc(c.device)
+        check(load().nhvr_loss_temporal(c.data_ptr(), p.data_ptr(), f.data_ptr(), N, Cc, H, W, acc.data_ptr(), stream_ptr()),
+              "nhvr_loss_temporal")
+        ctx.saved = (c, p, f, float(coef))
+        return (coef * acc[0] / c.numel()).float()
+
+    @staticmethod
+    def backward(ctx, gout):
+        c, p, f, coef = ctx.saved
+        N, Cc, H, W = c.shape
+        g = torch.empty_like(c)
+        gs = gout.detach().reshape(1).float().contiguous()
+        check(load().nhvr_loss_temporal_bwd(c.data_ptr(), p.data_ptr(), f.data_ptr(), N, Cc, H, W, coef, gs.data_ptr(), g.data_ptr(),
+                                            stream_ptr()), "nhvr_loss_temporal_bwd")
+        return g, None, None, None
+
+
+def temporal_diff(out_t, out_prev, flow_inv, coef: float = 1.0):
+    return _TemporalLoss.apply(out_t, out_prev.detach(), flow_inv, coef)

@@ -523,15 +523,19 @@ class MultiscaleDiscriminatorB200(nn.Module):
             h, w = (h + 1) // 2, (w + 1) // 2
         return engs
 
-    def forward(self, x):
-        if not x.is_cuda:
-            raise NhvrError("nhvr_b200 modules take CUDA tensors only (no CPU fallback)")
-        x = x.contiguous().float()
-        N, C, H, W = x.shape
-        train = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
-        engs = self._scale_engines(N, H, W, x.device, train)
+    def forward(self, x, *more):
+        """x (and optional further tensors, concatenated along C: condition + image) -> per-scale lists."""
+        xs = [t.contiguous().float() for t in (x,) + tuple(more)]
+        for t in xs:
+            if not t.is_cuda:
+                raise NhvrError("nhvr_b200 modules take CUDA tensors only (no CPU fallback)")
+        if sum(t.shape[1] for t in xs) != self.input_nc:
+            raise NhvrError("expected %d input channels, got %d" % (self.input_nc, sum(t.shape[1] for t in xs)))
+        N, _, H, W = xs[0].shape
+        train = torch.is_grad_enabled() and (any(t.requires_grad for t in xs) or any(p.requires_grad for p in self.parameters()))
+        engs = self._scale_engines(N, H, W, xs[0].device, train)
         result = []
-        xd = x
+        xd = xs
         for i, eng in enumerate(engs):
             eng.maybe_repack()
             n_feats = len(eng.plans) - 1 if self.getIntermFeat else 0
@@ -539,13 +543,13 @@ class MultiscaleDiscriminatorB200(nn.Module):
                 params = []
                 for Lr in eng.chain:
                     params += [Lr["params"].weight, Lr["params"].bias]
-                outs = _ChainFunction.apply(eng, 1, n_feats, xd, *params)
+                outs = _ChainFunction.apply(eng, len(xd), n_feats, *xd, *params)
                 result.append(list(outs) if n_feats else [outs])
             else:
-                out = eng.run([xd]).clone()
+                out = eng.run(xd).clone()
                 result.append([eng.feature(j) for j in range(1, n_feats + 1)] + [out])
             if i != self.num_D - 1:
-                xd = ops.avgpool3s2(xd)
+                xd = [ops.avgpool3s2(t) for t in xd]
         return result
 
 

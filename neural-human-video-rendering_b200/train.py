@@ -82,3 +82,70 @@ def synthetic_densepose(N: int, H: int, W: int, device, seed: int = 0):
     dp_uv = torch.rand(N, 2, H, W, generator=g)
     pose = torch.tanh(torch.nn.functional.interpolate(torch.randn(N, 3, 16, 16, generator=g), size=(H, W), mode="bilinear") * 2)
     return pose.to(device), dp_i.to(device), dp_uv.to(device)
+
+
+class RenderTrainer:
+    """configs[2]: the end-to-end training step of train.py [REF train_start/pretrain_start.sh:9-37].
+
+    Two consecutive frames per sample (the temporal term needs t-1): frame t-1 is rendered without gradient
+    from a zero previous frame, frame t is conditioned on it.  Objectives (pix2pixHD + the reference's lambdas):
+      D: 0.5 * (LSGAN(D(cond, fake.detach()), 0) + LSGAN(D(cond, real), 1))
+      G: LSGAN(D(cond, fake), 1) + lambda_feat * FM + lambda_L2 * MSE + lambda_UV * UV + lambda_Prob * CE
+         + lambda_Temp * L1(out_t - warp(out_{t-1}, flow_inv))
+    Adam(2e-4, beta1 0.5) for the G side (three networks, atlas, background image) and for D.  Under
+    torch.distributed each side does ONE flat-bucket NCCL all-reduce after its backward.
+    """
+
+    def __init__(self, pipe, netD, lr=2e-4, beta1=0.5, lambda_feat=10.0, lambda_l2=500.0, lambda_uv=1000.0, lambda_prob=10.0,
+                 lambda_temp=500.0, n_layers_D=3, num_D=2, distributed=False):
+        self.pipe, self.netD = pipe, netD
+        self.lam = dict(feat=lambda_feat, l2=lambda_l2, uv=lambda_uv, prob=lambda_prob, temp=lambda_temp)
+        self.n_layers_D, self.num_D = n_layers_D, num_D
+        self.opt_G = torch.optim.Adam(self.pipe.parameters(), lr=lr, betas=(beta1, 0.999))
+        self.opt_D = torch.optim.Adam(self.netD.parameters(), lr=lr, betas=(beta1, 0.999))
+        self.bucket_G = FlatGradBucket(self.pipe.parameters()) if distributed else None
+        self.bucket_D = FlatGradBucket(self.netD.parameters()) if distributed else None
+
+    def step(self, batch: dict) -> dict:
+        pipe, D, lam = self.pipe, self.netD, self.lam
+        pose0, pose1, real1 = batch["pose_prev"], batch["pose"], batch["image"]
+        with torch.no_grad():
+            r0 = pipe.forward_train(pose0, torch.zeros_like(real1))
+        r1 = pipe.forward_train(pose1, r0["out"])
+        fake = r1["out"]
+        # ---- discriminator
+        self.opt_D.zero_grad(set_to_none=True)
+        pred_fake_d = D(pose1, fake.detach())
+        pred_real = D(pose1, real1)
+        loss_D = losses.lsgan_diff(pred_fake_d, False, 0.5) + losses.lsgan_diff(pred_real, True, 0.5)
+        loss_D.backward()
+        if self.bucket_D is not None:
+            self.bucket_D.all_reduce_mean()
+        self.opt_D.step()
+        # ---- generator side
+        self.opt_G.zero_grad(set_to_none=True)
+        for p in D.parameters():
+            p.requires_grad_(False)
+        pred_fake = D(pose1, fake)
+        loss_G = (losses.lsgan_diff(pred_fake, True)
+                  + losses.feature_matching_diff(pred_fake, [[t.detach() for t in s] for s in pred_real], self.n_layers_D, self.num_D, lam["feat"])
+                  + losses.mse_diff(fake, real1, lam["l2"])
+                  + losses.uv_prob_objective(r1["uvp"], batch["dp_i"], batch["dp_uv"], lam["uv"], lam["prob"])
+                  + losses.temporal_diff(fake, r0["out"], batch["flow_inv"], lam["temp"]))
+        loss_G.backward()
+        for p in D.parameters():
+            p.requires_grad_(True)
+        if self.bucket_G is not None:
+            self.bucket_G.all_reduce_mean()
+        self.opt_G.step()
+        return {"loss_D": loss_D.detach(), "loss_G": loss_G.detach()}
+
+
+def synthetic_train_batch(N: int, size: int, device, seed: int = 0) -> dict:
+    """Synthetic sample of the end-to-end shapes (SURVEY §8d cfg 3): poses, real image U(-1,1), DensePose IUV, flow N(0, 2 px)."""
+    pose, dp_i, dp_uv = synthetic_densepose(N, size, size, device, seed)
+    g = torch.Generator().manual_seed(seed + 1000)
+    pose_prev = torch.roll(pose, shifts=3, dims=-1)
+    image = torch.tanh(torch.nn.functional.interpolate(torch.randn(N, 3, 32, 32, generator=g), size=(size, size), mode="bilinear")).to(device)
+    flow = (torch.randn(N, 2, size, size, generator=g) * 2.0).to(device)
+    return {"pose_prev": pose_prev, "pose": pose, "image": image, "dp_i": dp_i, "dp_uv": dp_uv, "flow_inv": flow}

@@ -442,3 +442,42 @@ def test_discriminator_backward_parity(cuda_dev):
             continue
         cos = torch.nn.functional.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0).item()
         assert cos >= 0.99, (name, cos)
+
+
+def test_full_training_step_runs_and_matches_oracle_losses(cuda_dev):
+    """configs[2] in miniature: one RenderTrainer step (D step + G step) — its loss values against the oracle's
+    formulas on the same weights/batch, and a few steps of Adam change every parameter group."""
+    from nhvr_b200.networks import define_D
+    from nhvr_b200.train import RenderTrainer, synthetic_train_batch
+    from oracle import losses as O
+    from oracle.networks import define_D as oracle_define_D
+    from oracle.texture import texture_sample, composite
+    pipe, ref = _pair_pipeline(cuda_dev, _small_kw(), seed=91)
+    torch.manual_seed(92)
+    refD = oracle_define_D(6, 16, 3, "instance", False, 2, True).to(cuda_dev)
+    netD = define_D(6, 16, 3, "instance", False, 2, True)
+    netD.load_state_dict(refD.state_dict())
+    batch = synthetic_train_batch(2, 64, cuda_dev, seed=5)
+    # oracle losses at the initial weights
+    with torch.no_grad():
+        def frame(pose, prev):
+            uvp = ref.netTransG(pose)
+            tex, _, _ = texture_sample(uvp, ref.atlas, True)
+            fgm = ref.netG(torch.cat([tex, pose, prev], 1))
+            return uvp, composite(fgm, ref.netBG(ref.bg.unsqueeze(0))[0])
+        _, out0 = frame(batch["pose_prev"], torch.zeros_like(batch["image"]))
+        uvp1, out1 = frame(batch["pose"], out0)
+        pf, pr = refD(torch.cat([batch["pose"], out1], 1)), refD(torch.cat([batch["pose"], batch["image"]], 1))
+        lD = 0.5 * (O.gan_loss(pf, False) + O.gan_loss(pr, True))
+    trainer = RenderTrainer(pipe, netD)
+    before = {k: v.detach().clone() for k, v in list(pipe.named_parameters()) + list(netD.named_parameters())}
+    out = trainer.step(batch)
+    assert abs(out["loss_D"].item() - lD.item()) <= 2e-2 * abs(lD.item()), (out["loss_D"].item(), lD.item())
+    for _ in range(2):
+        out = trainer.step(batch)
+    assert torch.isfinite(out["loss_G"]) and torch.isfinite(out["loss_D"])
+    changed = [k for k, v in list(pipe.named_parameters()) + list(netD.named_parameters())
+               if not k.endswith(".bias") and (v.detach() - before[k]).abs().max().item() > 0]
+    assert any(k.startswith("netTransG") for k in changed) and any(k.startswith("netG") for k in changed)
+    assert any(k.startswith("netBG") for k in changed) and "atlas" in changed and "bg" in changed
+    assert any(k.startswith("scale0") for k in changed) and any(k.startswith("scale1") for k in changed)
