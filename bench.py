@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_train", action="store_true", help="skip the configs[1] training leg")
     ap.add_argument("--train_batch", type=int, default=16)
+    ap.add_argument("--train_e2e_batch", type=int, default=8, help="configs[2] batch per GPU (0 = skip that leg)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -321,6 +322,35 @@ def main():
                              % (TS, TS, TB, ", NCCL gradient all-reduce" if world > 1 else ""),
                  "steps_per_s": 1000.0 / tms, "ms_per_step": tms, "samples_per_s": world * TB * 1000.0 / tms,
                  "conv_tflops_fwd_dgrad_wgrad": 3.0 * fwd_flops / (tms * 1e-3) / 1e12, "final_loss": float(last)}
+        # ---- configs[2]: end-to-end training step (UV gen + lookup + temporal generator + multiscale PatchGAN D)
+        if args.train_e2e_batch > 0:
+            from nhvr_b200.networks import define_D
+            from nhvr_b200.train import RenderTrainer, synthetic_train_batch
+            del trainer, netT
+            torch.cuda.empty_cache()
+            torch.manual_seed(0)
+            pipe2 = RenderPipeline(**PIPE_KW).to(dev)
+            netD = define_D(6, 64, 3, "instance", False, 2, True, gpu_ids=[local])
+            tr = RenderTrainer(pipe2, netD, distributed=world > 1)
+            EB = args.train_e2e_batch
+            batch = synthetic_train_batch(EB, SIZE, dev, seed=rank)
+            for _ in range(2):
+                tr.step(batch)
+            barrier()
+            KE = 5
+            t0.record()
+            for _ in range(KE):
+                o = tr.step(batch)
+            t1.record()
+            barrier()
+            tt = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ems = float(tt.item()) / KE
+            train["e2e_step"] = {"workload": "configs[2]: end-to-end train step 512x512, batch %d/GPU (2 frames/sample: t-1 without grad), "
+                                             "G-side + multiscale PatchGAN D, Adam%s" % (EB, ", NCCL all-reduce x2" if world > 1 else ""),
+                                 "steps_per_s": 1000.0 / ems, "ms_per_step": ems, "samples_per_s": world * EB * 1000.0 / ems,
+                                 "loss_G": float(o["loss_G"]), "loss_D": float(o["loss_D"])}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -183,3 +183,38 @@ def test_checkpoint_naming_roundtrip(tmp_path):
     for (k, v), (_, w) in zip(a.state_dict().items(), b.state_dict().items()):
         assert torch.equal(v.cpu(), w.cpu()), k
     assert not load_pipeline(b, str(tmp_path), 31)
+
+
+def _bucket_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from nhvr_b200.train import FlatGradBucket
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2, 2))]
+    params[0].grad = torch.full((3, 4), float(rank + 1))
+    params[1].grad = torch.arange(5, dtype=torch.float32) * (rank + 1)
+    params[2].grad = None                                     # a parameter that received no gradient on this rank
+    b = FlatGradBucket(params)
+    b.all_reduce_mean()
+    if rank == 0:
+        q.put([p.grad.tolist() for p in params])
+    dist.destroy_process_group()
+
+
+def test_flat_grad_bucket_allreduce_world_size_2_gloo():
+    """The training path's only collective: one flat all-reduce averaging the gradients over ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    g0, g1, g2 = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert g0 == [[1.5] * 4] * 3                               # mean of 1 and 2
+    assert g1 == [0.0, 1.5, 3.0, 4.5, 6.0]
+    assert g2 == [[0.0, 0.0], [0.0, 0.0]]
