@@ -39,14 +39,16 @@ NHVR_DEVINL void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
 NHVR_DEVINL void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait WITH a suspend-time hint: the waiting thread is descheduled by the hardware until the phase
+// completes (or the hint expires) instead of busy-polling and stealing issue slots from the MMA warp.
 NHVR_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
@@ -54,8 +56,16 @@ NHVR_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 NHVR_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) { __trap(); }
+    if (++spins > (1u << 22)) { __trap(); }
   }
+}
+// Long waits of whole warps (epilogue waiting for the accumulator): one lane polls, the others park at a
+// warp barrier, so at most one thread per warp competes for issue slots.
+NHVR_DEVINL void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+  // every lane observes the completed phase once (acquire) before touching the data it guards
+  while (!mbar_try_wait(bar, parity)) {}
 }
 
 // ------------------------------------------------------------------ bulk async copy (1-D TMA, SASS UBLKCP)

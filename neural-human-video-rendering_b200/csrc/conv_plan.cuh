@@ -47,7 +47,7 @@ struct ConvKParams {
   ActGeom og;              // BIAS_ACT_P8 destination
   int32_t mmas_per_chunk, stages_per_chunk;
   ConvRun runs[kMaxRuns];
-  ConvMma mma[kMaxMma];
+  ConvMma mma[kMaxMma + 1];   // +1: the issue loop prefetches one entry ahead
 };
 
 

@@ -174,36 +174,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
       const uint32_t a_lo0 = ((smem_u32(a_smem) & 0x3FFFFu) >> 4) | (a_lbo_u << 16);
       const uint32_t b_lo0 = ((smem_u32(b_smem) & 0x3FFFFu) >> 4) | (b_lbo_u << 16);
       const uint32_t a_stage_u = a_stage_bytes >> 4, b_block_u = b_block_bytes >> 4;
-      const int nmma = P.mmas_per_chunk, bpb = P.bpb, SA = P.SA, SB = P.SB, nchunks = P.nchunks;
-      const int dbg = P.debug;
-      int ast = 0, bst = 0, bi = 0;
+      const int bpb = P.bpb, SA = P.SA, SB = P.SB, nchunks = P.nchunks, spc = P.stages_per_chunk;
+      int ast = 0, bst = 0;
       uint32_t aph = 0, bph = 0;
       uint32_t b_lo = b_lo0;
       const bool leader = elect_one();
+      // chunk -> weight stage -> MMA.  All ring bookkeeping sits at stage granularity (bpb divides the MMAs of a
+      // chunk by construction); the innermost loop is: load table entry, two adds, tcgen05.mma.
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(&a_full[ast], aph);
-        tc_fence_after();
         const uint32_t a_st_lo = a_lo0 + (uint32_t)ast * a_stage_u;
-        const uint32_t first_mask = (c == 0) ? 1u : 0u;
-#pragma unroll 2
-        for (int i = 0; i < nmma; ++i) {
-          const ConvMma e = P.mma[i];
-          if (bi == 0) {
-            mbar_wait(&b_full[bst], bph);
-            tc_fence_after();
+        const uint32_t keep_mask = (c == 0) ? 0u : 1u;          // chunk 0: the first MMA of an accumulator overwrites
+        const ConvMma* e = P.mma;
+        ConvMma cur = e[0];                                   // software-pipelined table read: the constant-bank
+        for (int s = 0; s < spc; ++s) {                       // load of entry i+1 overlaps the issue of MMA i
+          mbar_wait(&b_full[bst], bph);
+          tc_fence_after();
+#pragma unroll 1
+          for (int k = 0; k < bpb; ++k) {
+            ++e;
+            const ConvMma nxt = *e;                           // one entry past the end is still inside ConvKParams
+            if (leader) {
+              umma_bf16(tmem_base + cur.acc_col, ((uint64_t)desc_hi << 32) | (a_st_lo + (uint32_t)cur.a_off),
+                        ((uint64_t)desc_hi << 32) | b_lo, idesc, keep_mask | ((uint32_t)cur.first ^ 1u));
+            }
+            b_lo += b_block_u;
+            cur = nxt;
           }
-          const uint64_t adesc = ((uint64_t)desc_hi << 32) | (a_st_lo + ((dbg & 2) ? 0u : (uint32_t)e.a_off));
-          const uint64_t bdesc = ((uint64_t)desc_hi << 32) | b_lo;
-          if (leader) {
-            if (!(dbg & 1)) umma_bf16(tmem_base + e.acc_col, adesc, bdesc, idesc, (first_mask & e.first) ^ 1u);
-            if (dbg & 4) umma_bf16(tmem_base + e.acc_col, adesc, bdesc, idesc, 1u);
-          }
-          b_lo += b_block_u;
-          if (++bi == bpb) {
-            if (leader) umma_commit(&b_empty[bst]);
-            bi = 0;
-            if (++bst == SB) { bst = 0; bph ^= 1u; b_lo = b_lo0; }
-          }
+          if (leader) umma_commit(&b_empty[bst]);
+          if (++bst == SB) { bst = 0; bph ^= 1u; b_lo = b_lo0; }
         }
         if (leader) umma_commit(&a_empty[ast]);
         if (++ast == SA) { ast = 0; aph ^= 1u; }
@@ -225,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
     const int cout_off = split * P.Npad;
     const int ngroups = P.Npad >> 4;
 
-    mbar_wait(acc_full, 0);
+    mbar_wait_warp(acc_full, 0);
     tc_fence_after();
 
     for (int a = 0; a < ((P.debug & 8) ? 0 : P.nacc); ++a) {
@@ -534,7 +533,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
       if (bpc > kMaxMma) continue;
       const long rem = budget - a_bytes - 1024 - (long)Npad * 8;
       for (int dv = 8; dv >= 1; --dv) {                      // blocks per B stage: a divisor of bpc, stage <= 16 KB
-        if (bpc % dv || (long)dv * b_block > 16384) continue;
+        if (bpc % dv || (long)dv * b_block > 24576) continue;
         const int sb = (int)std::min<long>(6, rem / ((long)dv * b_block));
         if (sb < 2) continue;
         // score: weight bytes in flight, mild preference for >= 3 stages and for fewer, larger chunks

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     const int m = we * 32 + lane;
     const int co = co_blk * kTileM + m;
     const uint32_t t_lane = tmem_base + ((uint32_t)(we * 32) << 16);
-    mbar_wait(acc_full, 0);
+    mbar_wait_warp(acc_full, 0);
     tc_fence_after();
     if (c_end > c_begin) {
       for (int t = 0; t < ntaps; ++t) {

@@ -1,0 +1,76 @@
+// Micro-benchmark: back-to-back tcgen05.mma from resident shared memory (no loads), to separate the tensor
+// pipe / operand-fetch rate from the operand pipeline.  Varies N, operand layout (un-swizzled K-major as the
+// conv kernel uses it vs SWIZZLE_128B K-major), and A start alignment (shifted views).
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include "../../neural-human-video-rendering_b200/csrc/common.cuh"
+using namespace nhvr;
+
+__global__ void __launch_bounds__(128, 1) mma_bench(int N, int iters, int mode, int shift_units, int two_acc, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_ptr, 512); tmem_relinquish(); }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_ptr;
+  if (warp == 1) {
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_16(128, (uint32_t)N, 0);
+    const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + 96 * 1024);
+    uint64_t adesc, bdesc;
+    if (mode == 0) {   // un-swizzled K-major: rows 16 B apart, SBO 128 B, LBO = plane stride (here 8 KB)
+      adesc = make_desc_nosw(a_base + shift_units * 16, 8192, 128);
+      bdesc = make_desc_nosw(b_base, (uint32_t)N * 16, 128);
+    } else {           // SWIZZLE_128B K-major: rows 128 B, 8-row atoms of 1024 B (SBO), layout type 2
+      adesc = ((uint64_t)((a_base & 0x3FFFF) >> 4)) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      bdesc = ((uint64_t)((b_base & 0x3FFFF) >> 4)) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    }
+    __syncwarp();
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      if (leader) {
+        umma_bf16(tmem + ((two_acc && (i & 1)) ? 256 : 0), adesc + (uint64_t)((i & 3) * 2), bdesc, idesc, 1u);
+      }
+    }
+    if (leader) umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (leader && blockIdx.x == 0) cycles[0] = t1 - t0;
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+int main() {
+  long long* d; cudaMalloc(&d, 8);
+  cudaFuncSetAttribute(mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const int iters = 4096;
+  printf("%-10s %-6s %-6s %-8s %10s %12s\n", "layout", "N", "shift", "accs", "cyc/MMA", "TFLOP/s@148");
+  for (int mode = 0; mode < 2; ++mode)
+    for (int N : {16, 48, 80, 96, 192, 256})
+      for (int shift : {0, 1})
+        for (int two : {0, 1}) {
+          if (mode == 1 && shift) continue;
+          if (two && N > 256) continue;
+          long long h = 0;
+          for (int rep = 0; rep < 2; ++rep) {
+            mma_bench<<<148, 128, 200 * 1024>>>(N, iters, mode, shift, two, d);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+          }
+          cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+          const double cyc = (double)h / iters;
+          printf("%-10s %-6d %-6d %-8d %10.1f %12.1f\n", mode ? "sw128" : "nosw", N, shift, two + 1, cyc,
+                 2.0 * 128 * N * 16 / cyc * 1.9e9 * 148 / 1e12);
+        }
+  return 0;
+}
