@@ -72,6 +72,7 @@ typedef struct nhvr_conv_desc {
   int32_t in_extra_rows; /* extra zero rows below the input's bottom halo (gradient buffers shared with wgrad) */
   int32_t in_extra_cols; /* extra zero columns right of the input's right halo (same purpose)                 */
   int32_t out_h, out_w;  /* NHVR_CONV_TRANSPOSE only: output size override (0 = 2H x 2W for k3, 2H-2 for k4)  */
+  int32_t flags;         /* bit 0: never use the row-mode lowering (wide kernels with few output channels)    */
 } nhvr_conv_desc;
 
 typedef struct nhvr_conv_plan nhvr_conv_plan;   /* opaque, host memory only */

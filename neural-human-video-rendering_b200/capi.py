@@ -34,7 +34,7 @@ class ActDesc(C.Structure):
 
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
-                ("kind", "Cin", "Cout", "kh", "kw", "stride", "pad", "N", "H", "W", "halo", "epilogue", "act", "in_extra_rows", "in_extra_cols", "out_h", "out_w")]
+                ("kind", "Cin", "Cout", "kh", "kw", "stride", "pad", "N", "H", "W", "halo", "epilogue", "act", "in_extra_rows", "in_extra_cols", "out_h", "out_w", "flags")]
 
 
 # every symbol include/nhvr.h declares: name -> (restype, argtypes)

@@ -46,6 +46,8 @@ struct ConvKParams {
   int32_t debug;           // NHVR_CONV_DEBUG experiments (results are wrong when set): 1 no MMA, 2 unshifted A, 4 double issue
   ActGeom og;              // BIAS_ACT_P8 destination
   int32_t mmas_per_chunk, stages_per_chunk;
+  int32_t tile_step;       // linear positions a CTA advances by: 128, or 128-(kw-1) in row mode
+  int32_t rowmode, Cp, kw; // row mode: accumulator column n = s*Cp + co, outputs = shifted sums over s (epilogue)
   ConvRun runs[kMaxRuns];
   ConvMma mma[kMaxMma + 1];   // +1: the issue loop prefetches one entry ahead
 };
@@ -62,6 +64,7 @@ struct PackParams {
   int32_t kcp, nchunks, njobs, Npad, nsplit, nblocks_padded;
   int32_t f16;
   int32_t flip;                // dgrad of a stride-1 conv: taps mirrored (r,s) -> (kh-1-r, kw-1-s)
+  int32_t rowmode, Cp;         // row mode: job_tap = r*8 + accumulator, column n = s*Cp + co
   int16_t job_tap[kMaxJobs];   // r*kw + s of each job
 };
 }  // namespace nhvr

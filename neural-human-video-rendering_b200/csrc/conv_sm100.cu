@@ -72,13 +72,73 @@ NHVR_DEVINL float apply_act(float x, int act, bool is_last) {
   }
 }
 
+// one 16-channel group of one output pixel: raw P8 store (+ InstanceNorm statistics), or bias + activation
+NHVR_DEVINL void emit16(const ConvKParams& P, const float (&v)[16], int c0, bool valid, int n, int Y, int X, int g_local, int lane,
+                        float* s_stats) {
+  if (P.epilogue == NHVR_EPI_RAW_STATS || P.epilogue == NHVR_EPI_RAW_P8) {
+    if (valid) {
+      uint4* o = reinterpret_cast<uint4*>(P.out);
+      const int64_t u0 = (((int64_t)n * P.Cout8 + (c0 >> 3)) * P.Ho + Y) * P.Wo + X;
+      const int64_t pstride = (int64_t)P.Ho * P.Wo;
+      uint4 lo, hi;
+      lo.x = pack2(v[0], v[1], P.f16);  lo.y = pack2(v[2], v[3], P.f16);
+      lo.z = pack2(v[4], v[5], P.f16);  lo.w = pack2(v[6], v[7], P.f16);
+      hi.x = pack2(v[8], v[9], P.f16);  hi.y = pack2(v[10], v[11], P.f16);
+      hi.z = pack2(v[12], v[13], P.f16); hi.w = pack2(v[14], v[15], P.f16);
+      if ((c0 >> 3) < P.Cout8) o[u0] = lo;
+      if ((c0 >> 3) + 1 < P.Cout8) o[u0 + pstride] = hi;
+    }
+    if (P.epilogue == NHVR_EPI_RAW_STATS && !(P.debug & 16)) {
+      float s[16], ss[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { s[i] = valid ? v[i] : 0.f; ss[i] = s[i] * s[i]; }
+      const float cs = warp_colsum16(s, lane);
+      const float css = warp_colsum16(ss, lane);
+      const int col = g_local * 16 + (lane >> 1);
+      atomicAdd(&s_stats[col * 2 + (lane & 1)], (lane & 1) ? css : cs);
+    }
+  } else if (P.epilogue == NHVR_EPI_BIAS_ACT_F32) {
+    if (valid) {
+      float* o = reinterpret_cast<float*>(P.out);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = c0 + i;
+        if (c < P.Cout) {
+          float val = v[i] + (P.bias ? __ldg(P.bias + c) : 0.f);
+          val = apply_act(val, P.act, c == P.Cout - 1);
+          o[(((int64_t)n * P.Cout + c) * P.Ho + Y) * P.Wo + X] = val;
+        }
+      }
+    }
+  } else {  // NHVR_EPI_BIAS_ACT_P8
+    if (valid) {
+      uint4* o = reinterpret_cast<uint4*>(P.out);
+      float t[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = c0 + i;
+        float val = (c < P.Cout) ? v[i] + (P.bias ? __ldg(P.bias + c) : 0.f) : 0.f;
+        t[i] = (c < P.Cout) ? apply_act(val, P.act, c == P.Cout - 1) : 0.f;
+      }
+      uint4 lo, hi;
+      lo.x = pack2(t[0], t[1], P.f16);  lo.y = pack2(t[2], t[3], P.f16);
+      lo.z = pack2(t[4], t[5], P.f16);  lo.w = pack2(t[6], t[7], P.f16);
+      hi.x = pack2(t[8], t[9], P.f16);  hi.y = pack2(t[10], t[11], P.f16);
+      hi.z = pack2(t[12], t[13], P.f16); hi.w = pack2(t[14], t[15], P.f16);
+      const int p0 = c0 >> 3;
+      if (p0 < P.og.C8) o[act_unit(P.og, n, p0, Y + P.og.pad_t, X + P.og.pad_l)] = lo;
+      if (p0 + 1 < P.og.C8) o[act_unit(P.og, n, p0 + 1, Y + P.og.pad_t, X + P.og.pad_l)] = hi;
+    }
+  }
+}
+
 constexpr int kThreads = 384;       // warps 0-3: roles, warps 4-11: epilogue
 
 __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __grid_constant__ ConvKParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.y, split = blockIdx.z;
-  const int64_t q0 = (int64_t)blockIdx.x * kTileM;
+  const int64_t q0 = (int64_t)blockIdx.x * P.tile_step;
   // K-chunk order is rotated per CTA: neighbouring CTAs stream different parts of the (shared) packed
   // weights at any instant instead of all hitting the same L2 lines in lock-step.
   const int rot = (int)(blockIdx.x % (unsigned)P.nchunks);
@@ -108,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
     tmem_relinquish();
   }
   if (warp >= 4) {
-    for (int i = threadIdx.x - 128; i < P.Npad * 2; i += 256) s_stats[i] = 0.f;
+    for (int i = threadIdx.x - 128; i < P.Npad * 2 * P.nacc; i += 256) s_stats[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -227,6 +287,49 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
     mbar_wait_warp(acc_full, 0);
     tc_fence_after();
 
+    if (P.rowmode) {
+      // ---- row mode: accumulator column n = s*Cp + co holds Z[m][s][co]; output Y[m][co] = sum_s Z[m+s][s][co].
+      // Warps 4-7 exchange one 16-column chunk at a time through shared memory (row m reads row m+s).
+      if (half == 0 && !(P.debug & 8)) {
+        float* S = s_stats + P.Npad * 2 * P.nacc;           // [128][17] floats
+        const bool valid = valid_m && (m < P.tile_step);
+        const int ngrp = (P.Cp + 15) >> 4;
+        for (int cg = 0; cg < ngrp; ++cg) {
+          float acc[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+          const int nchunk = (P.Cp >= 16) ? P.kw : (P.kw * P.Cp + 15) / 16;
+          for (int j = 0; j < nchunk; ++j) {
+            const int n0 = (P.Cp >= 16) ? (j * P.Cp + cg * 16) : j * 16;     // first accumulator column of this chunk
+            const int a = n0 / P.Npad;
+            uint32_t vr[16];
+            tmem_ld16(t_lane + (uint32_t)(a * P.Npad + (n0 - a * P.Npad)), vr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) S[m * 17 + i] = __uint_as_float(vr[i]);
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (P.Cp >= 16) {
+              if (m + j < kTileM) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] += S[(m + j) * 17 + i];
+              }
+            } else {                                          // Cp == 8: two filter columns per chunk
+              const int s0 = 2 * j, s1 = 2 * j + 1;
+              if (m + s0 < kTileM) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += S[(m + s0) * 17 + i];
+              }
+              if (s1 < P.kw && m + s1 < kTileM) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += S[(m + s1) * 17 + 8 + i];
+              }
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+          }
+          emit16(P, acc, cg * 16, valid, n, y, x, cg, lane, s_stats);
+        }
+      }
+    } else {
     for (int a = 0; a < ((P.debug & 8) ? 0 : P.nacc); ++a) {
       const int Y = y * P.oys + P.oy[a];
       const int X = x * P.oxs + P.ox[a];
@@ -238,69 +341,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(vr[i]);
-        const int c0 = cout_off + g * 16;
-
-        if (P.epilogue == NHVR_EPI_RAW_STATS || P.epilogue == NHVR_EPI_RAW_P8) {
-          if (valid) {
-            uint4* o = reinterpret_cast<uint4*>(P.out);
-            const int64_t u0 = (((int64_t)n * P.Cout8 + (c0 >> 3)) * P.Ho + Y) * P.Wo + X;
-            const int64_t pstride = (int64_t)P.Ho * P.Wo;
-            uint4 lo, hi;
-            lo.x = pack2(v[0], v[1], P.f16);  lo.y = pack2(v[2], v[3], P.f16);
-            lo.z = pack2(v[4], v[5], P.f16);  lo.w = pack2(v[6], v[7], P.f16);
-            hi.x = pack2(v[8], v[9], P.f16);  hi.y = pack2(v[10], v[11], P.f16);
-            hi.z = pack2(v[12], v[13], P.f16); hi.w = pack2(v[14], v[15], P.f16);
-            if ((c0 >> 3) < P.Cout8) o[u0] = lo;
-            if ((c0 >> 3) + 1 < P.Cout8) o[u0 + pstride] = hi;
-          }
-          if (P.epilogue == NHVR_EPI_RAW_STATS && !(P.debug & 16)) {
-          float s[16], ss[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { s[i] = valid ? v[i] : 0.f; ss[i] = s[i] * s[i]; }
-          const float cs = warp_colsum16(s, lane);
-          const float css = warp_colsum16(ss, lane);
-          const int col = g * 16 + (lane >> 1);
-          atomicAdd(&s_stats[col * 2 + (lane & 1)], (lane & 1) ? css : cs);
-          }
-        } else if (P.epilogue == NHVR_EPI_BIAS_ACT_F32) {
-          if (valid) {
-            float* o = reinterpret_cast<float*>(P.out);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int c = c0 + i;
-              if (c < P.Cout) {
-                float val = v[i] + (P.bias ? __ldg(P.bias + c) : 0.f);
-                val = apply_act(val, P.act, c == P.Cout - 1);
-                o[(((int64_t)n * P.Cout + c) * P.Ho + Y) * P.Wo + X] = val;
-              }
-            }
-          }
-        } else {  // NHVR_EPI_BIAS_ACT_P8
-          if (valid) {
-            uint4* o = reinterpret_cast<uint4*>(P.out);
-            float t[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int c = c0 + i;
-              float val = (c < P.Cout) ? v[i] + (P.bias ? __ldg(P.bias + c) : 0.f) : 0.f;
-              t[i] = (c < P.Cout) ? apply_act(val, P.act, c == P.Cout - 1) : 0.f;
-            }
-            uint4 lo, hi;
-            lo.x = pack2(t[0], t[1], P.f16);  lo.y = pack2(t[2], t[3], P.f16);
-            lo.z = pack2(t[4], t[5], P.f16);  lo.w = pack2(t[6], t[7], P.f16);
-            hi.x = pack2(t[8], t[9], P.f16);  hi.y = pack2(t[10], t[11], P.f16);
-            hi.z = pack2(t[12], t[13], P.f16); hi.w = pack2(t[14], t[15], P.f16);
-            const int p0 = c0 >> 3;
-            if (p0 < P.og.C8) o[act_unit(P.og, n, p0, Y + P.og.pad_t, X + P.og.pad_l)] = lo;
-            if (p0 + 1 < P.og.C8) o[act_unit(P.og, n, p0 + 1, Y + P.og.pad_t, X + P.og.pad_l)] = hi;
-          }
-        }
+        emit16(P, v, cout_off + g * 16, valid, n, Y, X, g, lane, s_stats);
       }
+    }
     }
     if (P.epilogue == NHVR_EPI_RAW_STATS) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
       float* gs = P.stats + ((int64_t)n * P.Cout8 * 8 + cout_off) * 2;
-      const int lim = min(P.Npad, P.Cout8 * 8 - cout_off) * 2;
+      const int lim = (P.rowmode ? P.Cout8 * 8 : min(P.Npad, P.Cout8 * 8 - cout_off)) * 2;
       for (int i = threadIdx.x - 128; i < lim; i += 256) atomicAdd(gs + i, s_stats[i]);
     }
   }
@@ -331,8 +379,14 @@ __global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
       const int qq = blk % qsteps;
       const int j = (blk / qsteps) % P.njobs;
       const int c = blk / (qsteps * P.njobs);
-      const int tap = P.flip ? (P.kh * P.kw - 1 - P.job_tap[j]) : P.job_tap[j];
-      const int co = z * P.Npad + nrow;
+      int tap = P.flip ? (P.kh * P.kw - 1 - P.job_tap[j]) : P.job_tap[j];
+      int co = z * P.Npad + nrow;
+      if (P.rowmode) {                       // job_tap = r*8 + accumulator; column n = s*Cp + co
+        const int r = P.job_tap[j] >> 3, ncol = (P.job_tap[j] & 7) * P.Npad + nrow;
+        const int sfl = ncol / P.Cp;
+        co = (sfl < P.kw) ? (ncol - sfl * P.Cp) : P.Cout;       // columns beyond kw*Cp are padding
+        tap = r * P.kw + min(sfl, P.kw - 1);
+      }
       float vals[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -381,6 +435,9 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   std::vector<std::pair<int, int>> run_specs;   // (g_off, len) before merging, indexed by run_key
   int nacc = 1;
   int Ho, Wo;
+  bool rowmode = false;
+  int row_npad = 0;
+  K.tile_step = kTileM;
 
   if (d->kind == NHVR_CONV && d->stride == 1) {
     in.pad_t = in.pad_b = in.pad_l = in.pad_r = d->pad;
@@ -388,9 +445,28 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
     Ho = d->H + 2 * d->pad - d->kh + 1;
     Wo = d->W + 2 * d->pad - d->kw + 1;
     if (Ho <= 0 || Wo <= 0) { delete p; return NHVR_ERR_SHAPE; }
-    for (int r = 0; r < d->kh; ++r) run_specs.push_back({r * Wp, kTileM + d->kw - 1});
-    for (int r = 0; r < d->kh; ++r)
-      for (int s = 0; s < d->kw; ++s) taps.push_back({r, s, 0, r * d->kw + s});
+    // Row mode (wide kernels, few output channels: the 7x7 stems / RGB head): instead of kh*kw MMAs of N = Cout,
+    // issue kh MMAs of N = kw*Cp whose column n = s*Cp + co accumulates filter column s un-shifted; the epilogue
+    // adds Z[m+s][s][co] over s.  kw x fewer MMAs and A-operand reads; tiles advance by 128-(kw-1) positions.
+    const int Cp_row = d->Cout <= 8 ? 8 : round_up(d->Cout, 16);
+    // measured (profiles/r01_selftest_v5_rowmode.log): 2x on the 48->4 head; the 16->48 stem loses 2x (two 176-column
+    // accumulators need all 512 TMEM columns -> one CTA per SM, epilogue-bound), so only narrow outputs qualify
+    rowmode = !(d->flags & 1) && d->kw >= 5 && d->kw <= 8 && d->kw * Cp_row <= 128 && !std::getenv("NHVR_NO_ROWMODE") &&
+              d->epilogue != NHVR_EPI_BIAS_ACT_P8;
+    if (rowmode) {
+      const int ntot = d->kw * Cp_row;
+      nacc = (ntot + 255) / 256;
+      row_npad = round_up((ntot + nacc - 1) / nacc, 16);
+      for (int r = 0; r < d->kh; ++r) run_specs.push_back({r * Wp, kTileM});
+      for (int r = 0; r < d->kh; ++r)
+        for (int a = 0; a < nacc; ++a) taps.push_back({r, 0, a, r * 8 + a});
+      K.rowmode = 1; K.Cp = Cp_row; K.kw = d->kw;
+      K.tile_step = kTileM - (d->kw - 1);
+    } else {
+      for (int r = 0; r < d->kh; ++r) run_specs.push_back({r * Wp, kTileM + d->kw - 1});
+      for (int r = 0; r < d->kh; ++r)
+        for (int s = 0; s < d->kw; ++s) taps.push_back({r, s, 0, r * d->kw + s});
+    }
     K.Wrow = Wp; K.Hv = Ho; K.Wv = Wo; K.oys = K.oxs = 1;
   } else if (d->kind == NHVR_CONV_DGRAD_S1) {
     // d describes the FORWARD conv (Cin, Cout, k, pad, input H x W).  dX over the padded input extent is the
@@ -505,10 +581,10 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   for (int j = 0; j < K.njobs; ++j) p->jobs_h[j] = jobs[j];
 
   // ---- N (Cout) tiling
-  int Npad = round_up(gemm_n, 16);
+  int Npad = rowmode ? row_npad : round_up(gemm_n, 16);
   int nsplit = 1;
   const int max_n = 256 / (nacc > 2 ? 2 : 1) / (nacc > 1 ? 2 : 1);   // nacc*Npad <= 512 and Npad <= 256
-  while (Npad > std::min(256, 512 / nacc)) { nsplit *= 2; Npad = round_up((gemm_n + nsplit - 1) / nsplit, 16); }
+  while (!rowmode && Npad > std::min(256, 512 / nacc)) { nsplit *= 2; Npad = round_up((gemm_n + nsplit - 1) / nsplit, 16); }
   (void)max_n;
   K.Npad = Npad;
   K.tmem_cols = next_pow2_cols(nacc * Npad);
@@ -531,7 +607,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
       const long a_bytes = (long)sa * cand * slab * 16;
       const int bpc = (int)taps.size() * cand / 2;          // MMA blocks per chunk
       if (bpc > kMaxMma) continue;
-      const long rem = budget - a_bytes - 1024 - (long)Npad * 8;
+      const long rem = budget - a_bytes - 1024 - (long)Npad * 8 * nacc - (rowmode ? 8704 : 0);
       for (int dv = 8; dv >= 1; --dv) {                      // blocks per B stage: a divisor of bpc, stage <= 16 KB
         if (bpc % dv || (long)dv * b_block > 24576) continue;
         const int sb = (int)std::min<long>(6, rem / ((long)dv * b_block));
@@ -574,13 +650,13 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   K.w_split_units = (int64_t)nblocks_padded * 2 * Npad;
   p->weight_bytes = (size_t)nsplit * K.w_split_units * 16;
   p->smem_bytes = (size_t)SA * kcp * slab * 16 + (size_t)SB * bpb * b_block + (size_t)(2 * SA + 2 * SB + 1) * 8 + 8 +
-                  (size_t)Npad * 8 + 128;
+                  (size_t)Npad * 8 * nacc + (rowmode ? 8704 : 0) + 128;
 
   if (!(d->kind == NHVR_CONV && d->stride == 2)) in.pad_b += d->in_extra_rows;   // plain formats: only the plane stride grows
   ActGeom gin = make_geom(in);
   K.in_plane_units = gin.plane_units;
   const int64_t last_q = (int64_t)(K.Hv - 1) * K.Wrow + K.Wv;   // one past the last valid linear position
-  p->tiles_per_img = (int)((last_q + kTileM - 1) / kTileM);
+  p->tiles_per_img = (int)((last_q + K.tile_step - 1) / K.tile_step);
 
   PackParams& PP = p->pp;
   PP.Cin = gemm_k; PP.Cout = gemm_n; PP.kh = d->kh; PP.kw = d->kw;
@@ -588,6 +664,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   // Conv2d weight [Cout][Cin] seen from its dgrad (K = Cout, N = Cin)
   PP.transposed = (d->kind == NHVR_CONV_TRANSPOSE || d->kind == NHVR_CONV_DGRAD_S1);
   PP.flip = (d->kind == NHVR_CONV_DGRAD_S1);
+  PP.rowmode = rowmode ? 1 : 0; PP.Cp = K.Cp;
   PP.kcp = kcp; PP.nchunks = K.nchunks; PP.njobs = K.njobs; PP.Npad = Npad; PP.nsplit = nsplit;
   PP.nblocks_padded = nblocks_padded;
   *out = p;

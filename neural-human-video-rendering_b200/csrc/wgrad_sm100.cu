@@ -224,6 +224,7 @@ extern "C" int nhvr_wgrad_plan_create(const nhvr_conv_desc* fwd, nhvr_wgrad_plan
   nhvr_conv_desc fd = *fwd;
   fd.epilogue = NHVR_EPI_RAW_P8;
   fd.in_extra_rows = fd.in_extra_cols = 0;
+  fd.flags |= 1;            // the tap program of the plain lowering is what wgrad mirrors
   nhvr_conv_plan* fp = nullptr;
   int st = nhvr_conv_plan_create(&fd, &fp);
   if (st != NHVR_OK) return st;
