@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--clips", type=int, default=4, help="independent clips advanced in lock-step per GPU")
+    ap.add_argument("--clips", type=int, default=8, help="independent clips advanced in lock-step per GPU")
     ap.add_argument("--impl", type=str, default="b200")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_train", action="store_true", help="skip the configs[1] training leg")

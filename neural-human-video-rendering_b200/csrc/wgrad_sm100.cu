@@ -28,7 +28,7 @@ extern int arch_ok_cached();
 extern int operand_f16();
 
 constexpr int kWgMaxTaps = 52;
-constexpr int kWgThreads = 256;   // warp0 producer, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
+constexpr int kWgThreads = 256;   // warps 0,2,3 producers (2 also TMEM alloc), warp1 MMA, warps 4-7 epilogue
 
 struct WgTap {
   int32_t x_off;    // shift (units) inside the X plane slab
@@ -93,29 +93,37 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   const int c_end = min(c_begin + P.chunks_per_cta, P.nchunks_total);
   const int g_planes = min(16, P.C8g - co_blk * 16);      // planes that exist; the rest of the slab stays stale
                                                            // (rows of D that are never written out)
-  if (warp == 0) {
-    // ------------------------------------------------------------------ producer: G and X slabs of a chunk
+  if (warp == 0 || warp == 2 || warp == 3) {
+    // ------------------------------------------------------------------ producers: G and X slabs of a chunk
+    // The slabs are many small plane runs (2-6 KB each); one thread issuing them all is latency-bound on the
+    // per-copy address arithmetic, so three warps (0, 2 after its TMEM allocation, 3) each issue every third copy.
+    // Warp 0 alone arms the transaction count; copies of the other warps may complete before that (the
+    // transaction count is signed within a phase, the pending arrival keeps the phase open).
+    const int pid = (warp == 0) ? 0 : warp - 1;          // 0, 1, 2
     int st = 0;
     uint32_t ph = 0;
     const uint32_t bytes = (uint32_t)g_planes * P.gslab_units * 16u + x_stage_bytes;
+    const int ncopy_g = g_planes * P.ngruns, ncopy_x = P.nci8 * P.nxruns;
     for (int c = c_begin; c < c_end; ++c) {
       const int n = c / P.tiles_per_img;
       const int64_t q0 = (int64_t)(c - n * P.tiles_per_img) * kTileM;
       mbar_wait(&empty[st], ph ^ 1u);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&full[st], bytes);
+        if (pid == 0) mbar_arrive_expect_tx(&full[st], bytes);
         uint8_t* gdst = smem + (size_t)st * stage_bytes;
         uint8_t* xdst = gdst + g_stage_bytes;
         const uint4* gimg = P.g + ((int64_t)n * P.C8g + co_blk * 16) * P.g_plane_units + q0;
-        for (int pl = 0; pl < g_planes; ++pl)
-          for (int r = 0; r < P.ngruns; ++r)
-            bulk_g2s(gdst + ((size_t)pl * P.gslab_units + P.gruns[r].s_off) * 16, gimg + (int64_t)pl * P.g_plane_units + P.gruns[r].g_off,
-                     (uint32_t)P.gruns[r].len * 16u, &full[st]);
         const uint4* ximg = P.x + ((int64_t)n * P.C8x + ci_blk * P.nci8) * P.x_plane_units + q0;
-        for (int pl = 0; pl < P.nci8; ++pl)
-          for (int r = 0; r < P.nxruns; ++r)
-            bulk_g2s(xdst + ((size_t)pl * P.xslab_units + P.xruns[r].s_off) * 16, ximg + (int64_t)pl * P.x_plane_units + P.xruns[r].g_off,
-                     (uint32_t)P.xruns[r].len * 16u, &full[st]);
+        for (int i = pid; i < ncopy_g; i += 3) {
+          const int pl = i / P.ngruns, r = i - pl * P.ngruns;
+          bulk_g2s(gdst + ((size_t)pl * P.gslab_units + P.gruns[r].s_off) * 16, gimg + (int64_t)pl * P.g_plane_units + P.gruns[r].g_off,
+                   (uint32_t)P.gruns[r].len * 16u, &full[st]);
+        }
+        for (int i = pid; i < ncopy_x; i += 3) {
+          const int pl = i / P.nxruns, r = i - pl * P.nxruns;
+          bulk_g2s(xdst + ((size_t)pl * P.xslab_units + P.xruns[r].s_off) * 16, ximg + (int64_t)pl * P.x_plane_units + P.xruns[r].g_off,
+                   (uint32_t)P.xruns[r].len * 16u, &full[st]);
+        }
       }
       __syncwarp();
       if (++st == P.S) { st = 0; ph ^= 1u; }
@@ -296,36 +304,51 @@ extern "C" int nhvr_wgrad_plan_create(const nhvr_conv_desc* fwd, nhvr_wgrad_plan
   W.CoutP = wg_round_up(fwd->Cout, kTileM);
   W.CinP = xg.C8 * 8;
 
-  // ---- N (input channels per CTA) and tap groups: ntaps_grp * nci <= 512 TMEM columns
-  int nci = 0;
+  // ---- N (input channels per CTA), tap groups (ntaps_grp * nci <= 512 TMEM columns) and pipeline depth.
+  // Cost model per (chunk, all input channels): tensor time ~ ntaps * (CinP/nci) * 8 MMAs * cycles(nci), operand
+  // staging ~ ngroups * (CinP/nci) * stage_bytes / ~24 B per cycle; a stage must fit at least twice.
+  int nci = 0, best_groups = 1, best_S = 1;
+  double best_cost = 1e30;
   for (int cand : {64, 48, 32, 16}) {
     if (W.CinP % cand) continue;
-    if (cand * std::min(W.ntaps_total, 512 / cand) < 16) continue;
-    // prefer all taps in one group; otherwise the widest N
-    if (cand * W.ntaps_total <= 512) { nci = cand; break; }
-    if (!nci) nci = cand;
+    const int ngroups = (W.ntaps_total * cand + 511) / 512;
+    const size_t stage = (size_t)16 * gslab * 16 + (size_t)(cand / 8) * W.xslab_units * 16;
+    const int S = (int)std::min<size_t>(4, (size_t)(210 * 1024) / stage);
+    if (S < 1) continue;
+    const double cyc = cand == 64 ? 48.0 : cand == 48 ? 44.0 : cand == 32 ? 40.0 : 39.0;
+    const double blocks = (double)W.CinP / cand;
+    const double t_mma = W.ntaps_total * blocks * 8.0 * cyc;
+    const double t_ld = ngroups * blocks * (double)stage / 24.0;
+    double cost = std::max(t_mma, t_ld) + 0.25 * std::min(t_mma, t_ld);
+    if (S < 2) cost *= 2.0;                     // no overlap of staging and MMAs
+    if (cost < best_cost) { best_cost = cost; nci = cand; best_groups = ngroups; best_S = S; }
   }
-  if (!nci) { nhvr_conv_plan_destroy(fp); delete p; return NHVR_ERR_SHAPE; }
+  if (!nci) { nhvr_conv_plan_destroy(fp); delete p; return NHVR_ERR_SMEM; }
   W.nci = nci; W.nci8 = nci / 8;
-  W.ntaps_grp = std::min(W.ntaps_total, 512 / nci);
-  p->n_tap_groups = (W.ntaps_total + W.ntaps_grp - 1) / W.ntaps_grp;
+  p->n_tap_groups = best_groups;
+  W.ntaps_grp = (W.ntaps_total + best_groups - 1) / best_groups;        // balanced groups
   int cols = 32; while (cols < W.ntaps_grp * nci) cols <<= 1;
   W.tmem_cols = cols;
   W.n_ci_blocks = W.CinP / nci;
   p->n_co_blocks = W.CoutP / kTileM;
 
-  // ---- stages and K split
+  // ---- stages and K split: whole waves of 148 CTAs (one CTA per SM: TMEM / shared memory bound)
   const size_t stage = (size_t)16 * gslab * 16 + (size_t)W.nci8 * W.xslab_units * 16;
-  int S = (int)std::min<size_t>(4, (200 * 1024) / stage);
-  if (S < 1) { nhvr_conv_plan_destroy(fp); delete p; return NHVR_ERR_SMEM; }
-  W.S = S;
-  p->smem_bytes = S * stage + (2 * S + 1) * 8 + 16 + 128;
+  W.S = best_S;
+  p->smem_bytes = best_S * stage + (2 * best_S + 1) * 8 + 16 + 128;
   W.tiles_per_img = fp->tiles_per_img;
   W.nchunks_total = fp->tiles_per_img * fwd->N;
   const int ctas_other = p->n_co_blocks * W.n_ci_blocks * p->n_tap_groups;
-  int want_splits = std::max(1, (148 * 2 + ctas_other - 1) / ctas_other);
-  want_splits = std::min(want_splits, W.nchunks_total);
-  W.chunks_per_cta = (W.nchunks_total + want_splits - 1) / want_splits;
+  int best_split = 1;
+  double best_t = 1e30;
+  for (int sp = 1; sp <= std::min(W.nchunks_total, 64); ++sp) {
+    const int cpc = (W.nchunks_total + sp - 1) / sp;
+    const int nsp = (W.nchunks_total + cpc - 1) / cpc;
+    const int waves = (ctas_other * nsp + 147) / 148;
+    const double t = waves * (cpc + 6.0);      // + per-CTA prologue / epilogue in chunk units
+    if (t < best_t) { best_t = t; best_split = nsp; }
+  }
+  W.chunks_per_cta = (W.nchunks_total + best_split - 1) / best_split;
   p->nsplit_k = (W.nchunks_total + W.chunks_per_cta - 1) / W.chunks_per_cta;
   p->ws_bytes = (size_t)W.ntaps_total * W.CoutP * W.CinP * sizeof(float);
   nhvr_conv_plan_destroy(fp);

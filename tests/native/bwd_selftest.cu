@@ -184,6 +184,47 @@ int main(int argc, char** argv) {
     if (only >= 0 && (int)i != only) continue;
     fails += run_case(cases[i]);
   }
+  if (only < 0 || only >= 100) {
+    // wgrad timing at training shapes (no CPU check)
+    std::vector<Case> perf = {
+        {"PERF wgrad c3 256->256 64^2 b16", NHVR_CONV, 256, 256, 3, 1, 1, 16, 64, 64, R},
+        {"PERF wgrad c3 192->192 128^2 b8", NHVR_CONV, 192, 192, 3, 1, 1, 8, 128, 128, R},
+        {"PERF wgrad c7 64->73 256^2 b16", NHVR_CONV, 64, 73, 7, 1, 3, 16, 256, 256, R},
+        {"PERF wgrad c3s2 64->128 256^2 b16", NHVR_CONV, 64, 128, 3, 2, 1, 16, 256, 256, Z},
+        {"PERF wgrad ct 128->64 128^2 b16", NHVR_CONV_TRANSPOSE, 128, 64, 3, 2, 1, 16, 128, 128, Z},
+    };
+    int pi = 100;
+    for (auto& c : perf) {
+      ++pi;
+      if (only > 100 && only != pi) continue;
+      nhvr_conv_desc d{};
+      d.kind = c.kind; d.Cin = c.Cin; d.Cout = c.Cout; d.kh = d.kw = c.k; d.stride = c.stride; d.pad = c.pad;
+      d.N = c.N; d.H = c.H; d.W = c.W; d.halo = c.halo; d.epilogue = NHVR_EPI_RAW_P8;
+      nhvr_conv_plan* fplan = nullptr; nhvr_wgrad_plan* wplan = nullptr;
+      if (nhvr_conv_plan_create(&d, &fplan) || nhvr_wgrad_plan_create(&d, &wplan)) { printf("%s plan failed\n", c.name); ++fails; continue; }
+      nhvr_act_desc x_desc, g_desc; nhvr_conv_input_desc(fplan, &x_desc); nhvr_wgrad_grad_desc(wplan, &g_desc);
+      void *px, *pg, *ws; float* dwg;
+      CK(cudaMalloc(&px, nhvr_act_bytes(&x_desc))); CK(cudaMemset(px, 0, nhvr_act_bytes(&x_desc)));
+      CK(cudaMalloc(&pg, nhvr_act_bytes(&g_desc))); CK(cudaMemset(pg, 0, nhvr_act_bytes(&g_desc)));
+      CK(cudaMalloc(&ws, nhvr_wgrad_workspace_bytes(wplan)));
+      CK(cudaMalloc(&dwg, (size_t)c.Cin * c.Cout * c.k * c.k * 4));
+      cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+      const int iters = (only > 100) ? 2 : 10;
+      for (int it = 0; it < iters + 2; ++it) {
+        if (it == 2) CK(cudaEventRecord(e0, 0));
+        if (nhvr_wgrad(wplan, px, pg, ws, dwg, 1.0f, 0, 0)) { printf("launch failed\n"); break; }
+      }
+      CK(cudaEventRecord(e1, 0));
+      cudaError_t se = cudaDeviceSynchronize();
+      float ms = 0; if (se == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+      ms /= iters;
+      int Ho, Wo, C8; nhvr_conv_output_dims(fplan, &Ho, &Wo, &C8);
+      const double gflop = 2.0 * c.k * c.k * c.Cin * c.Cout * (c.kind == NHVR_CONV_TRANSPOSE ? (double)c.H * c.W : (double)Ho * Wo) * c.N * 1e-9;
+      printf("%-36s %s %.4f ms  %.1f TFLOP/s\n", c.name, se == cudaSuccess ? "" : cudaGetErrorString(se), ms, gflop / ms);
+      nhvr_conv_plan_destroy(fplan); nhvr_wgrad_plan_destroy(wplan);
+      cudaFree(px); cudaFree(pg); cudaFree(ws); cudaFree(dwg);
+    }
+  }
   printf("bwd selftest: %d failure(s)\n", fails);
   return fails;
 }

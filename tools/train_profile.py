@@ -1,0 +1,44 @@
+"""Per-kernel-class time of the training steps (event-bracketed launches through ops.PROFILE)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from nhvr_b200 import ops
+from nhvr_b200.networks import define_G, define_D
+from nhvr_b200.pipeline import RenderPipeline
+from nhvr_b200.train import UVPretrainer, RenderTrainer, synthetic_densepose, synthetic_train_batch
+from bench import PIPE_KW
+
+dev = torch.device("cuda", 0)
+mode = sys.argv[1] if len(sys.argv) > 1 else "uv"
+if mode == "uv":
+    net = define_G(3, 73, 64, "translate", 2, 5)
+    tr = UVPretrainer(net)
+    data = synthetic_densepose(16, 256, 256, dev)
+    step = lambda: tr.step(*data)
+else:
+    pipe = RenderPipeline(**PIPE_KW).to(dev)
+    netD = define_D(6, 64, 3, "instance", False, 2, True)
+    tr = RenderTrainer(pipe, netD)
+    batch = synthetic_train_batch(8, 512, dev)
+    step = lambda: tr.step(batch)
+for _ in range(2):
+    step()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(3):
+    step()
+e1.record(); torch.cuda.synchronize()
+print("step ms (unprofiled):", e0.elapsed_time(e1) / 3)
+ops.PROFILE = []
+step()
+torch.cuda.synchronize()
+recs, ops.PROFILE = ops.PROFILE, None
+agg = {}
+for kind, work, a, b in recs:
+    d = agg.setdefault(kind, [0.0, 0.0, 0]); d[0] += work; d[1] += a.elapsed_time(b); d[2] += 1
+tot = sum(v[1] for v in agg.values())
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    rate = v[0] / (v[1] * 1e-3)
+    print("%-12s n=%4d  %8.2f ms  %5.1f%%  %s" % (k, v[2], v[1], 100 * v[1] / tot, ("%.0f TFLOP/s" % (rate / 1e12)) if k in ("conv", "wgrad") else ("%.0f GB/s" % (rate / 1e9))))
+print("sum of bracketed launches: %.2f ms" % tot)
