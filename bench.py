@@ -278,8 +278,15 @@ def main():
         if conv:
             ach = conv[0] / conv[1] / 1e12
             peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+            traffic, traffic_src = None, None
+            tp = os.path.join(ROOT, "profiles", "r01_conv_dram_traffic.json")
+            if os.path.exists(tp):                      # dram__bytes_read+write per conv launch from a committed ncu capture
+                tj = json.load(open(tp))
+                if tj.get("clips") == B:
+                    traffic, traffic_src = tj["mean_dram_bytes_per_launch"], tj["source"]
             roof = {"kernel": "conv_shiftgemm_kernel (tcgen05)", "bound": "tensor", "achieved": ach, "peak": peak,
-                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": pk_src + ", sustained",
+                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes of DRAM per launch (mean over the step's conv launches)",
+                    "traffic_source": traffic_src, "peak_source": pk_src + ", sustained",
                     "launches_per_step": conv[2] // 3, "flops_per_step": conv[0] / 3,
                     "share_of_step": conv[1] / sum(v[1] for v in agg.values())}
         for kind in ("sampler", "composite", "in_apply", "pack"):
