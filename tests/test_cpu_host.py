@@ -57,7 +57,7 @@ def test_conv_plans_of_the_reference_networks():
         (capi.CONV, 192, 192, 3, 1, 1, 1, 128, 128, R, 9, 1),
         (capi.CONV_TRANSPOSE, 192, 96, 3, 2, 1, 1, 128, 128, Z, 9, 4),
         (capi.CONV_TRANSPOSE, 96, 48, 3, 2, 1, 1, 256, 256, Z, 9, 4),
-        (capi.CONV, 48, 4, 7, 1, 3, 1, 512, 512, R, 49, 1),
+        (capi.CONV, 48, 4, 7, 1, 3, 1, 512, 512, R, 7, 1),     # row mode: one job per filter row, N = kw*8
         (capi.CONV, 64, 73, 7, 1, 3, 1, 512, 512, R, 49, 1),
         (capi.CONV, 256, 256, 3, 1, 1, 8, 128, 128, R, 9, 1),
         (capi.CONV, 6, 64, 4, 2, 2, 1, 512, 512, Z, 16, 1),
