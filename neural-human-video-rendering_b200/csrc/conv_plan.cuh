@@ -7,7 +7,7 @@ namespace nhvr {
 
 constexpr int kMaxJobs = 52;
 constexpr int kMaxMma = 208;   // jobs x k-steps per chunk
-constexpr int kMaxRuns = 8;
+constexpr int kMaxRuns = 16;
 constexpr int kTileM = 128;
 
 struct ConvJob {
@@ -17,8 +17,8 @@ struct ConvJob {
 };
 struct ConvMma {     // one tcgen05.mma of a chunk: precomputed so the issue loop has no arithmetic chains
   int32_t a_off;     // (job shift + k-step plane offset) in 16-B units inside the chunk slab
-  uint16_t acc_col;  // accumulator column offset in TMEM
-  uint16_t first;    // overwrites its accumulator when executed in the first chunk
+  uint32_t meta;     // bits 0-15: accumulator column offset in TMEM; bit 16: first MMA of its accumulator (overwrites
+                     // instead of accumulating when executed in the first chunk).  32-bit fields keep the reads uniform.
 };
 struct ConvRun {
   int32_t g_off;   // offset (units) from the plane base + q0
@@ -32,6 +32,7 @@ struct ConvKParams {
   const float* bias;
   void* out;
   float* stats;
+  long long* trace;        // NHVR_CONV_TRACE: per-CTA cycle counters (nullptr in production)
   int64_t in_plane_units;
   int64_t w_split_units;   // packed-weight units per N-split
   int32_t C8in, kcp, nchunks, njobs, nruns, nacc;
@@ -43,11 +44,16 @@ struct ConvKParams {
   int32_t epilogue, act;
   int32_t tmem_cols;
   int32_t f16;             // operand element type: 0 bf16, 1 fp16
-  int32_t debug;           // NHVR_CONV_DEBUG experiments (results are wrong when set): 1 no MMA, 2 unshifted A, 4 double issue
+  int32_t debug;           // NHVR_CONV_DEBUG experiments (results are wrong when set): 8 no epilogue, 16 no statistics, 64 no global stores
+  int32_t dephase_cycles;  // > 0: CTAs that land in the second slot of an SM in the first wave start their MMAs this much later
   ActGeom og;              // BIAS_ACT_P8 destination
   int32_t mmas_per_chunk, stages_per_chunk;
   int32_t tile_step;       // linear positions a CTA advances by: 128, or 128-(kw-1) in row mode
   int32_t rowmode, Cp, kw; // row mode: accumulator column n = s*Cp + co, outputs = shifted sums over s (epilogue)
+  // M replication: one CTA owns `mrep` 128-position blocks that share every weight block (one smem B tile feeds
+  // mrep MMAs), `q_mstride` linear positions / `a_mstride` slab units apart.  xtiles > 0: the blocks are the same
+  // 128-pixel row segment of mrep consecutive output rows ("stacked"); xtiles == 0: mrep*128 consecutive positions.
+  int32_t mrep, a_mstride, q_mstride, xtiles, acc_mstride;
   ConvRun runs[kMaxRuns];
   ConvMma mma[kMaxMma + 1];   // +1: the issue loop prefetches one entry ahead
 };

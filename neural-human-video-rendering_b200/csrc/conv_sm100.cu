@@ -75,6 +75,7 @@ NHVR_DEVINL float apply_act(float x, int act, bool is_last) {
 // one 16-channel group of one output pixel: raw P8 store (+ InstanceNorm statistics), or bias + activation
 NHVR_DEVINL void emit16(const ConvKParams& P, const float (&v)[16], int c0, bool valid, int n, int Y, int X, int g_local, int lane,
                         float* s_stats) {
+  if (P.debug & 64) valid = valid && (v[0] == 123456.f);
   if (P.epilogue == NHVR_EPI_RAW_STATS || P.epilogue == NHVR_EPI_RAW_P8) {
     if (valid) {
       uint4* o = reinterpret_cast<uint4*>(P.out);
@@ -136,9 +137,21 @@ constexpr int kThreads = 384;       // warps 0-3: roles, warps 4-11: epilogue
 
 __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __grid_constant__ ConvKParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the role branches and everything inside them (ring
+  // counters, descriptors, table reads) stay on the uniform datapath instead of R2UR round trips per MMA
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int n = blockIdx.y, split = blockIdx.z;
-  const int64_t q0 = (int64_t)blockIdx.x * P.tile_step;
+  const long long t_entry = P.trace ? clock64() : 0;
+  long long* trace = P.trace ? P.trace + 8 * ((int64_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+  int ty0 = 0, tx0 = 0;                 // stacked tiles: first output row / column of the tile
+  int64_t q0;
+  if (P.xtiles) {
+    const int yg = blockIdx.x / P.xtiles;
+    ty0 = yg * P.mrep; tx0 = (blockIdx.x - yg * P.xtiles) * kTileM;
+    q0 = (int64_t)ty0 * P.Wrow + tx0;
+  } else {
+    q0 = (int64_t)blockIdx.x * P.tile_step;
+  }
   // K-chunk order is rotated per CTA: neighbouring CTAs stream different parts of the (shared) packed
   // weights at any instant instead of all hitting the same L2 lines in lock-step.
   const int rot = (int)(blockIdx.x % (unsigned)P.nchunks);
@@ -211,6 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
       uint32_t ph = 0;
       for (int s = 0; s < P.nbstages; ++s) {
         mbar_wait(&b_empty[st], ph ^ 1u);
+        if (trace && s == P.nbstages - 1 && lane == 0) trace[6] = clock64() - t_entry;   // last weight stage requested
         if (elect_one()) {
           mbar_arrive_expect_tx(&b_full[st], b_stage_bytes);
           bulk_g2s(b_smem + (size_t)st * b_stage_bytes, wsrc, b_stage_bytes, &b_full[st]);
@@ -235,33 +249,59 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
       const uint32_t b_lo0 = ((smem_u32(b_smem) & 0x3FFFFu) >> 4) | (b_lbo_u << 16);
       const uint32_t a_stage_u = a_stage_bytes >> 4, b_block_u = b_block_bytes >> 4;
       const int bpb = P.bpb, SA = P.SA, SB = P.SB, nchunks = P.nchunks, spc = P.stages_per_chunk;
+      const int mrep = P.mrep;
+      const uint32_t a_mstride = (uint32_t)P.a_mstride, acc_mstride = (uint32_t)P.acc_mstride;
       int ast = 0, bst = 0;
       uint32_t aph = 0, bph = 0;
       uint32_t b_lo = b_lo0;
       const bool leader = elect_one();
       // chunk -> weight stage -> MMA.  All ring bookkeeping sits at stage granularity (bpb divides the MMAs of a
       // chunk by construction); the innermost loop is: load table entry, two adds, tcgen05.mma.
+      // Two CTAs share an SM.  Started together they stay in lock-step: both in their MMA phase (each at half the
+      // tensor rate), then both in their epilogue with the tensor pipe idle.  Delaying the second CTA of each SM by
+      // about one MMA phase once, in the first wave, makes every later epilogue / prologue run under the other
+      // CTA's MMAs (the lag is preserved from tile to tile: profiles/r01_conv_ablation.md).
+      if (P.dephase_cycles > 0) {
+        const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        unsigned nsm;
+        asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+        if (lin >= nsm && lin < 2 * nsm) {
+          const long long until = clock64() + P.dephase_cycles;
+          while (clock64() < until) __nanosleep(200);
+        }
+      }
+      long long wa = 0, wb = 0, wi = 0;
+      const long long t_mma0 = trace ? clock64() : 0;
       for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(&a_full[ast], aph);
+        if (trace) { const long long c0 = clock64(); mbar_wait(&a_full[ast], aph); wa += clock64() - c0; }
+        else mbar_wait(&a_full[ast], aph);
         const uint32_t a_st_lo = a_lo0 + (uint32_t)ast * a_stage_u;
         const uint32_t keep_mask = (c == 0) ? 0u : 1u;          // chunk 0: the first MMA of an accumulator overwrites
         const ConvMma* e = P.mma;
         ConvMma cur = e[0];                                   // software-pipelined table read: the constant-bank
         for (int s = 0; s < spc; ++s) {                       // load of entry i+1 overlaps the issue of MMA i
-          mbar_wait(&b_full[bst], bph);
+          if (trace) { const long long c0 = clock64(); mbar_wait(&b_full[bst], bph); wb += clock64() - c0; }
+          else mbar_wait(&b_full[bst], bph);
           tc_fence_after();
+          const long long ci0 = trace ? clock64() : 0;
 #pragma unroll 1
           for (int k = 0; k < bpb; ++k) {
             ++e;
             const ConvMma nxt = *e;                           // one entry past the end is still inside ConvKParams
             if (leader) {
-              umma_bf16(tmem_base + cur.acc_col, ((uint64_t)desc_hi << 32) | (a_st_lo + (uint32_t)cur.a_off),
-                        ((uint64_t)desc_hi << 32) | b_lo, idesc, keep_mask | ((uint32_t)cur.first ^ 1u));
+              const uint32_t acc_flag = keep_mask | ((cur.meta >> 16) ^ 1u);
+              uint32_t a_lo = a_st_lo + (uint32_t)cur.a_off, d_col = tmem_base + (cur.meta & 0xffffu);
+              umma_bf16(d_col, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc_flag);
+              for (int i = 1; i < mrep; ++i) {               // the same weight block feeds the other M blocks
+                a_lo += a_mstride; d_col += acc_mstride;
+                umma_bf16(d_col, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc_flag);
+              }
             }
             b_lo += b_block_u;
             cur = nxt;
           }
           if (leader) umma_commit(&b_empty[bst]);
+          if (trace) wi += clock64() - ci0;
           if (++bst == SB) { bst = 0; bph ^= 1u; b_lo = b_lo0; }
         }
         if (leader) umma_commit(&a_empty[ast]);
@@ -269,6 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
       }
       __syncwarp();
       if (elect_one()) umma_commit(acc_full);
+      if (trace && lane == 0) { trace[0] = t_mma0 - t_entry; trace[1] = wa; trace[2] = wb; trace[3] = clock64() - t_entry; trace[7] = wi; }
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -276,9 +317,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
     const int we = warp & 3;                  // TMEM lane quarter == warp % 4
     const int half = (warp - 4) >> 2;         // warps 4-7 take the even column groups, 8-11 the odd ones
     const int m = we * 32 + lane;
-    const int64_t q = q0 + m;
-    const int y = (int)(q / P.Wrow);
-    const int x = (int)(q - (int64_t)y * P.Wrow);
+    int y, x;
+    if (P.xtiles) { y = ty0; x = tx0 + m; }
+    else { const int64_t q = q0 + m; y = (int)(q / P.Wrow); x = (int)(q - (int64_t)y * P.Wrow); }
     const bool valid_m = (y < P.Hv) && (x < P.Wv);
     const uint32_t t_lane = tmem_base + ((uint32_t)(we * 32) << 16);
     const int cout_off = split * P.Npad;
@@ -286,6 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
 
     mbar_wait_warp(acc_full, 0);
     tc_fence_after();
+    if (trace && threadIdx.x == 128) trace[4] = clock64() - t_entry;
 
     if (P.rowmode) {
       // ---- row mode: accumulator column n = s*Cp + co holds Z[m][s][co]; output Y[m][co] = sum_s Z[m+s][s][co].
@@ -330,18 +372,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
         }
       }
     } else {
-    for (int a = 0; a < ((P.debug & 8) ? 0 : P.nacc); ++a) {
-      const int Y = y * P.oys + P.oy[a];
-      const int X = x * P.oxs + P.ox[a];
-      const bool valid = valid_m && Y < P.Ho && X < P.Wo;
-      for (int g = half; g < ngroups; g += 2) {
-        uint32_t vr[16];
-        tmem_ld16(t_lane + (uint32_t)(a * P.Npad + g * 16), vr);
-        tmem_ld_wait();
-        float v[16];
+    for (int rep = 0; rep < ((P.debug & 8) ? 0 : P.mrep); ++rep) {
+      int yr = y, xr = x;
+      if (rep) {
+        if (P.xtiles) { yr = y + rep; }
+        else { const int64_t q = q0 + (int64_t)rep * P.q_mstride + m; yr = (int)(q / P.Wrow); xr = (int)(q - (int64_t)yr * P.Wrow); }
+      }
+      const bool valid_r = (yr < P.Hv) && (xr < P.Wv);
+      for (int a = 0; a < P.nacc; ++a) {
+        const int Y = yr * P.oys + P.oy[a];
+        const int X = xr * P.oxs + P.ox[a];
+        const bool valid = valid_r && Y < P.Ho && X < P.Wo;
+        for (int g = half; g < ngroups; g += 2) {
+          uint32_t vr[16];
+          tmem_ld16(t_lane + (uint32_t)(rep * P.acc_mstride + a * P.Npad + g * 16), vr);
+          tmem_ld_wait();
+          float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(vr[i]);
-        emit16(P, v, cout_off + g * 16, valid, n, Y, X, g, lane, s_stats);
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(vr[i]);
+          emit16(P, v, cout_off + g * 16, valid, n, Y, X, g, lane, s_stats);
+        }
       }
     }
     }
@@ -353,6 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
     }
   }
 
+  if (trace && threadIdx.x == 128) trace[5] = clock64() - t_entry;
   tc_fence_before();
   __syncthreads();
   if (warp == 3) {
@@ -434,171 +485,186 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   std::vector<Tap> taps;
   std::vector<std::pair<int, int>> run_specs;   // (g_off, len) before merging, indexed by run_key
   int nacc = 1;
-  int Ho, Wo;
+  int Ho = 0, Wo = 0;
   bool rowmode = false;
   int row_npad = 0;
-  K.tile_step = kTileM;
+  int key_stride = 1;                            // run-key distance between consecutive input rows (stacked tiles)
 
-  if (d->kind == NHVR_CONV && d->stride == 1) {
-    in.pad_t = in.pad_b = in.pad_l = in.pad_r = d->pad;
-    const int Wp = d->W + 2 * d->pad;
-    Ho = d->H + 2 * d->pad - d->kh + 1;
-    Wo = d->W + 2 * d->pad - d->kw + 1;
-    if (Ho <= 0 || Wo <= 0) { delete p; return NHVR_ERR_SHAPE; }
-    // Row mode (wide kernels, few output channels: the 7x7 stems / RGB head): instead of kh*kw MMAs of N = Cout,
-    // issue kh MMAs of N = kw*Cp whose column n = s*Cp + co accumulates filter column s un-shifted; the epilogue
-    // adds Z[m+s][s][co] over s.  kw x fewer MMAs and A-operand reads; tiles advance by 128-(kw-1) positions.
-    const int Cp_row = d->Cout <= 8 ? 8 : round_up(d->Cout, 16);
-    // measured (profiles/r01_selftest_v5_rowmode.log): 2x on the 48->4 head; the 16->48 stem loses 2x (two 176-column
-    // accumulators need all 512 TMEM columns -> one CTA per SM, epilogue-bound), so only narrow outputs qualify
-    rowmode = !(d->flags & 1) && d->kw >= 5 && d->kw <= 8 && d->kw * Cp_row <= 128 && !std::getenv("NHVR_NO_ROWMODE") &&
-              d->epilogue != NHVR_EPI_BIAS_ACT_P8;
-    if (rowmode) {
-      const int ntot = d->kw * Cp_row;
-      nacc = (ntot + 255) / 256;
-      row_npad = round_up((ntot + nacc - 1) / nacc, 16);
-      for (int r = 0; r < d->kh; ++r) run_specs.push_back({r * Wp, kTileM});
-      for (int r = 0; r < d->kh; ++r)
-        for (int a = 0; a < nacc; ++a) taps.push_back({r, 0, a, r * 8 + a});
-      K.rowmode = 1; K.Cp = Cp_row; K.kw = d->kw;
-      K.tile_step = kTileM - (d->kw - 1);
-    } else {
-      for (int r = 0; r < d->kh; ++r) run_specs.push_back({r * Wp, kTileM + d->kw - 1});
+  // ---- geometry: the shift program for tiles of `mrep` M blocks (stacked rows or consecutive positions)
+  auto build_geometry = [&](int mrep, bool stacked) -> int {
+    taps.clear(); run_specs.clear();
+    nacc = 1; rowmode = false; row_npad = 0; key_stride = 1;
+    in.N = d->N; in.C8 = C8; in.H = d->H; in.W = d->W; in.halo = d->halo; in.split = 0;
+    K.rowmode = 0; K.Cp = 0; K.kw = 0;
+    const int L = stacked ? kTileM : kTileM * mrep;     // consecutive positions one run has to cover
+    const int xrows = stacked ? mrep - 1 : 0;           // extra input rows below the first block's
+    K.tile_step = kTileM * mrep;
+    if (d->kind == NHVR_CONV && d->stride == 1) {
+      in.pad_t = in.pad_b = in.pad_l = in.pad_r = d->pad;
+      const int Wp = d->W + 2 * d->pad;
+      Ho = d->H + 2 * d->pad - d->kh + 1;
+      Wo = d->W + 2 * d->pad - d->kw + 1;
+      if (Ho <= 0 || Wo <= 0) return NHVR_ERR_SHAPE;
+      // Row mode (wide kernels, few output channels: the 7x7 stems / RGB head): instead of kh*kw MMAs of N = Cout,
+      // issue kh MMAs of N = kw*Cp whose column n = s*Cp + co accumulates filter column s un-shifted; the epilogue
+      // adds Z[m+s][s][co] over s.  kw x fewer MMAs and A-operand reads; tiles advance by 128-(kw-1) positions.
+      const int Cp_row = d->Cout <= 8 ? 8 : round_up(d->Cout, 16);
+      // measured (profiles/r01_selftest_v5_rowmode.log): 2x on the 48->4 head; the 16->48 stem loses 2x (two 176-column
+      // accumulators need all 512 TMEM columns -> one CTA per SM, epilogue-bound), so only narrow outputs qualify
+      rowmode = !(d->flags & 1) && d->kw >= 5 && d->kw <= 8 && d->kw * Cp_row <= 128 && !std::getenv("NHVR_NO_ROWMODE") &&
+                d->epilogue != NHVR_EPI_BIAS_ACT_P8;
+      if (rowmode) {
+        if (mrep != 1) return NHVR_ERR_UNSUPPORTED;
+        const int ntot = d->kw * Cp_row;
+        nacc = (ntot + 255) / 256;
+        row_npad = round_up((ntot + nacc - 1) / nacc, 16);
+        for (int r = 0; r < d->kh; ++r) run_specs.push_back({r * Wp, kTileM});
+        for (int r = 0; r < d->kh; ++r)
+          for (int a = 0; a < nacc; ++a) taps.push_back({r, 0, a, r * 8 + a});
+        K.rowmode = 1; K.Cp = Cp_row; K.kw = d->kw;
+        K.tile_step = kTileM - (d->kw - 1);
+      } else {
+        for (int r = 0; r < d->kh + xrows; ++r) run_specs.push_back({r * Wp, L + d->kw - 1});
+        for (int r = 0; r < d->kh; ++r)
+          for (int s = 0; s < d->kw; ++s) taps.push_back({r, s, 0, r * d->kw + s});
+      }
+      K.Wrow = Wp; K.Hv = Ho; K.Wv = Wo; K.oys = K.oxs = 1;
+    } else if (d->kind == NHVR_CONV_DGRAD_S1) {
+      // d describes the FORWARD conv (Cin, Cout, k, pad, input H x W).  dX over the padded input extent is the
+      // correlation of the output gradient (stored with k-1 zero rows above/below and k-1 zero columns LEFT of
+      // every row: consecutive rows share that gap in the linearised image) with the mirrored, transposed taps.
+      if (d->stride != 1) return NHVR_ERR_UNSUPPORTED;
+      const int Hof = d->H + 2 * d->pad - d->kh + 1, Wof = d->W + 2 * d->pad - d->kw + 1;
+      if (Hof <= 0 || Wof <= 0) return NHVR_ERR_SHAPE;
+      in.H = Hof; in.W = Wof;
+      in.C8 = round_up((d->Cout + 7) / 8, 2);
+      in.pad_t = in.pad_b = d->kh - 1; in.pad_l = d->kw - 1; in.pad_r = 0;
+      in.halo = NHVR_HALO_ZERO;
+      const int Wpi = Wof + d->kw - 1;                 // == W + 2*pad: same pitch as the forward input
+      Ho = d->H + 2 * d->pad; Wo = d->W + 2 * d->pad;  // gradient w.r.t. the PADDED forward input
+      for (int r = 0; r < d->kh + xrows; ++r) run_specs.push_back({r * Wpi, L + d->kw - 1});
       for (int r = 0; r < d->kh; ++r)
         for (int s = 0; s < d->kw; ++s) taps.push_back({r, s, 0, r * d->kw + s});
-    }
-    K.Wrow = Wp; K.Hv = Ho; K.Wv = Wo; K.oys = K.oxs = 1;
-  } else if (d->kind == NHVR_CONV_DGRAD_S1) {
-    // d describes the FORWARD conv (Cin, Cout, k, pad, input H x W).  dX over the padded input extent is the
-    // correlation of the output gradient (stored with k-1 zero rows above/below and k-1 zero columns LEFT of
-    // every row: consecutive rows share that gap in the linearised image) with the mirrored, transposed taps.
-    if (d->stride != 1) { delete p; return NHVR_ERR_UNSUPPORTED; }
-    const int Hof = d->H + 2 * d->pad - d->kh + 1, Wof = d->W + 2 * d->pad - d->kw + 1;
-    if (Hof <= 0 || Wof <= 0) { delete p; return NHVR_ERR_SHAPE; }
-    in.H = Hof; in.W = Wof;
-    in.C8 = round_up((d->Cout + 7) / 8, 2);
-    in.pad_t = in.pad_b = d->kh - 1; in.pad_l = d->kw - 1; in.pad_r = 0;
-    in.halo = NHVR_HALO_ZERO;
-    const int Wpi = Wof + d->kw - 1;                 // == W + 2*pad: same pitch as the forward input
-    Ho = d->H + 2 * d->pad; Wo = d->W + 2 * d->pad;  // gradient w.r.t. the PADDED forward input
-    for (int r = 0; r < d->kh; ++r) run_specs.push_back({r * Wpi, kTileM + d->kw - 1});
-    for (int r = 0; r < d->kh; ++r)
-      for (int s = 0; s < d->kw; ++s) taps.push_back({r, s, 0, r * d->kw + s});
-    K.Wrow = Wpi; K.Hv = Ho; K.Wv = Wo; K.oys = K.oxs = 1;
-  } else if (d->kind == NHVR_CONV && d->stride == 2) {
-    in.pad_t = in.pad_b = in.pad_l = in.pad_r = d->pad;
-    in.pad_b += d->in_extra_rows;
-    in.split = 1;
-    ActGeom g = make_geom(in);
-    const int Hq = g.Hp / 2, Wq = g.Wp / 2;
-    Ho = (d->H + 2 * d->pad - d->kh) / 2 + 1;
-    Wo = (d->W + 2 * d->pad - d->kw) / 2 + 1;
-    if (Ho <= 0 || Wo <= 0) { delete p; return NHVR_ERR_SHAPE; }
-    const int rr_n = (d->kh - 1) / 2 + 1;
-    // run key = parity-plane * rr_n + (r >> 1)
-    for (int pp = 0; pp < 4; ++pp)
-      for (int rr = 0; rr < rr_n; ++rr) run_specs.push_back({pp * Hq * Wq + rr * Wq, kTileM + (d->kw - 1) / 2});
-    for (int r = 0; r < d->kh; ++r)
-      for (int s = 0; s < d->kw; ++s) {
-        const int pp = ((r & 1) << 1) | (s & 1);
-        taps.push_back({pp * rr_n + (r >> 1), s >> 1, 0, r * d->kw + s});
-      }
-    K.Wrow = Wq; K.Hv = Ho; K.Wv = Wo; K.oys = K.oxs = 1;
-  } else if (d->kind == NHVR_CONV_TRANSPOSE) {
-    const bool k3 = (d->kh == 3 && d->kw == 3 && d->pad == 1), k4 = (d->kh == 4 && d->kw == 4 && d->pad == 2);
-    if (d->stride != 2 || !(k3 || k4)) { delete p; return NHVR_ERR_UNSUPPORTED; }
-    in.pad_t = in.pad_l = 0; in.pad_b = 1; in.pad_r = 1 + d->in_extra_cols;
-    in.halo = NHVR_HALO_ZERO;
-    const int Wp = d->W + in.pad_r;
-    // out[2i - pad + ky] += x[i] * w[ky]:  k3 p1 -> 2H (output_padding 1);  k4 p2 -> 2H-2 (+ output_padding via out_h)
-    Ho = d->out_h > 0 ? d->out_h : (k3 ? 2 * d->H : 2 * d->H - 2);
-    Wo = d->out_w > 0 ? d->out_w : (k3 ? 2 * d->W : 2 * d->W - 2);
-    if (Ho < 1 || Wo < 1 || Ho > 2 * d->H || Wo > 2 * d->W) { delete p; return NHVR_ERR_SHAPE; }
-    run_specs.push_back({0, kTileM + 1});
-    run_specs.push_back({Wp, kTileM + 1});
-    nacc = 4;
-    // phase a (output row parity), M index t <-> output row 2t+a, input row t+di:
-    //   k3 p1: a=0 -> (di 0, ky 1);          a=1 -> (0, 2), (1, 0)
-    //   k4 p2: a=0 -> (di 1, ky 0), (0, 2);  a=1 -> (1, 1), (0, 3)
-    int n_opt[2], o_d[2][2], o_k[2][2];
-    if (k3) { n_opt[0] = 1; n_opt[1] = 2; o_d[0][0] = 0; o_k[0][0] = 1; o_d[0][1] = 0; o_k[0][1] = 1; o_d[1][0] = 0; o_k[1][0] = 2; o_d[1][1] = 1; o_k[1][1] = 0; }
-    else    { n_opt[0] = 2; n_opt[1] = 2; o_d[0][0] = 1; o_k[0][0] = 0; o_d[0][1] = 0; o_k[0][1] = 2; o_d[1][0] = 1; o_k[1][0] = 1; o_d[1][1] = 0; o_k[1][1] = 3; }
-    for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 2; ++b)
-        for (int ia = 0; ia < n_opt[a]; ++ia)
-          for (int ib = 0; ib < n_opt[b]; ++ib)
-            taps.push_back({o_d[a][ia], o_d[b][ib], a * 2 + b, o_k[a][ia] * d->kw + o_k[b][ib]});
-    K.Wrow = Wp; K.Hv = (Ho + 1) / 2; K.Wv = (Wo + 1) / 2; K.oys = K.oxs = 2;
-    for (int a = 0; a < 4; ++a) { K.oy[a] = a >> 1; K.ox[a] = a & 1; }
-  } else {
-    delete p; return NHVR_ERR_UNSUPPORTED;
-  }
-  if ((int)taps.size() > kMaxJobs) { delete p; return NHVR_ERR_UNSUPPORTED; }
-
-  // ---- runs: drop unused, sort by offset, merge neighbours that touch / nearly touch
-  std::vector<int> used(run_specs.size(), 0);
-  for (auto& t : taps) used[t.run_key] = 1;
-  std::vector<int> order;
-  for (size_t i = 0; i < run_specs.size(); ++i) if (used[i]) order.push_back((int)i);
-  std::sort(order.begin(), order.end(), [&](int a, int b) { return run_specs[a].first < run_specs[b].first; });
-  std::vector<ConvRun> runs;
-  std::vector<int> key_soff(run_specs.size(), 0);
-  int slab = 0;
-  for (int k : order) {
-    const int g = run_specs[k].first, len = run_specs[k].second;
-    if (!runs.empty() && g <= runs.back().g_off + runs.back().len + 16) {
-      ConvRun& r = runs.back();
-      key_soff[k] = r.s_off + (g - r.g_off);
-      const int new_len = std::max(r.len, g + len - r.g_off);
-      slab += new_len - r.len;
-      r.len = new_len;
+      K.Wrow = Wpi; K.Hv = Ho; K.Wv = Wo; K.oys = K.oxs = 1;
+    } else if (d->kind == NHVR_CONV && d->stride == 2) {
+      in.pad_t = in.pad_b = in.pad_l = in.pad_r = d->pad;
+      in.pad_b += d->in_extra_rows;
+      in.split = 1;
+      ActGeom g = make_geom(in);
+      const int Hq = g.Hp / 2, Wq = g.Wp / 2;
+      Ho = (d->H + 2 * d->pad - d->kh) / 2 + 1;
+      Wo = (d->W + 2 * d->pad - d->kw) / 2 + 1;
+      if (Ho <= 0 || Wo <= 0) return NHVR_ERR_SHAPE;
+      const int rr_n = (d->kh - 1) / 2 + 1 + xrows;
+      // run key = parity-plane * rr_n + (r >> 1)
+      for (int pp = 0; pp < 4; ++pp)
+        for (int rr = 0; rr < rr_n; ++rr) run_specs.push_back({pp * Hq * Wq + rr * Wq, L + (d->kw - 1) / 2});
+      for (int r = 0; r < d->kh; ++r)
+        for (int s = 0; s < d->kw; ++s) {
+          const int pp = ((r & 1) << 1) | (s & 1);
+          taps.push_back({pp * rr_n + (r >> 1), s >> 1, 0, r * d->kw + s});
+        }
+      K.Wrow = Wq; K.Hv = Ho; K.Wv = Wo; K.oys = K.oxs = 1;
+    } else if (d->kind == NHVR_CONV_TRANSPOSE) {
+      if (mrep != 1) return NHVR_ERR_UNSUPPORTED;
+      const bool k3 = (d->kh == 3 && d->kw == 3 && d->pad == 1), k4 = (d->kh == 4 && d->kw == 4 && d->pad == 2);
+      if (d->stride != 2 || !(k3 || k4)) return NHVR_ERR_UNSUPPORTED;
+      in.pad_t = in.pad_l = 0; in.pad_b = 1; in.pad_r = 1 + d->in_extra_cols;
+      in.halo = NHVR_HALO_ZERO;
+      const int Wp = d->W + in.pad_r;
+      // out[2i - pad + ky] += x[i] * w[ky]:  k3 p1 -> 2H (output_padding 1);  k4 p2 -> 2H-2 (+ output_padding via out_h)
+      Ho = d->out_h > 0 ? d->out_h : (k3 ? 2 * d->H : 2 * d->H - 2);
+      Wo = d->out_w > 0 ? d->out_w : (k3 ? 2 * d->W : 2 * d->W - 2);
+      if (Ho < 1 || Wo < 1 || Ho > 2 * d->H || Wo > 2 * d->W) return NHVR_ERR_SHAPE;
+      run_specs.push_back({0, kTileM + 1});
+      run_specs.push_back({Wp, kTileM + 1});
+      nacc = 4;
+      // phase a (output row parity), M index t <-> output row 2t+a, input row t+di:
+      //   k3 p1: a=0 -> (di 0, ky 1);          a=1 -> (0, 2), (1, 0)
+      //   k4 p2: a=0 -> (di 1, ky 0), (0, 2);  a=1 -> (1, 1), (0, 3)
+      int n_opt[2], o_d[2][2], o_k[2][2];
+      if (k3) { n_opt[0] = 1; n_opt[1] = 2; o_d[0][0] = 0; o_k[0][0] = 1; o_d[0][1] = 0; o_k[0][1] = 1; o_d[1][0] = 0; o_k[1][0] = 2; o_d[1][1] = 1; o_k[1][1] = 0; }
+      else    { n_opt[0] = 2; n_opt[1] = 2; o_d[0][0] = 1; o_k[0][0] = 0; o_d[0][1] = 0; o_k[0][1] = 2; o_d[1][0] = 1; o_k[1][0] = 1; o_d[1][1] = 0; o_k[1][1] = 3; }
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b)
+          for (int ia = 0; ia < n_opt[a]; ++ia)
+            for (int ib = 0; ib < n_opt[b]; ++ib)
+              taps.push_back({o_d[a][ia], o_d[b][ib], a * 2 + b, o_k[a][ia] * d->kw + o_k[b][ib]});
+      K.Wrow = Wp; K.Hv = (Ho + 1) / 2; K.Wv = (Wo + 1) / 2; K.oys = K.oxs = 2;
+      for (int a = 0; a < 4; ++a) { K.oy[a] = a >> 1; K.ox[a] = a & 1; }
     } else {
-      ConvRun r{g, len, slab};
-      key_soff[k] = slab;
-      slab += len;
-      runs.push_back(r);
+      return NHVR_ERR_UNSUPPORTED;
     }
-  }
-  if ((int)runs.size() > kMaxRuns) { delete p; return NHVR_ERR_UNSUPPORTED; }
-  K.nruns = (int)runs.size();
-  for (int i = 0; i < K.nruns; ++i) K.runs[i] = runs[i];
-  K.slab_units = slab;
+    if ((int)taps.size() > kMaxJobs) return NHVR_ERR_UNSUPPORTED;
+    return NHVR_OK;
+  };
 
-  // ---- jobs (grouped by accumulator so that "first" is well defined)
-  std::stable_sort(taps.begin(), taps.end(), [](const Tap& a, const Tap& b) { return a.acc < b.acc; });
-  K.njobs = (int)taps.size();
-  std::vector<ConvJob> jobs(K.njobs);
-  int prev_acc = -1;
-  for (int j = 0; j < K.njobs; ++j) {
-    jobs[j].a_off = key_soff[taps[j].run_key] + taps[j].shift;
-    jobs[j].acc = (int16_t)taps[j].acc;
-    jobs[j].first = (taps[j].acc != prev_acc) ? 1 : 0;
-    prev_acc = taps[j].acc;
-    p->pp.job_tap[j] = (int16_t)taps[j].tap;
-  }
-  K.nacc = nacc;
-  p->njobs_h = K.njobs;
-  for (int j = 0; j < K.njobs; ++j) p->jobs_h[j] = jobs[j];
+  // ---- runs: drop unused, sort by offset, merge neighbours that touch / nearly touch.  With stacked tiles block i
+  // of a tap reads run (key + i): the slab distance between consecutive rows must be one constant (a_mstride).
+  std::vector<int> key_soff;
+  int slab = 0;
+  auto layout_runs = [&](int mrep, bool stacked) -> int {
+    std::vector<int> used(run_specs.size(), 0);
+    for (auto& t : taps)
+      for (int i = 0; i < (stacked ? mrep : 1); ++i) {
+        if (t.run_key + i * key_stride >= (int)run_specs.size()) return NHVR_ERR_UNSUPPORTED;
+        used[t.run_key + i * key_stride] = 1;
+      }
+    std::vector<int> order;
+    for (size_t i = 0; i < run_specs.size(); ++i) if (used[i]) order.push_back((int)i);
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return run_specs[a].first < run_specs[b].first; });
+    std::vector<ConvRun> runs;
+    key_soff.assign(run_specs.size(), 0);
+    slab = 0;
+    for (int k : order) {
+      const int g = run_specs[k].first, len = run_specs[k].second;
+      if (!runs.empty() && g <= runs.back().g_off + runs.back().len + 16) {
+        ConvRun& r = runs.back();
+        key_soff[k] = r.s_off + (g - r.g_off);
+        const int new_len = std::max(r.len, g + len - r.g_off);
+        slab += new_len - r.len;
+        r.len = new_len;
+      } else {
+        ConvRun r{g, len, slab};
+        key_soff[k] = slab;
+        slab += len;
+        runs.push_back(r);
+      }
+    }
+    if ((int)runs.size() > kMaxRuns) return NHVR_ERR_UNSUPPORTED;
+    K.nruns = (int)runs.size();
+    for (int i = 0; i < K.nruns; ++i) K.runs[i] = runs[i];
+    K.slab_units = slab;
+    K.mrep = mrep;
+    K.xtiles = 0;
+    K.a_mstride = kTileM; K.q_mstride = kTileM;
+    if (stacked && mrep > 1) {
+      const int k0 = taps[0].run_key;
+      K.a_mstride = key_soff[k0 + key_stride] - key_soff[k0];
+      K.q_mstride = K.Wrow;
+      for (auto& t : taps)
+        for (int i = 1; i < mrep; ++i)
+          if (key_soff[t.run_key + i * key_stride] - key_soff[t.run_key] != i * K.a_mstride) return NHVR_ERR_UNSUPPORTED;
+    }
+    if (stacked) K.xtiles = (K.Wv + kTileM - 1) / kTileM;
+    return NHVR_OK;
+  };
 
-  // ---- N (Cout) tiling
-  int Npad = rowmode ? row_npad : round_up(gemm_n, 16);
-  int nsplit = 1;
-  const int max_n = 256 / (nacc > 2 ? 2 : 1) / (nacc > 1 ? 2 : 1);   // nacc*Npad <= 512 and Npad <= 256
-  while (!rowmode && Npad > std::min(256, 512 / nacc)) { nsplit *= 2; Npad = round_up((gemm_n + nsplit - 1) / nsplit, 16); }
-  (void)max_n;
-  K.Npad = Npad;
-  K.tmem_cols = next_pow2_cols(nacc * Npad);
-  p->nsplit = nsplit;
-  p->Ho = Ho; p->Wo = Wo;
-  // P8 outputs carry an even number of planes (zero channels beyond Cout) so that they can feed the next
-  // conv directly: one MMA consumes K = 16 channels = 2 planes
-  p->Cout8 = round_up((gemm_n + 7) / 8, 2);
-  K.Ho = Ho; K.Wo = Wo; K.Cout = gemm_n; K.Cout8 = p->Cout8;
-  K.epilogue = d->epilogue; K.act = d->act;
-
-  // ---- shared-memory budget: prefer two co-resident CTAs per SM (<= ~100 KB, <= 256 TMEM columns)
-  const int b_block = Npad * 32;
-  auto try_fit = [&](int budget, int& kcp, int& SA, int& bpb, int& SB) -> bool {
+  // ---- N (Cout) tiling, TMEM columns, shared-memory rings
+  int Npad = 0, nsplit = 1;
+  auto tile_n = [&](int mrep, int want_split) {
+    Npad = rowmode ? row_npad : round_up(gemm_n, 16);
+    nsplit = 1;
+    while (!rowmode && (Npad > std::min(256, 512 / nacc) || nsplit < want_split)) {
+      nsplit *= 2; Npad = round_up((gemm_n + nsplit - 1) / nsplit, 16);
+    }
+    K.Npad = Npad;
+    K.acc_mstride = nacc * Npad;
+    K.tmem_cols = next_pow2_cols(mrep * nacc * Npad);
+  };
+  int kcp = 0, SA = 0, bpb = 0, SB = 0;
+  auto try_fit = [&](int budget) -> bool {
+    const int b_block = Npad * 32;
     long best_score = -1;
     for (int cand = 8; cand >= 2; cand -= 2) {
       if (C8 % cand) continue;
@@ -608,7 +674,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
       const int bpc = (int)taps.size() * cand / 2;          // MMA blocks per chunk
       if (bpc > kMaxMma) continue;
       const long rem = budget - a_bytes - 1024 - (long)Npad * 8 * nacc - (rowmode ? 8704 : 0);
-      for (int dv = 8; dv >= 1; --dv) {                      // blocks per B stage: a divisor of bpc, stage <= 16 KB
+      for (int dv = 8; dv >= 1; --dv) {                      // blocks per B stage: a divisor of bpc, stage <= 24 KB
         if (bpc % dv || (long)dv * b_block > 24576) continue;
         const int sb = (int)std::min<long>(6, rem / ((long)dv * b_block));
         if (sb < 2) continue;
@@ -620,19 +686,97 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
     }
     return best_score >= 0;
   };
-  int kcp = 0, SA = 0, bpb = 0, SB = 0;
+  auto count_tiles = [&](int mrep, bool stacked) -> int {
+    if (stacked) return ((K.Hv + mrep - 1) / mrep) * ((K.Wv + kTileM - 1) / kTileM);
+    const int64_t last_q = (int64_t)(K.Hv - 1) * K.Wrow + K.Wv;   // one past the last valid linear position
+    return (int)((last_q + K.tile_step - 1) / K.tile_step);
+  };
+
+  int st0 = build_geometry(1, false);
+  if (st0 != NHVR_OK) { delete p; return st0; }
+  // M replication (profiles/r01_conv_ablation.md): a tile of mrep M blocks streams the layer's packed weights once
+  // instead of once per 128 positions and amortises the per-CTA prologue.  Candidates keep two CTAs per SM
+  // (<= 256 TMEM columns, <= 112 KB).
+  int mrep = 1, want_split = 1;
+  bool stacked = false;
   bool ok = false;
-  if (const char* tune = std::getenv("NHVR_CONV_TUNE")) {   // experiments: "kcp,SA,bpb,SB"
-    int a, b, c, e;
-    if (std::sscanf(tune, "%d,%d,%d,%d", &a, &b, &c, &e) == 4 && a >= 2 && (a % 2) == 0 && C8 % a == 0 && b >= 1 && c >= 1 && e >= 2 &&
-        ((int)taps.size() * a / 2) % c == 0 && (int)taps.size() * a / 2 <= kMaxMma) {
-      const long need = (long)std::min(b, C8 / a) * a * slab * 16 + (long)e * c * b_block + 2048 + (long)Npad * 8;
-      if (need <= 227 * 1024) { kcp = a; SA = std::min(b, C8 / a); bpb = c; SB = e; ok = true; }
+  const bool plain = (d->flags & 1) || rowmode || d->kind == NHVR_CONV_TRANSPOSE || std::getenv("NHVR_CONV_TUNE");
+  int force_m = 0, force_split = 0;
+  if (const char* e = std::getenv("NHVR_CONV_MREP")) std::sscanf(e, "%d,%d", &force_m, &force_split);
+  if (!plain && force_m != 1) {
+    const int n16 = round_up(gemm_n, 16);
+    // measured (profiles/r01_conv_ablation.md): splitting wide outputs over two CTAs to make room for a second M block
+    // loses (N = 96 MMAs are shared-memory bound, the input slab is fetched twice) - replicate only where N <= 128
+    int ws = 1;
+    (void)n16;
+    if (force_split > 0) ws = force_split;
+    tile_n(1, ws);
+    int mmax = std::min(4, 256 / (nacc * Npad));
+    if (force_m > 1) mmax = force_m;
+    // reads of the last tile run past the image into the tail slack of the buffer
+    while (mmax > 1 && (int64_t)(mmax - 1) * K.Wrow + 2 * kTileM > kActSlackUnits) --mmax;
+    for (int m = mmax; m >= 2 && !ok; --m) {
+      const int xt = (K.Wv + kTileM - 1) / kTileM;
+      const bool prefer_stk = d->kind != NHVR_CONV_DGRAD_S1 && xt * kTileM * 10 <= K.Wv * 11;
+      for (int alt = 0; alt < (prefer_stk ? 2 : 1) && !ok; ++alt) {
+        const bool stk = prefer_stk && alt == 0;
+        if (m * nacc * Npad > 512) continue;
+        if (build_geometry(m, stk) != NHVR_OK) continue;
+        if (!force_m && (int64_t)count_tiles(m, stk) * d->N * std::max(ws, 1) < 148) continue;   // keep every SM busy
+        if (layout_runs(m, stk) != NHVR_OK) continue;
+        tile_n(m, ws);
+        if (K.tmem_cols <= 256) ok = try_fit(112 * 1024);
+        else if (force_m) ok = try_fit(220 * 1024);
+        if (ok) { mrep = m; stacked = stk; want_split = ws; }
+      }
     }
   }
-  if (!ok && K.tmem_cols <= 256) ok = try_fit(100 * 1024, kcp, SA, bpb, SB);
-  if (!ok) ok = try_fit(220 * 1024, kcp, SA, bpb, SB);
-  if (!ok) { delete p; return NHVR_ERR_SMEM; }
+  if (!ok) {
+    mrep = 1; stacked = false; want_split = 1;
+    st0 = build_geometry(1, false);
+    if (st0 == NHVR_OK) st0 = layout_runs(1, false);
+    if (st0 != NHVR_OK) { delete p; return st0; }
+    tile_n(1, 1);
+    const int b_block = Npad * 32;
+    if (const char* tune = std::getenv("NHVR_CONV_TUNE")) {   // experiments: "kcp,SA,bpb,SB"
+      int a, b, c, e;
+      if (std::sscanf(tune, "%d,%d,%d,%d", &a, &b, &c, &e) == 4 && a >= 2 && (a % 2) == 0 && C8 % a == 0 && b >= 1 && c >= 1 && e >= 2 &&
+          ((int)taps.size() * a / 2) % c == 0 && (int)taps.size() * a / 2 <= kMaxMma) {
+        const long need = (long)std::min(b, C8 / a) * a * slab * 16 + (long)e * c * b_block + 2048 + (long)Npad * 8;
+        if (need <= 227 * 1024) { kcp = a; SA = std::min(b, C8 / a); bpb = c; SB = e; ok = true; }
+      }
+    }
+    if (!ok && K.tmem_cols <= 256) ok = try_fit(100 * 1024);
+    if (!ok) ok = try_fit(220 * 1024);
+    if (!ok) { delete p; return NHVR_ERR_SMEM; }
+  }
+  const int b_block = Npad * 32;
+
+  // ---- jobs (grouped by accumulator so that "first" is well defined)
+  std::vector<Tap> staps = taps;
+  std::stable_sort(staps.begin(), staps.end(), [](const Tap& a, const Tap& b) { return a.acc < b.acc; });
+  K.njobs = (int)staps.size();
+  std::vector<ConvJob> jobs(K.njobs);
+  int prev_acc = -1;
+  for (int j = 0; j < K.njobs; ++j) {
+    jobs[j].a_off = key_soff[staps[j].run_key] + staps[j].shift;
+    jobs[j].acc = (int16_t)staps[j].acc;
+    jobs[j].first = (staps[j].acc != prev_acc) ? 1 : 0;
+    prev_acc = staps[j].acc;
+    p->pp.job_tap[j] = (int16_t)staps[j].tap;
+  }
+  K.nacc = nacc;
+  p->njobs_h = K.njobs;
+  for (int j = 0; j < K.njobs; ++j) p->jobs_h[j] = jobs[j];
+
+  p->nsplit = nsplit;
+  p->Ho = Ho; p->Wo = Wo;
+  // P8 outputs carry an even number of planes (zero channels beyond Cout) so that they can feed the next
+  // conv directly: one MMA consumes K = 16 channels = 2 planes
+  p->Cout8 = round_up((gemm_n + 7) / 8, 2);
+  K.Ho = Ho; K.Wo = Wo; K.Cout = gemm_n; K.Cout8 = p->Cout8;
+  K.epilogue = d->epilogue; K.act = d->act;
+
   K.kcp = kcp; K.SA = SA; K.bpb = bpb; K.SB = SB;
   K.nchunks = C8 / kcp;
   K.mmas_per_chunk = K.njobs * (kcp / 2);
@@ -644,8 +788,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
     for (int q = 0; q < kcp / 2; ++q) {
       ConvMma& m = K.mma[j * (kcp / 2) + q];
       m.a_off = jobs[j].a_off + 2 * q * slab;
-      m.acc_col = (uint16_t)(jobs[j].acc * Npad);
-      m.first = (uint16_t)((jobs[j].first && q == 0) ? 1 : 0);
+      m.meta = (uint32_t)(jobs[j].acc * Npad) | ((jobs[j].first && q == 0) ? 0x10000u : 0u);
     }
   K.w_split_units = (int64_t)nblocks_padded * 2 * Npad;
   p->weight_bytes = (size_t)nsplit * K.w_split_units * 16;
@@ -655,8 +798,8 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   if (!(d->kind == NHVR_CONV && d->stride == 2)) in.pad_b += d->in_extra_rows;   // plain formats: only the plane stride grows
   ActGeom gin = make_geom(in);
   K.in_plane_units = gin.plane_units;
-  const int64_t last_q = (int64_t)(K.Hv - 1) * K.Wrow + K.Wv;   // one past the last valid linear position
-  p->tiles_per_img = (int)((last_q + K.tile_step - 1) / K.tile_step);
+  p->tiles_per_img = count_tiles(mrep, stacked);
+  (void)want_split;
 
   PackParams& PP = p->pp;
   PP.Cin = gemm_k; PP.Cout = gemm_n; PP.kh = d->kh; PP.kw = d->kw;
@@ -762,6 +905,32 @@ extern "C" int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const 
     attr_set = true;
   }
   dim3 grid(p->tiles_per_img, p->d.N, p->nsplit);
+  K.trace = nullptr;
+  K.dephase_cycles = 0;
+  {
+    static const char* dp = std::getenv("NHVR_CONV_DEPHASE");       // "0" disables, a number overrides the delay
+    const bool two_per_sm = p->smem_bytes <= 113 * 1024 && K.tmem_cols <= 256;
+    if (two_per_sm && (int64_t)grid.x * grid.y * grid.z >= 4 * 148 && !(dp && std::atoi(dp) == 0)) {
+      const int cyc = std::max({K.Npad / 2, (4096 + 32 * K.Npad) / 128, 40});
+      K.dephase_cycles = (dp && std::atoi(dp) > 0) ? std::atoi(dp) : K.nblocks * K.mrep * cyc;
+    }
+  }
+  if (std::getenv("NHVR_CONV_TRACE")) {     // diagnostics: per-CTA cycle breakdown printed to stderr (synchronises)
+    const size_t nct = (size_t)grid.x * grid.y * grid.z;
+    cudaMalloc(&K.trace, nct * 64);
+    cudaMemset(K.trace, 0, nct * 64);
+    conv_shiftgemm_kernel<<<grid, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(K);
+    cudaDeviceSynchronize();
+    std::vector<long long> h(nct * 8);
+    cudaMemcpy(h.data(), K.trace, nct * 64, cudaMemcpyDeviceToHost);
+    cudaFree(K.trace);
+    double m[8] = {0};
+    for (size_t i = 0; i < nct; ++i) for (int j = 0; j < 8; ++j) m[j] += (double)h[i * 8 + j] / nct;
+    std::fprintf(stderr, "[conv trace] ctas=%zu mrep=%d N=%d  first_wait@%.0f  wait_a=%.0f wait_b=%.0f issue=%.0f  mma_issued@%.0f  last_b_req@%.0f  acc_full@%.0f  epi_done@%.0f cycles (mean per CTA)\n",
+                 nct, K.mrep, K.Npad, m[0], m[1], m[2], m[7], m[3], m[6], m[4], m[5]);
+    count_launch();
+    return NHVR_OK;
+  }
   conv_shiftgemm_kernel<<<grid, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(K);
   count_launch();
   cudaError_t e = cudaGetLastError();

@@ -59,7 +59,7 @@ struct WgParams {
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ WgParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
   const int split = blockIdx.x;
   const int co_blk = blockIdx.y / P.n_ci_blocks, ci_blk = blockIdx.y % P.n_ci_blocks;
   const int grp = blockIdx.z;

@@ -97,10 +97,13 @@ class RenderPipeline(nn.Module):
         step.reset()
         if out is None:
             out = torch.empty(B, T, 3, H, W, dtype=torch.float32, device=dev)
-        for t in range(T):
-            step.pose.copy_(poses[:, t], non_blocking=True)
-            step.run()
-            out[:, t].copy_(step.out, non_blocking=True)
+        if poses.is_cuda and out.is_cuda:
+            for t in range(T):
+                step.pose.copy_(poses[:, t], non_blocking=True)
+                step.run()
+                out[:, t].copy_(step.out, non_blocking=True)
+            return out
+        step.stream_clips(poses, out)
         return out
 
     def step_graph(self, B: int, H: int, W: int, use_graph: bool = True) -> "_StepGraph":
@@ -127,6 +130,7 @@ class _StepGraph:
         self.engG = pipe.netG.engine(B, H, W)
         self.tex = torch.empty(B, pipe.tex_nc, H, W, dtype=torch.float32, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._stage = None
         self.launches_per_step = 0
         if use_graph:
             # warm up on a side stream (attribute set-up, weight packing), then capture
@@ -153,6 +157,69 @@ class _StepGraph:
 
     def reset(self) -> None:
         self.prev.zero_()
+
+    def _staging(self):
+        if self._stage is None:
+            dev = self.pose.device
+            self._stage = {
+                "pose": [torch.empty_like(self.pose) for _ in range(2)],
+                "out": [torch.empty_like(self.out) for _ in range(2)],
+                "h2d": torch.cuda.Stream(device=dev), "d2h": torch.cuda.Stream(device=dev),
+                "pose_ready": [torch.cuda.Event() for _ in range(2)], "pose_free": [torch.cuda.Event() for _ in range(2)],
+                "out_ready": [torch.cuda.Event() for _ in range(2)], "out_free": [torch.cuda.Event() for _ in range(2)],
+            }
+        return self._stage
+
+    def stream_clips(self, poses: torch.Tensor, out: torch.Tensor) -> None:
+        """Host-resident clips: the host->device copy of step t+1's poses and the device->host copy of step
+        t-1's frames run on their own streams under step t's kernels (double-buffered device staging; each
+        clip's frame is one contiguous copy, so pinned host tensors go at full PCIe rate)."""
+        st = self._staging()
+        B, T = poses.shape[:2]
+        cur = torch.cuda.current_stream()
+        h2d, d2h = st["h2d"], st["d2h"]
+        h2d.wait_stream(cur)
+        d2h.wait_stream(cur)
+        used = [False, False]
+
+        def fetch(t: int) -> None:
+            s = t & 1
+            with torch.cuda.stream(h2d):
+                if used[s]:
+                    h2d.wait_event(st["pose_free"][s])
+                if poses.is_cuda:
+                    st["pose"][s].copy_(poses[:, t], non_blocking=True)
+                else:
+                    for b in range(B):
+                        st["pose"][s][b].copy_(poses[b, t], non_blocking=True)
+                st["pose_ready"][s].record(h2d)
+
+        fetch(0)
+        for t in range(T):
+            s = t & 1
+            if t + 1 < T:
+                fetch(t + 1)
+            cur.wait_event(st["pose_ready"][s])
+            self.pose.copy_(st["pose"][s], non_blocking=True)
+            st["pose_free"][s].record(cur)
+            self.run()
+            if used[s]:
+                cur.wait_event(st["out_free"][s])
+            st["out"][s].copy_(self.out, non_blocking=True)
+            st["out_ready"][s].record(cur)
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(st["out_ready"][s])
+                if out.is_cuda:
+                    out[:, t].copy_(st["out"][s], non_blocking=True)
+                else:
+                    for b in range(B):
+                        out[b, t].copy_(st["out"][s][b], non_blocking=True)
+                st["out_free"][s].record(d2h)
+            used[s] = True
+        cur.wait_stream(d2h)
+        cur.wait_stream(h2d)
+        if not out.is_cuda:
+            d2h.synchronize()
 
     def _body(self) -> None:
         pipe = self.pipe

@@ -206,6 +206,12 @@ int main(int argc, char** argv) {
         {"PERF c7s1 48->4 512^2 b1", NHVR_CONV, 48, 4, 7, 1, 3, 1, 512, 512, R, NHVR_EPI_BIAS_ACT_F32, NHVR_ACT_TANH_SIGMOID_LAST},
         {"PERF c3s2 48->96 512^2 b1", NHVR_CONV, 48, 96, 3, 2, 1, 1, 512, 512, Z, NHVR_EPI_RAW_STATS, 0},
         {"PERF ct 96->48 256^2 b1", NHVR_CONV_TRANSPOSE, 96, 48, 3, 2, 1, 1, 256, 256, Z, NHVR_EPI_RAW_STATS, 0},
+        {"PERF c7s1 64->73 512^2 b8", NHVR_CONV, 64, 73, 7, 1, 3, 8, 512, 512, R, NHVR_EPI_BIAS_ACT_F32, 0},
+        {"PERF c7s1 16->64 512^2 b8", NHVR_CONV, 16, 64, 7, 1, 3, 8, 512, 512, R, NHVR_EPI_RAW_STATS, 0},
+        {"PERF c3s2 64->128 512^2 b8", NHVR_CONV, 64, 128, 3, 2, 1, 8, 512, 512, Z, NHVR_EPI_RAW_STATS, 0},
+        {"PERF c3s2 128->256 256^2 b8", NHVR_CONV, 128, 256, 3, 2, 1, 8, 256, 256, Z, NHVR_EPI_RAW_STATS, 0},
+        {"PERF ct 256->128 128^2 b8", NHVR_CONV_TRANSPOSE, 256, 128, 3, 2, 1, 8, 128, 128, Z, NHVR_EPI_RAW_STATS, 0},
+        {"PERF ct 128->64 256^2 b8", NHVR_CONV_TRANSPOSE, 128, 64, 3, 2, 1, 8, 256, 256, Z, NHVR_EPI_RAW_STATS, 0},
     };
     int pidx = -1;
     for (auto& c : perf) {

@@ -50,6 +50,64 @@ __global__ void __launch_bounds__(128, 1) mma_bench(int N, int iters, int mode, 
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// Cadence experiment: the conv kernel commits to an mbarrier after every weight stage (grp MMAs) and waits on the
+// next stage's full barrier.  cadence 1: commit only; 2: + wait on an already-completed barrier + fence;
+// 3: full handshake with a second warp that re-arms the stage as soon as the commit arrives (no copies).
+__global__ void __launch_bounds__(128, 1) mma_cadence(int N, int iters, int grp, int cadence, int nst, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full[8], empty[8], done;
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(&done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(&tmem_ptr, 512); tmem_relinquish(); }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_ptr;
+  const int nstage_iters = iters / grp;
+  if (warp == 2 && cadence == 3) {          // "producer": stage s is full again as soon as it was released
+    int st = 0; uint32_t ph = 0;
+    for (int s = 0; s < nstage_iters; ++s) {
+      mbar_wait(&empty[st], ph ^ 1u);
+      if (elect_one()) mbar_arrive(&full[st]);
+      __syncwarp();
+      if (++st == nst) { st = 0; ph ^= 1u; }
+    }
+  }
+  if (warp == 1) {
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_16(128, (uint32_t)N, 0);
+    const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + 96 * 1024);
+    const uint64_t adesc = make_desc_nosw(a_base, 8192, 128);
+    const uint64_t bdesc = make_desc_nosw(b_base, (uint32_t)N * 16, 128);
+    __syncwarp();
+    long long t0 = clock64();
+    int st = 0; uint32_t ph = 0;
+    for (int s = 0; s < nstage_iters; ++s) {
+      if (cadence == 3) { mbar_wait(&full[st], ph); tc_fence_after(); }
+      else if (cadence == 2) { mbar_wait(&done, 1); tc_fence_after(); }      // parity-1 wait on a fresh barrier returns at once
+      for (int k = 0; k < grp; ++k)
+        if (leader) umma_bf16(tmem, adesc + (uint64_t)((k & 3) * 2), bdesc + (uint64_t)(k * 64), idesc, 1u);
+      if (cadence >= 1 && leader) umma_commit(&empty[st]);
+      if (++st == nst) { st = 0; ph ^= 1u; }
+    }
+    if (leader) umma_commit(&done);
+    mbar_wait(&done, 0);
+    long long t1 = clock64();
+    if (leader && blockIdx.x == 0) cycles[0] = t1 - t0;
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
 int main() {
   long long* d; cudaMalloc(&d, 8);
   cudaFuncSetAttribute(mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -71,6 +129,23 @@ int main() {
           const double cyc = (double)h / iters;
           printf("%-10s %-6d %-6d %-8d %10.1f %12.1f\n", mode ? "sw128" : "nosw", N, shift, two + 1, cyc,
                  2.0 * 128 * N * 16 / cyc * 1.9e9 * 148 / 1e12);
+        }
+  cudaFuncSetAttribute(mma_cadence, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  printf("\n%-8s %-5s %-5s %-8s %-4s %10s\n", "cadence", "N", "grp", "stages", "", "cyc/MMA");
+  for (int N : {96, 192, 256})
+    for (int grp : {1, 3, 6, 9})
+      for (int cad : {0, 1, 2, 3})
+        for (int nst : {2, 4}) {
+          if (cad != 3 && nst != 4) continue;
+          const int it2 = 4096 / grp * grp;
+          long long h = 0;
+          for (int rep = 0; rep < 2; ++rep) {
+            mma_cadence<<<148, 128, 200 * 1024>>>(N, it2, grp, cad, nst, d);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+          }
+          cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+          printf("%-8d %-5d %-5d %-8d %-4s %10.1f\n", cad, N, grp, nst, "", (double)h / it2);
         }
   return 0;
 }

@@ -225,6 +225,25 @@ def test_pipeline_lockstep_clips_equal_single(cuda_dev):
         assert (both[b] - single).abs().max().item() <= 5e-3
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_pipeline_host_clips_stream_under_compute(cuda_dev, pinned):
+    """Host-resident poses in / frames out (copies double-buffered on side streams) equal the
+    device-resident call; 5 steps so both staging slots are reused."""
+    kw = _small_kw()
+    kw.update(n_downsample_global=1, n_blocks_global=1, n_downsample_translate=1, n_downsample_bg=1)
+    pipe, _ = _pair_pipeline(cuda_dev, kw, seed=17)
+    poses_h = torch.rand(2, 5, 3, 64, 64) * 2 - 1
+    out_h = torch.full((2, 5, 3, 64, 64), float("nan"))
+    if pinned:
+        poses_h, out_h = poses_h.pin_memory(), out_h.pin_memory()
+    dev_frames = pipe.render_clips(poses_h.to(cuda_dev))
+    for _ in range(2):
+        ret = pipe.render_clips(poses_h, out=out_h)
+        assert ret is out_h and torch.isfinite(out_h).all()
+        assert (out_h - dev_frames.cpu()).abs().max().item() <= 5e-3
+        out_h.fill_(float("nan"))
+
+
 # ------------------------------------------------------------------ training side: discriminator + losses (forward)
 @pytest.mark.parametrize("getIntermFeat,num_D,size,batch", [(True, 2, 96, 2), (False, 2, 64, 1), (True, 3, 128, 1)])
 def test_discriminator_parity(cuda_dev, getIntermFeat, num_D, size, batch):
