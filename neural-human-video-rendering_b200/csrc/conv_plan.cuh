@@ -45,7 +45,6 @@ struct ConvKParams {
   int32_t tmem_cols;
   int32_t f16;             // operand element type: 0 bf16, 1 fp16
   int32_t debug;           // NHVR_CONV_DEBUG experiments (results are wrong when set): 8 no epilogue, 16 no statistics, 64 no global stores
-  int32_t dephase_cycles;  // > 0: CTAs that land in the second slot of an SM in the first wave start their MMAs this much later
   ActGeom og;              // BIAS_ACT_P8 destination
   int32_t mmas_per_chunk, stages_per_chunk;
   int32_t tile_step;       // linear positions a CTA advances by: 128, or 128-(kw-1) in row mode
@@ -54,6 +53,8 @@ struct ConvKParams {
   // mrep MMAs), `q_mstride` linear positions / `a_mstride` slab units apart.  xtiles > 0: the blocks are the same
   // 128-pixel row segment of mrep consecutive output rows ("stacked"); xtiles == 0: mrep*128 consecutive positions.
   int32_t mrep, a_mstride, q_mstride, xtiles, acc_mstride;
+  int32_t dephase_cycles;  // experiment: CTAs in the second slot of an SM (first wave) start their MMAs this much later
+  int32_t pair;            // 1: launched as clusters of two CTAs running cta_group::2 MMAs (weights packed per CTA half)
   ConvRun runs[kMaxRuns];
   ConvMma mma[kMaxMma + 1];   // +1: the issue loop prefetches one entry ahead
 };
@@ -71,6 +72,7 @@ struct PackParams {
   int32_t f16;
   int32_t flip;                // dgrad of a stride-1 conv: taps mirrored (r,s) -> (kh-1-r, kw-1-s)
   int32_t rowmode, Cp;         // row mode: job_tap = r*8 + accumulator, column n = s*Cp + co
+  int32_t pair, bpb;           // CTA-pair layout: [stage of bpb blocks][rank][bpb][2][Npad/2][8]
   int16_t job_tap[kMaxJobs];   // r*kw + s of each job
 };
 }  // namespace nhvr

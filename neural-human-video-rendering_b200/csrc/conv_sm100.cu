@@ -62,19 +62,31 @@ NHVR_DEVINL float warp_colsum16(const float (&v)[16], int lane) {
   return a1;
 }
 
-NHVR_DEVINL float apply_act(float x, int act, bool is_last) {
-  switch (act) {
-    case NHVR_ACT_RELU: return fmaxf(x, 0.f);
-    case NHVR_ACT_LRELU02: return x > 0.f ? x : 0.2f * x;
-    case NHVR_ACT_TANH: return tanhf(x);
-    case NHVR_ACT_TANH_SIGMOID_LAST: return is_last ? 1.f / (1.f + __expf(-x)) : tanhf(x);
-    default: return x;
+// bias + activation on 16 consecutive output channels.  The switch sits OUTSIDE the per-channel loops: a per-element
+// switch compiles to an indirect branch per value and serialises the epilogue (measured: 13.5 K cycles per 128 x 80
+// block of the UV head, profiles/r01_conv_ablation.md).
+NHVR_DEVINL void bias_act16(const float (&v)[16], const float* sb, int act, int c0, int Cout, float (&t)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) t[i] = v[i] + sb[i];
+  if (act == NHVR_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = fmaxf(t[i], 0.f);
+  } else if (act == NHVR_ACT_LRELU02) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = t[i] > 0.f ? t[i] : 0.2f * t[i];
+  } else if (act == NHVR_ACT_TANH) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = tanhf(t[i]);
+  } else if (act == NHVR_ACT_TANH_SIGMOID_LAST) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = (c0 + i == Cout - 1) ? 1.f / (1.f + __expf(-t[i])) : tanhf(t[i]);
   }
 }
 
-// one 16-channel group of one output pixel: raw P8 store (+ InstanceNorm statistics), or bias + activation
+// one 16-channel group of one output pixel: raw P8 store (+ InstanceNorm statistics), or bias + activation.
+// sb: this group's 16 bias values in shared memory (zeros beyond Cout / without bias).
 NHVR_DEVINL void emit16(const ConvKParams& P, const float (&v)[16], int c0, bool valid, int n, int Y, int X, int g_local, int lane,
-                        float* s_stats) {
+                        float* s_stats, const float* sb) {
   if (P.debug & 64) valid = valid && (v[0] == 123456.f);
   if (P.epilogue == NHVR_EPI_RAW_STATS || P.epilogue == NHVR_EPI_RAW_P8) {
     if (valid) {
@@ -100,27 +112,22 @@ NHVR_DEVINL void emit16(const ConvKParams& P, const float (&v)[16], int c0, bool
     }
   } else if (P.epilogue == NHVR_EPI_BIAS_ACT_F32) {
     if (valid) {
-      float* o = reinterpret_cast<float*>(P.out);
+      float t[16];
+      bias_act16(v, sb, P.act, c0, P.Cout, t);
+      const int64_t plane = (int64_t)P.Ho * P.Wo;
+      float* o = reinterpret_cast<float*>(P.out) + (((int64_t)n * P.Cout + c0) * P.Ho + Y) * P.Wo + X;
+      const int nc = P.Cout - c0;            // channels of this group that exist (warp-uniform)
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int c = c0 + i;
-        if (c < P.Cout) {
-          float val = v[i] + (P.bias ? __ldg(P.bias + c) : 0.f);
-          val = apply_act(val, P.act, c == P.Cout - 1);
-          o[(((int64_t)n * P.Cout + c) * P.Ho + Y) * P.Wo + X] = val;
-        }
-      }
+      for (int i = 0; i < 16; ++i)
+        if (i < nc) o[i * plane] = t[i];
     }
   } else {  // NHVR_EPI_BIAS_ACT_P8
     if (valid) {
       uint4* o = reinterpret_cast<uint4*>(P.out);
       float t[16];
+      bias_act16(v, sb, P.act, c0, P.Cout, t);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int c = c0 + i;
-        float val = (c < P.Cout) ? v[i] + (P.bias ? __ldg(P.bias + c) : 0.f) : 0.f;
-        t[i] = (c < P.Cout) ? apply_act(val, P.act, c == P.Cout - 1) : 0.f;
-      }
+      for (int i = 0; i < 16; ++i) t[i] = (c0 + i < P.Cout) ? t[i] : 0.f;
       uint4 lo, hi;
       lo.x = pack2(t[0], t[1], P.f16);  lo.y = pack2(t[2], t[3], P.f16);
       lo.z = pack2(t[4], t[5], P.f16);  lo.w = pack2(t[6], t[7], P.f16);
@@ -135,6 +142,12 @@ NHVR_DEVINL void emit16(const ConvKParams& P, const float (&v)[16], int c0, bool
 
 constexpr int kThreads = 384;       // warps 0-3: roles, warps 4-11: epilogue
 
+// PAIR: two CTAs of a cluster (the two SMs of a TPC) run ONE M = 256 tcgen05.mma.cta_group::2 per weight block: each
+// CTA stages its own 128-position input slab and only HALF of the weight block's N rows, so the shared-memory traffic
+// per MMA (the measured ceiling of the single-CTA kernel: profiles/r01_conv_ablation.md) drops from
+// A + 2*B to A + B bytes.  The leader (rank 0) issues the MMAs; the peer's MMA warp relays its local "stage full"
+// events to the leader's barriers; commits are multicast to both CTAs; each CTA drains its own 128 TMEM lanes.
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __grid_constant__ ConvKParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   // warp index through a shuffle: provably warp-uniform, so the role branches and everything inside them (ring
@@ -152,12 +165,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
   } else {
     q0 = (int64_t)blockIdx.x * P.tile_step;
   }
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   // K-chunk order is rotated per CTA: neighbouring CTAs stream different parts of the (shared) packed
   // weights at any instant instead of all hitting the same L2 lines in lock-step.
-  const int rot = (int)(blockIdx.x % (unsigned)P.nchunks);
+  const int rot = (int)((PAIR ? blockIdx.x >> 1 : blockIdx.x) % (unsigned)P.nchunks);   // one rotation per CTA pair
 
   const uint32_t a_stage_bytes = (uint32_t)P.kcp * P.slab_units * 16u;
-  const uint32_t b_block_bytes = (uint32_t)P.Npad * 32u;
+  const uint32_t b_block_bytes = (uint32_t)P.Npad * (PAIR ? 16u : 32u);   // PAIR: this CTA's N/2 rows of the block
   const uint32_t b_stage_bytes = b_block_bytes * P.bpb;
   uint8_t* a_smem = smem;
   uint8_t* b_smem = a_smem + (size_t)P.SA * a_stage_bytes;
@@ -167,24 +181,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
   uint64_t* b_full = a_empty + P.SA;
   uint64_t* b_empty = b_full + P.SB;
   uint64_t* acc_full = b_empty + P.SB;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* a_peer = acc_full + 1;           // PAIR, leader only: the peer's slab / weight stage is full
+  uint64_t* b_peer = a_peer + P.SA;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_peer + P.SB);
   float* s_stats = reinterpret_cast<float*>(tmem_ptr + 2);   // [Npad][2]
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < P.SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < P.SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     mbar_init(acc_full, 1);
+    for (int i = 0; i < P.SA; ++i) mbar_init(&a_peer[i], 1);
+    for (int i = 0; i < P.SB; ++i) mbar_init(&b_peer[i], 1);
     fence_mbar_init();
   }
   if (warp == 3) {
-    tmem_alloc(tmem_ptr, (uint32_t)P.tmem_cols);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc2(tmem_ptr, (uint32_t)P.tmem_cols); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_ptr, (uint32_t)P.tmem_cols); tmem_relinquish(); }
   }
+  float* s_bias = s_stats + P.Npad * 2 * P.nacc;             // [Npad] bias of this CTA's output channels
   if (warp >= 4) {
     for (int i = threadIdx.x - 128; i < P.Npad * 2 * P.nacc; i += 256) s_stats[i] = 0.f;
+    for (int i = threadIdx.x - 128; i < P.Npad; i += 256) {
+      const int c = split * P.Npad + i;
+      s_bias[i] = (P.bias && c < P.Cout) ? __ldg(P.bias + c) : 0.f;
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();     // PAIR: the peer's barriers must be initialised before remote arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -219,7 +242,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
       const uint4* wbase = P.w + (int64_t)split * P.w_split_units;
       const uint32_t stage_units = b_stage_bytes >> 4;
       int gs = rot * P.stages_per_chunk;              // global stage index, rotated start
-      const uint4* wsrc = wbase + (int64_t)gs * stage_units;
+      // PAIR weights are packed [stage][rank][bpb][2][N/2][8]: each CTA's half of a stage is one contiguous copy
+      const uint32_t src_step = PAIR ? 2u * stage_units : stage_units;
+      const uint4* wsrc = wbase + (int64_t)gs * src_step + (PAIR ? rank * stage_units : 0u);
       int st = 0;
       uint32_t ph = 0;
       for (int s = 0; s < P.nbstages; ++s) {
@@ -230,9 +255,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
           bulk_g2s(b_smem + (size_t)st * b_stage_bytes, wsrc, b_stage_bytes, &b_full[st]);
         }
         __syncwarp();
-        wsrc += stage_units;
-        if (++gs == P.nbstages) { gs = 0; wsrc = wbase; }
+        wsrc += src_step;
+        if (++gs == P.nbstages) { gs = 0; wsrc = wbase + (PAIR ? rank * stage_units : 0u); }
         if (++st == P.SB) { st = 0; ph ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2 && PAIR && rank != 0) {
+    // ------------------------------------------------------------------ peer of a CTA pair: relay "stage full" to the leader
+    {
+      const int SA = P.SA, SB = P.SB, nchunks = P.nchunks, spc = P.stages_per_chunk;
+      int ast = 0, bst = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(&a_full[ast], aph);
+        if (elect_one()) mbar_arrive_remote(&a_peer[ast], 0);
+        __syncwarp();
+        for (int s = 0; s < spc; ++s) {
+          mbar_wait(&b_full[bst], bph);
+          if (elect_one()) mbar_arrive_remote(&b_peer[bst], 0);
+          __syncwarp();
+          if (++bst == SB) { bst = 0; bph ^= 1u; }
+        }
+        if (++ast == SA) { ast = 0; aph ^= 1u; }
       }
     }
     __syncwarp();
@@ -241,9 +286,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
     // One thread feeds the tensor core, so this loop is kept to a handful of integer ops per MMA:
     // descriptors are advanced incrementally in 16-byte units, ring positions by counters (no div/mod).
     {
-      const uint32_t idesc = make_idesc_16(kTileM, (uint32_t)P.Npad, P.f16);
+      const uint32_t idesc = make_idesc_16(PAIR ? 2 * kTileM : kTileM, (uint32_t)P.Npad, P.f16);
       const uint32_t a_lbo_u = (uint32_t)P.slab_units;            // plane stride, 16-B units
-      const uint32_t b_lbo_u = (uint32_t)P.Npad;
+      const uint32_t b_lbo_u = PAIR ? (uint32_t)P.Npad >> 1 : (uint32_t)P.Npad;   // K-group stride = rows held by this CTA
       const uint32_t desc_hi = (128u >> 4) | (1u << 14);          // SBO = 128 B, version 1, no swizzle
       const uint32_t a_lo0 = ((smem_u32(a_smem) & 0x3FFFFu) >> 4) | (a_lbo_u << 16);
       const uint32_t b_lo0 = ((smem_u32(b_smem) & 0x3FFFFu) >> 4) | (b_lbo_u << 16);
@@ -257,59 +302,77 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
       const bool leader = elect_one();
       // chunk -> weight stage -> MMA.  All ring bookkeeping sits at stage granularity (bpb divides the MMAs of a
       // chunk by construction); the innermost loop is: load table entry, two adds, tcgen05.mma.
-      // Two CTAs share an SM.  Started together they stay in lock-step: both in their MMA phase (each at half the
-      // tensor rate), then both in their epilogue with the tensor pipe idle.  Delaying the second CTA of each SM by
-      // about one MMA phase once, in the first wave, makes every later epilogue / prologue run under the other
-      // CTA's MMAs (the lag is preserved from tile to tile: profiles/r01_conv_ablation.md).
-      if (P.dephase_cycles > 0) {
+      if (P.dephase_cycles > 0) {       // experiment (NHVR_CONV_DEPHASE=<cycles>): break the lock-step of the two co-resident CTAs
         const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
         unsigned nsm;
         asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsm));
         if (lin >= nsm && lin < 2 * nsm) {
           const long long until = clock64() + P.dephase_cycles;
-          while (clock64() < until) __nanosleep(200);
+          while (clock64() < until) {}
         }
       }
-      long long wa = 0, wb = 0, wi = 0;
+      long long wa = 0, wb = 0;
       const long long t_mma0 = trace ? clock64() : 0;
+      // The barrier wait of the NEXT weight stage (and slab chunk) is issued before the LAST MMA of the current stage:
+      // a try_wait costs ~100-200 cycles even on a completed phase, and the tensor pipe only buffers about two MMAs
+      // behind the running one - waiting between stages drained it once per stage (profiles/r01_conv_ablation.md).
+      auto wait_a = [&](int st, uint32_t ph) {
+        const long long c0 = trace ? clock64() : 0;
+        mbar_wait(&a_full[st], ph);
+        if (PAIR) mbar_wait_cluster(&a_peer[st], ph);
+        if (trace) wa += clock64() - c0;
+      };
+      auto wait_b = [&](int st, uint32_t ph) {
+        const long long c0 = trace ? clock64() : 0;
+        mbar_wait(&b_full[st], ph);
+        if (PAIR) mbar_wait_cluster(&b_peer[st], ph);
+        if (trace) wb += clock64() - c0;
+      };
+      wait_a(0, 0);
+      wait_b(0, 0);
+      tc_fence_after();
       for (int c = 0; c < nchunks; ++c) {
-        if (trace) { const long long c0 = clock64(); mbar_wait(&a_full[ast], aph); wa += clock64() - c0; }
-        else mbar_wait(&a_full[ast], aph);
         const uint32_t a_st_lo = a_lo0 + (uint32_t)ast * a_stage_u;
         const uint32_t keep_mask = (c == 0) ? 0u : 1u;          // chunk 0: the first MMA of an accumulator overwrites
+        const int nast = (ast + 1 == SA) ? 0 : ast + 1;
+        const uint32_t naph = aph ^ ((ast + 1 == SA) ? 1u : 0u);
         const ConvMma* e = P.mma;
         ConvMma cur = e[0];                                   // software-pipelined table read: the constant-bank
         for (int s = 0; s < spc; ++s) {                       // load of entry i+1 overlaps the issue of MMA i
-          if (trace) { const long long c0 = clock64(); mbar_wait(&b_full[bst], bph); wb += clock64() - c0; }
-          else mbar_wait(&b_full[bst], bph);
-          tc_fence_after();
-          const long long ci0 = trace ? clock64() : 0;
+          const int nbst = (bst + 1 == SB) ? 0 : bst + 1;
+          const uint32_t nbph = bph ^ ((bst + 1 == SB) ? 1u : 0u);
 #pragma unroll 1
           for (int k = 0; k < bpb; ++k) {
             ++e;
             const ConvMma nxt = *e;                           // one entry past the end is still inside ConvKParams
+            if (k == bpb - 1) {                               // pre-wait what the next stage needs
+              if (s + 1 < spc) wait_b(nbst, nbph);
+              else if (c + 1 < nchunks) { wait_a(nast, naph); wait_b(nbst, nbph); }
+            }
             if (leader) {
               const uint32_t acc_flag = keep_mask | ((cur.meta >> 16) ^ 1u);
               uint32_t a_lo = a_st_lo + (uint32_t)cur.a_off, d_col = tmem_base + (cur.meta & 0xffffu);
-              umma_bf16(d_col, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc_flag);
+              if (PAIR) umma2_bf16(d_col, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc_flag);
+              else umma_bf16(d_col, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc_flag);
               for (int i = 1; i < mrep; ++i) {               // the same weight block feeds the other M blocks
                 a_lo += a_mstride; d_col += acc_mstride;
-                umma_bf16(d_col, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc_flag);
+                if (PAIR) umma2_bf16(d_col, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc_flag);
+                else umma_bf16(d_col, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc_flag);
               }
             }
             b_lo += b_block_u;
             cur = nxt;
           }
-          if (leader) umma_commit(&b_empty[bst]);
-          if (trace) wi += clock64() - ci0;
-          if (++bst == SB) { bst = 0; bph ^= 1u; b_lo = b_lo0; }
+          if (leader) { if (PAIR) umma2_commit(&b_empty[bst]); else umma_commit(&b_empty[bst]); }
+          bst = nbst; bph = nbph;
+          if (bst == 0) b_lo = b_lo0;
         }
-        if (leader) umma_commit(&a_empty[ast]);
-        if (++ast == SA) { ast = 0; aph ^= 1u; }
+        if (leader) { if (PAIR) umma2_commit(&a_empty[ast]); else umma_commit(&a_empty[ast]); }
+        ast = nast; aph = naph;
       }
       __syncwarp();
-      if (elect_one()) umma_commit(acc_full);
-      if (trace && lane == 0) { trace[0] = t_mma0 - t_entry; trace[1] = wa; trace[2] = wb; trace[3] = clock64() - t_entry; trace[7] = wi; }
+      if (elect_one()) { if (PAIR) umma2_commit(acc_full); else umma_commit(acc_full); }
+      if (trace && lane == 0) { trace[0] = t_mma0 - t_entry; trace[1] = wa; trace[2] = wb; trace[3] = clock64() - t_entry; }
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -333,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
       // ---- row mode: accumulator column n = s*Cp + co holds Z[m][s][co]; output Y[m][co] = sum_s Z[m+s][s][co].
       // Warps 4-7 exchange one 16-column chunk at a time through shared memory (row m reads row m+s).
       if (half == 0 && !(P.debug & 8)) {
-        float* S = s_stats + P.Npad * 2 * P.nacc;           // [128][17] floats
+        float* S = s_bias + P.Npad;                         // [128][17] floats
         const bool valid = valid_m && (m < P.tile_step);
         const int ngrp = (P.Cp + 15) >> 4;
         for (int cg = 0; cg < ngrp; ++cg) {
@@ -368,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");
           }
-          emit16(P, acc, cg * 16, valid, n, y, x, cg, lane, s_stats);
+          emit16(P, acc, cg * 16, valid, n, y, x, cg, lane, s_stats, s_bias + cg * 16);
         }
       }
     } else {
@@ -390,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(vr[i]);
-          emit16(P, v, cout_off + g * 16, valid, n, Y, X, g, lane, s_stats);
+          emit16(P, v, cout_off + g * 16, valid, n, Y, X, g, lane, s_stats, s_bias + g * 16);
         }
       }
     }
@@ -405,10 +468,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
 
   if (trace && threadIdx.x == 128) trace[5] = clock64() - t_entry;
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();     // PAIR: the leader's MMAs read the peer's shared memory and TMEM
   if (warp == 3) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+    if (PAIR) tmem_dealloc2(tmem_base, (uint32_t)P.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
   }
 }
 
@@ -453,7 +516,14 @@ __global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
       packed[0] = pack2(vals[0], vals[1], P.f16); packed[1] = pack2(vals[2], vals[3], P.f16);
       packed[2] = pack2(vals[4], vals[5], P.f16); packed[3] = pack2(vals[6], vals[7], P.f16);
     }
-    P.dst[u] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    int64_t du = u;
+    if (P.pair) {              // [split][stage][rank][block in stage][k-group][N/2 rows]
+      const int half = P.Npad >> 1;
+      const int r = nrow >= half ? 1 : 0;
+      const int stage = blk / P.bpb, j = blk - stage * P.bpb;
+      du = (int64_t)z * P.nblocks_padded * 2 * P.Npad + ((int64_t)(stage * 2 + r) * P.bpb + j) * P.Npad + (int64_t)kp * half + (nrow - r * half);
+    }
+    P.dst[du] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
   }
 }
 
@@ -466,6 +536,9 @@ using namespace nhvr;
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline int next_pow2_cols(int c) { int p = 32; while (p < c) p <<= 1; return p; }
+// dynamic shared memory per CTA: two co-resident CTAs need 2 * (bytes + 1 KB reserved) <= 228 KB; one CTA may use 227 KB
+constexpr long kSmemTwoPerSm = (228 * 1024) / 2 - 1024 - 256;
+constexpr long kSmemOnePerSm = 227 * 1024 - 1024;
 
 extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** out) {
   if (!d || !out) return NHVR_ERR_NULL;
@@ -663,20 +736,25 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
     K.tmem_cols = next_pow2_cols(mrep * nacc * Npad);
   };
   int kcp = 0, SA = 0, bpb = 0, SB = 0;
-  auto try_fit = [&](int budget) -> bool {
+  // exact dynamic shared memory of a configuration (must equal what the kernel carves up)
+  int pair = 0;
+  auto smem_need = [&](int kcp_, int sa, int dv, int sb) -> long {
+    return (long)sa * kcp_ * slab * 16 + (long)sb * dv * Npad * (pair ? 16 : 32) + (long)(3 * sa + 3 * sb + 1) * 8 + 8 + (long)Npad * 8 * nacc +
+           (long)Npad * 4 + (rowmode ? 8704 : 0) + 128;
+  };
+  auto try_fit = [&](long limit) -> bool {
     const int b_block = Npad * 32;
     long best_score = -1;
     for (int cand = 8; cand >= 2; cand -= 2) {
       if (C8 % cand) continue;
       const int nch = C8 / cand;
       const int sa = std::min(2, nch);
-      const long a_bytes = (long)sa * cand * slab * 16;
       const int bpc = (int)taps.size() * cand / 2;          // MMA blocks per chunk
       if (bpc > kMaxMma) continue;
-      const long rem = budget - a_bytes - 1024 - (long)Npad * 8 * nacc - (rowmode ? 8704 : 0);
       for (int dv = 8; dv >= 1; --dv) {                      // blocks per B stage: a divisor of bpc, stage <= 24 KB
-        if (bpc % dv || (long)dv * b_block > 24576) continue;
-        const int sb = (int)std::min<long>(6, rem / ((long)dv * b_block));
+        if (bpc % dv || (long)dv * b_block > (pair ? 49152 : 24576)) continue;
+        int sb = 6;
+        while (sb >= 2 && smem_need(cand, sa, dv, sb) > limit) --sb;
         if (sb < 2) continue;
         // score: weight bytes in flight, mild preference for >= 3 stages and for fewer, larger chunks
         const long score = (long)std::min(sb, 4) * dv * b_block + (sb >= 3 ? 4096 : 0) + cand * 64;
@@ -725,8 +803,8 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
         if (!force_m && (int64_t)count_tiles(m, stk) * d->N * std::max(ws, 1) < 148) continue;   // keep every SM busy
         if (layout_runs(m, stk) != NHVR_OK) continue;
         tile_n(m, ws);
-        if (K.tmem_cols <= 256) ok = try_fit(112 * 1024);
-        else if (force_m) ok = try_fit(220 * 1024);
+        if (K.tmem_cols <= 256) ok = try_fit(kSmemTwoPerSm);
+        else if (force_m) ok = try_fit(kSmemOnePerSm);
         if (ok) { mrep = m; stacked = stk; want_split = ws; }
       }
     }
@@ -736,7 +814,23 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
     st0 = build_geometry(1, false);
     if (st0 == NHVR_OK) st0 = layout_runs(1, false);
     if (st0 != NHVR_OK) { delete p; return st0; }
-    tile_n(1, 1);
+    // transposed convs hold 4 phase accumulators: wide outputs are split over CTAs so that 4*N <= 256 TMEM columns and
+    // two CTAs share an SM (the epilogue of 4 x 128 x N outputs is otherwise fully exposed); 256->128: 419 -> 448 TFLOP/s
+    int tsplit = 1;
+    if (d->kind == NHVR_CONV_TRANSPOSE && !(d->flags & 1) && !(std::getenv("NHVR_CONVT_SPLIT") && std::atoi(std::getenv("NHVR_CONVT_SPLIT")) == 0))
+      while (nacc * round_up((gemm_n + tsplit - 1) / tsplit, 16) > 256 && round_up((gemm_n + tsplit - 1) / tsplit, 16) > 32) tsplit *= 2;
+    if (force_m == 1 && force_split > tsplit) tsplit = force_split;          // experiments: NHVR_CONV_MREP=1,<nsplit>
+    tile_n(1, tsplit);
+    // CTA pairs (cta_group::2) for the wide layers: one accumulator, N >= 96 (below that the A operand dominates the
+    // shared-memory traffic and M replication is the better tool), not for the plain lowering wgrad mirrors
+    {
+      // measured (profiles/r01_conv_ablation.md): +4 % at N = 192, -14 % at N = 256 (the relay hop costs more than the
+      // halved weight stream saves once the MMA is 128 cycles long) -> default only for 128 < N <= 192;
+      // NHVR_CONV_PAIR=1 forces every eligible layer, =0 disables
+      const char* pe = std::getenv("NHVR_CONV_PAIR");
+      const bool eligible = nacc == 1 && !rowmode && !(d->flags & 1) && Npad >= 96 && (Npad % 16) == 0;
+      pair = eligible && (pe ? std::atoi(pe) != 0 : (Npad > 128 && Npad <= 192)) ? 1 : 0;
+    }
     const int b_block = Npad * 32;
     if (const char* tune = std::getenv("NHVR_CONV_TUNE")) {   // experiments: "kcp,SA,bpb,SB"
       int a, b, c, e;
@@ -746,8 +840,9 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
         if (need <= 227 * 1024) { kcp = a; SA = std::min(b, C8 / a); bpb = c; SB = e; ok = true; }
       }
     }
-    if (!ok && K.tmem_cols <= 256) ok = try_fit(100 * 1024);
-    if (!ok) ok = try_fit(220 * 1024);
+    if (const char* lim = std::getenv("NHVR_CONV_SMEM_LIMIT")) { if (!ok) ok = try_fit(std::atol(lim)); }   // experiments
+    if (!ok && K.tmem_cols <= 256) ok = try_fit(kSmemTwoPerSm);
+    if (!ok) ok = try_fit(kSmemOnePerSm);
     if (!ok) { delete p; return NHVR_ERR_SMEM; }
   }
   const int b_block = Npad * 32;
@@ -778,6 +873,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   K.epilogue = d->epilogue; K.act = d->act;
 
   K.kcp = kcp; K.SA = SA; K.bpb = bpb; K.SB = SB;
+  K.pair = pair;
   K.nchunks = C8 / kcp;
   K.mmas_per_chunk = K.njobs * (kcp / 2);
   K.stages_per_chunk = K.mmas_per_chunk / bpb;           // bpb divides mmas_per_chunk by construction
@@ -792,8 +888,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
     }
   K.w_split_units = (int64_t)nblocks_padded * 2 * Npad;
   p->weight_bytes = (size_t)nsplit * K.w_split_units * 16;
-  p->smem_bytes = (size_t)SA * kcp * slab * 16 + (size_t)SB * bpb * b_block + (size_t)(2 * SA + 2 * SB + 1) * 8 + 8 +
-                  (size_t)Npad * 8 * nacc + (rowmode ? 8704 : 0) + 128;
+  p->smem_bytes = (size_t)smem_need(kcp, SA, bpb, SB);
 
   if (!(d->kind == NHVR_CONV && d->stride == 2)) in.pad_b += d->in_extra_rows;   // plain formats: only the plane stride grows
   ActGeom gin = make_geom(in);
@@ -810,6 +905,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   PP.rowmode = rowmode ? 1 : 0; PP.Cp = K.Cp;
   PP.kcp = kcp; PP.nchunks = K.nchunks; PP.njobs = K.njobs; PP.Npad = Npad; PP.nsplit = nsplit;
   PP.nblocks_padded = nblocks_padded;
+  PP.pair = pair; PP.bpb = bpb;
   *out = p;
   return NHVR_OK;
 }
@@ -900,40 +996,45 @@ extern "C" int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const 
   K.stats = stats;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_shiftgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_shiftgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_shiftgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
     attr_set = true;
   }
-  dim3 grid(p->tiles_per_img, p->d.N, p->nsplit);
-  K.trace = nullptr;
-  K.dephase_cycles = 0;
-  {
-    static const char* dp = std::getenv("NHVR_CONV_DEPHASE");       // "0" disables, a number overrides the delay
-    const bool two_per_sm = p->smem_bytes <= 113 * 1024 && K.tmem_cols <= 256;
-    if (two_per_sm && (int64_t)grid.x * grid.y * grid.z >= 4 * 148 && !(dp && std::atoi(dp) == 0)) {
-      const int cyc = std::max({K.Npad / 2, (4096 + 32 * K.Npad) / 128, 40});
-      K.dephase_cycles = (dp && std::atoi(dp) > 0) ? std::atoi(dp) : K.nblocks * K.mrep * cyc;
+  dim3 grid(K.pair ? (p->tiles_per_img + 1) & ~1 : p->tiles_per_img, p->d.N, p->nsplit);   // pairs: an even number of tiles
+  auto launch = [&]() -> cudaError_t {
+    if (!K.pair) {
+      conv_shiftgemm_kernel<false><<<grid, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(K);
+      return cudaGetLastError();
     }
-  }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = p->smem_bytes; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, conv_shiftgemm_kernel<true>, K);
+  };
+  K.trace = nullptr;
+  { static const char* dp = std::getenv("NHVR_CONV_DEPHASE"); K.dephase_cycles = dp ? std::atoi(dp) : 0; }
   if (std::getenv("NHVR_CONV_TRACE")) {     // diagnostics: per-CTA cycle breakdown printed to stderr (synchronises)
     const size_t nct = (size_t)grid.x * grid.y * grid.z;
     cudaMalloc(&K.trace, nct * 64);
     cudaMemset(K.trace, 0, nct * 64);
-    conv_shiftgemm_kernel<<<grid, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(K);
+    launch();
     cudaDeviceSynchronize();
     std::vector<long long> h(nct * 8);
     cudaMemcpy(h.data(), K.trace, nct * 64, cudaMemcpyDeviceToHost);
     cudaFree(K.trace);
     double m[8] = {0};
     for (size_t i = 0; i < nct; ++i) for (int j = 0; j < 8; ++j) m[j] += (double)h[i * 8 + j] / nct;
-    std::fprintf(stderr, "[conv trace] ctas=%zu mrep=%d N=%d  first_wait@%.0f  wait_a=%.0f wait_b=%.0f issue=%.0f  mma_issued@%.0f  last_b_req@%.0f  acc_full@%.0f  epi_done@%.0f cycles (mean per CTA)\n",
-                 nct, K.mrep, K.Npad, m[0], m[1], m[2], m[7], m[3], m[6], m[4], m[5]);
+    std::fprintf(stderr, "[conv trace] ctas=%zu pair=%d mrep=%d N=%d  first_wait@%.0f  wait_a=%.0f wait_b=%.0f  mma_issued@%.0f  last_b_req@%.0f  acc_full@%.0f  epi_done@%.0f cycles (mean per CTA)\n",
+                 nct, K.pair, K.mrep, K.Npad, m[0], m[1], m[2], m[3], m[6], m[4], m[5]);
     count_launch();
     return NHVR_OK;
   }
-  conv_shiftgemm_kernel<<<grid, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(K);
+  cudaError_t e = launch();
   count_launch();
-  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
   return NHVR_OK;
 }

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "p8.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace nhvr {
 
@@ -98,49 +99,88 @@ struct ApplyParams {
   int32_t f16;
 };
 
-__global__ void __launch_bounds__(256) in_apply_kernel(const __grid_constant__ ApplyParams P) {
+// Latency-bound gather: the statistics loads, and two destination units per thread and pass, are in flight before
+// anything is consumed (software-pipelined: the next pass is loaded while the current one is normalised and stored).
+struct ApplyItem {
+  uint4 r, s;
+  int64_t du;
+  bool live, ok;
+};
+
+template <bool HAS_RES>
+NHVR_DEVINL void apply_fetch(const ApplyParams& P, const ActGeom& g, const uint4* raw, const uint4* res, int i, int total, ApplyItem& it) {
+  it.live = i < total;
+  const int yy = i / g.Wp, xx = i - yy * g.Wp;
+  int y, x;
+  it.ok = it.live && dst_to_src(g, yy, xx, y, x);
+  it.du = plane_unit(g, yy, xx);
+  it.r = make_uint4(0, 0, 0, 0);
+  it.s = make_uint4(0, 0, 0, 0);
+  if (it.ok) {
+    it.r = __ldg(raw + plane_unit(P.rg, y + P.rg.pad_t, x + P.rg.pad_l));
+    if (HAS_RES) it.s = __ldg(res + plane_unit(P.sg, y + P.sg.pad_t, x + P.sg.pad_l));
+  }
+}
+
+template <bool HAS_RES>
+NHVR_DEVINL void apply_emit(const ApplyParams& P, const float (&scale)[8], const float (&shift)[8], uint4* dst, const ApplyItem& it) {
+  if (!it.live) return;
+  uint4 o = make_uint4(0, 0, 0, 0);
+  if (it.ok) {
+    const uint32_t rw[4] = {it.r.x, it.r.y, it.r.z, it.r.w};
+    const uint32_t sw[4] = {it.s.x, it.s.y, it.s.z, it.s.w};
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xv = (e & 1) ? unpack_hi(rw[e >> 1], P.f16) : unpack_lo(rw[e >> 1], P.f16);
+      float t = fmaf(xv, scale[e], shift[e]);
+      if (P.act == NHVR_ACT_RELU) t = fmaxf(t, 0.f);
+      else if (P.act == NHVR_ACT_LRELU02) t = t > 0.f ? t : 0.2f * t;
+      if (HAS_RES) t += (e & 1) ? unpack_hi(sw[e >> 1], P.f16) : unpack_lo(sw[e >> 1], P.f16);
+      v[e] = t;
+    }
+    o.x = pack2(v[0], v[1], P.f16); o.y = pack2(v[2], v[3], P.f16);
+    o.z = pack2(v[4], v[5], P.f16); o.w = pack2(v[6], v[7], P.f16);
+  }
+  dst[it.du] = o;
+}
+
+template <bool HAS_RES>
+__global__ void __launch_bounds__(256, 4) in_apply_kernel(const __grid_constant__ ApplyParams P) {
   const ActGeom& g = P.dg;
   const int np = blockIdx.y;
   const int n = np / g.C8, p = np - n * g.C8;
+  const float4* st4 = reinterpret_cast<const float4*>(P.stats + ((int64_t)n * g.C8 + p) * 16);
+  const float4 q0 = __ldg(st4), q1 = __ldg(st4 + 1), q2 = __ldg(st4 + 2), q3 = __ldg(st4 + 3);
+  const int total = g.Hp * g.Wp;
+  const int stride = gridDim.x * blockDim.x;
+  const uint4* raw = P.raw + ((int64_t)n * P.rg.C8 + p) * P.rg.plane_units;
+  const uint4* res = HAS_RES ? P.res + ((int64_t)n * P.sg.C8 + p) * P.sg.plane_units : nullptr;
+  uint4* dst = P.dst + (int64_t)np * g.plane_units;
+  int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  ApplyItem a0, a1;
+  apply_fetch<HAS_RES>(P, g, raw, res, i0, total, a0);
+  apply_fetch<HAS_RES>(P, g, raw, res, i0 + stride, total, a1);
   float scale[8], shift[8];
   {
-    const float* st = P.stats + ((int64_t)n * g.C8 + p) * 16;
+    const float sv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float mean = st[2 * e] * P.inv_hw;
-      const float var = fmaxf(st[2 * e + 1] * P.inv_hw - mean * mean, 0.f);
+      const float mean = sv[2 * e] * P.inv_hw;
+      const float var = fmaxf(sv[2 * e + 1] * P.inv_hw - mean * mean, 0.f);
       const float rstd = rsqrtf(var + P.eps);
       scale[e] = rstd;
       shift[e] = -mean * rstd;
     }
   }
-  const int total = g.Hp * g.Wp;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int yy = i / g.Wp, xx = i - yy * g.Wp;
-    int y, x;
-    uint4 o = make_uint4(0, 0, 0, 0);
-    if (dst_to_src(g, yy, xx, y, x)) {
-      const uint4 r = P.raw[act_unit(P.rg, n, p, y + P.rg.pad_t, x + P.rg.pad_l)];
-      const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-      float v[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float xv = (e & 1) ? unpack_hi(rw[e >> 1], P.f16) : unpack_lo(rw[e >> 1], P.f16);
-        float t = fmaf(xv, scale[e], shift[e]);
-        if (P.act == NHVR_ACT_RELU) t = fmaxf(t, 0.f);
-        else if (P.act == NHVR_ACT_LRELU02) t = t > 0.f ? t : 0.2f * t;
-        v[e] = t;
-      }
-      if (P.res) {
-        const uint4 s = P.res[act_unit(P.sg, n, p, y + P.sg.pad_t, x + P.sg.pad_l)];
-        const uint32_t sw[4] = {s.x, s.y, s.z, s.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] += (e & 1) ? unpack_hi(sw[e >> 1], P.f16) : unpack_lo(sw[e >> 1], P.f16);
-      }
-      o.x = pack2(v[0], v[1], P.f16); o.y = pack2(v[2], v[3], P.f16);
-      o.z = pack2(v[4], v[5], P.f16); o.w = pack2(v[6], v[7], P.f16);
-    }
-    P.dst[(int64_t)np * g.plane_units + plane_unit(g, yy, xx)] = o;
+  while (i0 < total) {
+    i0 += 2 * stride;
+    ApplyItem b0, b1;
+    apply_fetch<HAS_RES>(P, g, raw, res, i0, total, b0);
+    apply_fetch<HAS_RES>(P, g, raw, res, i0 + stride, total, b1);
+    apply_emit<HAS_RES>(P, scale, shift, dst, a0);
+    apply_emit<HAS_RES>(P, scale, shift, dst, a1);
+    a0 = b0; a1 = b1;
   }
 }
 
@@ -225,8 +265,14 @@ extern "C" int nhvr_in_apply(const void* raw, const nhvr_act_desc* raw_desc, con
   P.act = act;
   P.f16 = operand_f16();
   const int planes = P.dg.N * P.dg.C8;
-  dim3 grid(grid_x_for((int64_t)P.dg.Hp * P.dg.Wp, planes), planes);
-  in_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  const int64_t units = (int64_t)P.dg.Hp * P.dg.Wp;
+  int gx = (int)((units + 256 * 4 - 1) / (256 * 4));                      // two passes of two units per thread ...
+  const int64_t cap = std::max<int64_t>(1, (int64_t)148 * 8 * 4 / std::max(1, planes));
+  if (gx > cap) gx = (int)cap;                                            // ... unless that is more than ~4 waves of CTAs
+  if (const char* e = std::getenv("NHVR_APPLY_GX")) gx = std::max(1, std::atoi(e));
+  dim3 grid(gx, planes);
+  if (P.res) in_apply_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  else in_apply_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }

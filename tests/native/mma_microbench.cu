@@ -108,6 +108,64 @@ __global__ void __launch_bounds__(128, 1) mma_cadence(int N, int iters, int grp,
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// CTA-pair experiment (cta_group::2): M = 256 over two SMs, each CTA supplies its 128 rows of A and half of B.
+// Numeric probe: A rows of CTA r hold (r+1), B rows of CTA r hold (r+1) -> D[m][n] = 16*iters*(rank of m + 1)*(half of n + 1).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma_pair(int N, int iters, long long* cycles, float* probe) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t done;
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const __nv_bfloat16 val = __float2bfloat16((float)(rank + 1));
+  for (int i = threadIdx.x; i < 160 * 1024 / 2; i += 128) reinterpret_cast<__nv_bfloat16*>(smem)[i] = val;
+  if (threadIdx.x == 0) { mbar_init(&done, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc2(&tmem_ptr, 512); tmem_relinquish2(); }
+  fence_proxy_async();
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_ptr;
+  if (warp == 1 && rank == 0) {
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_16(256, (uint32_t)N, 0);
+    const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + 96 * 1024);
+    const uint64_t adesc = make_desc_nosw(a_base, 8192, 128);
+    const uint64_t bdesc = make_desc_nosw(b_base, (uint32_t)(N / 2) * 16, 128);   // this CTA's N/2 rows of B
+    __syncwarp();
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i)
+      if (leader) umma2_bf16(tmem, adesc + (uint64_t)((i & 3) * 2), bdesc, idesc, i ? 1u : 0u);
+    if (leader) umma2_commit(&done);
+    mbar_wait(&done, 0);
+    long long t1 = clock64();
+    if (leader && blockIdx.x == 0) cycles[0] = t1 - t0;
+    __syncwarp();
+  } else {
+    if (warp == 1) mbar_wait(&done, 0);      // the peer learns about completion through the multicast commit
+  }
+  __syncthreads();
+  tc_fence_after();
+  if (blockIdx.x < 2 && probe) {             // rows 0 and 127 of each CTA, columns 0 and N-1
+    if (warp == 0) {
+      uint32_t v[16];
+      tmem_ld16(tmem, v); tmem_ld_wait();
+      if (threadIdx.x == 0) probe[rank * 4 + 0] = __uint_as_float(v[0]);
+      tmem_ld16(tmem + (uint32_t)(N - 16), v); tmem_ld_wait();
+      if (threadIdx.x == 0) probe[rank * 4 + 1] = __uint_as_float(v[15]);
+    }
+    if (warp == 3) {
+      uint32_t v[16];
+      tmem_ld16(tmem + ((uint32_t)96 << 16), v); tmem_ld_wait();
+      if (threadIdx.x == 127) probe[rank * 4 + 2] = __uint_as_float(v[0]);
+      tmem_ld16(tmem + ((uint32_t)96 << 16) + (uint32_t)(N - 16), v); tmem_ld_wait();
+      if (threadIdx.x == 127) probe[rank * 4 + 3] = __uint_as_float(v[15]);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc2(tmem, 512); }
+}
+
 int main() {
   long long* d; cudaMalloc(&d, 8);
   cudaFuncSetAttribute(mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -130,6 +188,26 @@ int main() {
           printf("%-10s %-6d %-6d %-8d %10.1f %12.1f\n", mode ? "sw128" : "nosw", N, shift, two + 1, cyc,
                  2.0 * 128 * N * 16 / cyc * 1.9e9 * 148 / 1e12);
         }
+  {
+    cudaFuncSetAttribute(mma_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    float* probe; cudaMalloc(&probe, 64); cudaMemset(probe, 0, 64);
+    printf("\nCTA pair (cta_group::2), M=256: cyc/MMA and probe D values [rank][row0col0,row0colN-1,row127col0,row127colN-1]\n");
+    for (int N : {96, 192, 256}) {
+      const int it2 = 1024;
+      long long h = 0;
+      for (int rep = 0; rep < 2; ++rep) {
+        mma_pair<<<148, 128, 200 * 1024>>>(N, it2, d, probe);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("pair error %s\n", cudaGetErrorString(e)); return 1; }
+      }
+      float hp[8];
+      cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(hp, probe, 32, cudaMemcpyDeviceToHost);
+      printf("N=%d  %.1f cyc/MMA (M=256: %.1f TFLOP/s @148)  probe/(16*iters): r0 [%.2f %.2f %.2f %.2f] r1 [%.2f %.2f %.2f %.2f]\n", N, (double)h / it2,
+             2.0 * 256 * N * 16 / ((double)h / it2) * 1.9e9 * 74 / 1e12, hp[0] / (16.f * it2), hp[1] / (16.f * it2), hp[2] / (16.f * it2),
+             hp[3] / (16.f * it2), hp[4] / (16.f * it2), hp[5] / (16.f * it2), hp[6] / (16.f * it2), hp[7] / (16.f * it2));
+    }
+  }
   cudaFuncSetAttribute(mma_cadence, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   printf("\n%-8s %-5s %-5s %-8s %-4s %10s\n", "cadence", "N", "grp", "stages", "", "cyc/MMA");
   for (int N : {96, 192, 256})
