@@ -166,6 +166,76 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma_pair(int
   if (warp == 0) { tc_fence_after(); tmem_dealloc2(tmem, 512); }
 }
 
+// Does a concurrent bulk-copy stream into shared memory slow the MMAs down?  warp 0 copies `chunk` bytes at a time from
+// global memory into a ring (as the conv kernel's weight producer does, `depth` copies in flight), warp 1 issues MMAs on
+// resident operands (mode 0) or on B blocks walking through the ring that is being written (mode 1, data irrelevant).
+__global__ void __launch_bounds__(128, 1) mma_with_tma(int N, int iters, int chunk, int depth, int mode, int a_lbo, const uint4* __restrict__ src,
+                                                       long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full[8], done;
+  __shared__ uint32_t tmem_ptr;
+  __shared__ volatile int stop;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) mbar_init(&full[i], 1);
+    mbar_init(&done, 1);
+    stop = 0;
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(&tmem_ptr, 512); tmem_relinquish(); }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_ptr;
+  uint8_t* ring = smem + 64 * 1024;             // 128 KB ring region; A at 0, resident B at 32 KB
+  if (warp == 2 && chunk > 0) {
+    const uint4* g = src + (size_t)blockIdx.x * (1 << 16);     // 1 MB window per CTA (L2 resident)
+    int st = 0; uint32_t ph = 0; long long n = 0;
+    // prime `depth` copies, then keep the ring full until the MMA warp says stop
+    for (int i = 0; i < depth; ++i) {
+      if (elect_one()) { mbar_arrive_expect_tx(&full[i], chunk); bulk_g2s(ring + (size_t)i * chunk, g + ((n * chunk / 16) & 0x7fff), chunk, &full[i]); }
+      ++n;
+    }
+    __syncwarp();
+    while (!stop) {
+      mbar_wait(&full[st], ph);
+      if (elect_one()) { mbar_arrive_expect_tx(&full[st], chunk); bulk_g2s(ring + (size_t)st * chunk, g + ((n * chunk / 16) & 0x7fff), chunk, &full[st]); }
+      __syncwarp();
+      ++n;
+      if (++st == depth) { st = 0; ph ^= 1u; }
+    }
+    for (int i = 0; i < depth; ++i) { mbar_wait(&full[st], ph); if (++st == depth) { st = 0; ph ^= 1u; } }   // drain
+    if (blockIdx.x == 0 && elect_one()) cycles[1] = n * chunk;
+  }
+  if (warp == 1) {
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_16(128, (uint32_t)N, 0);
+    const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + 32 * 1024), r_base = smem_u32(ring);
+    const uint64_t adesc = make_desc_nosw(a_base, (uint32_t)a_lbo, 128);
+    const uint32_t bblk = (uint32_t)N * 32;
+    const int nring = (depth * chunk) / (int)bblk > 0 ? (depth * chunk) / (int)bblk : 1;
+    __syncwarp();
+    long long t0 = clock64();
+    int rb = 0;
+    for (int i = 0; i < iters; ++i) {
+      const uint64_t bdesc = make_desc_nosw((mode ? r_base + (uint32_t)rb * bblk : b_base), (uint32_t)N * 16, 128);
+      if (leader) umma_bf16(tmem, adesc + (uint64_t)((i % 9) * 3), bdesc, idesc, 1u);
+      if (++rb == nring) rb = 0;
+    }
+    if (leader) umma_commit(&done);
+    mbar_wait(&done, 0);
+    long long t1 = clock64();
+    stop = 1;
+    if (leader && blockIdx.x == 0) cycles[0] = t1 - t0;
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
 int main() {
   long long* d; cudaMalloc(&d, 8);
   cudaFuncSetAttribute(mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -188,6 +258,29 @@ int main() {
           printf("%-10s %-6d %-6d %-8d %10.1f %12.1f\n", mode ? "sw128" : "nosw", N, shift, two + 1, cyc,
                  2.0 * 128 * N * 16 / cyc * 1.9e9 * 148 / 1e12);
         }
+  {
+    cudaFuncSetAttribute(mma_with_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    uint4* src; cudaMalloc(&src, (size_t)148 << 20); cudaMemset(src, 0, (size_t)148 << 20);
+    long long* d2; cudaMalloc(&d2, 16);
+    printf("\nMMA (M=128) with a concurrent bulk-copy stream into shared memory: N, chunk bytes x depth, mode (1 = B walks the ring)\n");
+    for (int N : {192, 256})
+     for (int a_lbo : {6240, 6272, 8192})
+      for (int chunk : {0, 18432})
+        for (int depth : {2, 6})
+          for (int mode : {0, 1}) {
+            if (chunk == 0 && (depth != 2 || mode)) continue;
+            const int it2 = 8192;
+            long long h[2] = {0, 0};
+            cudaMemset(d2, 0, 16);
+            for (int rep = 0; rep < 2; ++rep) {
+              mma_with_tma<<<148, 128, 200 * 1024>>>(N, it2, chunk, depth, mode, a_lbo, src, d2);
+              cudaError_t e = cudaDeviceSynchronize();
+              if (e != cudaSuccess) { printf("tma error %s\n", cudaGetErrorString(e)); return 1; }
+            }
+            cudaMemcpy(h, d2, 16, cudaMemcpyDeviceToHost);
+            printf("N=%d a_lbo=%d chunk=%5d depth=%d mode=%d  %.1f cyc/MMA   copy %.1f B/clk\n", N, a_lbo, chunk, depth, mode, (double)h[0] / it2, (double)h[1] / (double)h[0]);
+          }
+  }
   {
     cudaFuncSetAttribute(mma_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     float* probe; cudaMalloc(&probe, 64); cudaMemset(probe, 0, 64);
