@@ -198,6 +198,10 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly ONE JSON line: keep NCCL's "NCCL version ..." banner (printed to stdout when the image
+        # sets NCCL_DEBUG=VERSION) out of it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     B, K, Wm = args.clips, args.steps, args.warmup
