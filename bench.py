@@ -202,6 +202,7 @@ def main():
         # sets NCCL_DEBUG=VERSION) out of it
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     B, K, Wm = args.clips, args.steps, args.warmup
