@@ -5,6 +5,8 @@ Tolerances (BASELINE.json north_star): integer part / texel indices bit-exact; r
 """
 import math
 
+import os
+
 import pytest
 import torch
 
@@ -111,6 +113,93 @@ def test_texture_sample_parity(cuda_dev, N, H, W, S, Ctex, mask):
     assert torch.equal(texel, texel_r)
     assert (tex - tex_r).abs().max().item() <= 1e-4 * max(1.0, tex_r.abs().max().item())
     assert part[0, 1, 0].item() == 0 and part[0, 1, 1].item() == 3      # ties: lowest index wins
+
+
+
+def _conv_case(dev, kind, cin, cout, k, stride, pad, N, H, W, halo, epi, act, env=None):
+    """One conv through the C-ABI (pack -> plan -> conv) against torch.nn.functional on the 16-bit-rounded operands.
+    Returns (max abs err / max|ref|, statistics rel err, plan info)."""
+    import torch.nn.functional as F
+    from nhvr_b200 import ops, capi
+    old = {}
+    for kk, vv in (env or {}).items():
+        old[kk] = os.environ.get(kk)
+        os.environ[kk] = vv
+    try:
+        plan = ops.ConvPlan(kind, cin, cout, k, stride, pad, N, H, W, halo, epi, act)
+    finally:
+        for kk, vv in old.items():
+            if vv is None:
+                os.environ.pop(kk, None)
+            else:
+                os.environ[kk] = vv
+    g = torch.Generator(device="cpu").manual_seed(cin * 1000 + cout + k)
+    x = (torch.rand(N, cin, H, W, generator=g) * 2 - 1).to(dev)
+    transposed = kind == capi.CONV_TRANSPOSE
+    w = (torch.randn(*((cin, cout, k, k) if transposed else (cout, cin, k, k)), generator=g) * (1.0 / (cin * k * k) ** 0.5)).to(dev)
+    b = (torch.rand(cout, generator=g) - 0.5).to(dev)
+    rnd = (lambda t: t.half().float()) if capi.operand_dtype() == "f16" else (lambda t: t.bfloat16().float())
+    xin = ops.P8Buffer(plan.in_desc.copy(), dev)
+    ops.pack_nchw([x], xin)
+    plan.pack_weights(w)
+    xr, wr = rnd(x), rnd(w)
+    if transposed:
+        ref = F.conv_transpose2d(xr, wr, stride=2, padding=pad, output_padding=1 if k == 3 else 0)
+    else:
+        xp = F.pad(xr, (pad,) * 4, mode="reflect" if halo == capi.HALO_REFLECT else "constant")
+        ref = F.conv2d(xp, wr, stride=stride)
+    assert (plan.Ho, plan.Wo) == tuple(ref.shape[-2:])
+    stat_err = 0.0
+    if epi == capi.EPI_RAW_STATS:
+        raw = ops.P8Buffer(plan.raw_desc(), dev)
+        stats = torch.zeros(N * plan.Cout8 * 8 * 2, dtype=torch.float32, device=dev)
+        plan.forward(xin, raw.ptr, stats=stats)
+        out = ops.unpack_nchw(raw, cout)
+        st = stats.view(N, plan.Cout8 * 8, 2)[:, :cout].double()
+        s_ref = torch.stack([ref.double().sum((2, 3)), (ref.double() ** 2).sum((2, 3))], -1)
+        stat_err = ((st - s_ref).abs() / (1.0 + s_ref.abs())).max().item()
+    else:
+        out = torch.empty(N, cout, plan.Ho, plan.Wo, dtype=torch.float32, device=dev)
+        plan.forward(xin, out.data_ptr(), bias=b)
+        ref = ref + b.view(1, -1, 1, 1)
+        if act == capi.ACT_TANH:
+            ref = torch.tanh(ref)
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item() / max(1.0, ref.abs().max().item())
+    return err, stat_err, plan.info()
+
+
+@pytest.mark.parametrize("name,env,kind,cin,cout,k,stride,pad,N,H,W,halo,epi,act,expect", [
+    # CTA pairs (cta_group::2): odd tile count per image, two images, statistics epilogue
+    ("pair_192", None, "CONV", 192, 192, 3, 1, 1, 2, 35, 37, "R", "RAW_STATS", "NONE", dict(Npad=192)),
+    ("pair_forced_256", {"NHVR_CONV_PAIR": "1"}, "CONV", 64, 256, 3, 1, 1, 1, 20, 50, "R", "RAW_STATS", "NONE", dict(Npad=256)),
+    ("pair_s2_192", None, "CONV", 96, 192, 3, 2, 1, 1, 66, 70, "Z", "RAW_STATS", "NONE", dict(Npad=192)),
+    ("pair_off_192", {"NHVR_CONV_PAIR": "0"}, "CONV", 192, 192, 3, 1, 1, 1, 35, 37, "R", "RAW_STATS", "NONE", dict(Npad=192)),
+    # M replication, stacked rows (W multiple of 128) and consecutive positions (W = 100), fp32 head epilogue
+    ("mrep_stacked_7x7", None, "CONV", 16, 73, 7, 1, 3, 2, 224, 128, "R", "BIAS_ACT_F32", "NONE", dict(slab_min=1000)),
+    ("mrep_linear_3x3", None, "CONV", 32, 48, 3, 1, 1, 2, 200, 200, "R", "RAW_STATS", "NONE", dict(slab_min=900)),
+    ("mrep_s2", None, "CONV", 48, 96, 3, 2, 1, 3, 256, 256, "Z", "RAW_STATS", "NONE", dict(slab_min=1200)),
+    ("mrep_forced_3", {"NHVR_CONV_MREP": "3"}, "CONV", 16, 64, 3, 1, 1, 1, 31, 128, "R", "BIAS_ACT_F32", "TANH", None),
+    # transposed conv with the N split (4 accumulators x 64 columns), row mode head
+    ("convT_split", None, "CONV_TRANSPOSE", 64, 128, 3, 2, 1, 1, 24, 40, "Z", "RAW_STATS", "NONE", dict(nsplit=2)),
+    ("rowmode_head", None, "CONV", 48, 4, 7, 1, 3, 1, 40, 150, "R", "BIAS_ACT_F32", "TANH", dict(njobs=7)),
+])
+def test_conv_lowering_variants(cuda_dev, name, env, kind, cin, cout, k, stride, pad, N, H, W, halo, epi, act, expect):
+    """Every lowering of the shift-GEMM kernel (CTA pair / M replication / N split / row mode) at a size where the
+    plan builder really picks it, against torch on identically rounded operands: the only differences left are the
+    fp32 accumulation order and the 16-bit rounding of the RAW output (<= 2^-11 relative)."""
+    from nhvr_b200 import capi
+    err, stat_err, info = _conv_case(cuda_dev, getattr(capi, kind), cin, cout, k, stride, pad, N, H, W,
+                                     capi.HALO_REFLECT if halo == "R" else capi.HALO_ZERO, getattr(capi, "EPI_" + epi),
+                                     getattr(capi, "ACT_" + act), env)
+    for key, val in (expect or {}).items():
+        if key == "slab_min":
+            assert info["slab_units"] >= val, (name, info)
+        else:
+            assert info[key] == val, (name, info)
+    tol = 2e-3 if epi == "RAW_STATS" else 2e-4
+    assert err <= tol, (name, err, info)
+    assert stat_err <= 2e-3, (name, stat_err)
 
 
 def test_texture_sample_matches_numpy_loops(cuda_dev):
