@@ -290,7 +290,7 @@ def main():
                 if tj.get("clips") == B:
                     traffic, traffic_src = tj["mean_dram_bytes_per_launch"], tj["source"]
             roof = {"kernel": "conv_shiftgemm_kernel (tcgen05)", "bound": "tensor", "achieved": ach, "peak": peak,
-                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes of DRAM per launch (mean over the step's conv launches)",
+                    "unit": "TFLOP/s", "frac": ach / peak, "frac_of_burst_peak": ach / pk["bf16_tflops"], "traffic": traffic, "traffic_unit": "bytes of DRAM per launch (mean over the step's conv launches)",
                     "traffic_source": traffic_src, "peak_source": pk_src + ", sustained",
                     "launches_per_step": conv[2] // 3, "flops_per_step": conv[0] / 3,
                     "share_of_step": conv[1] / sum(v[1] for v in agg.values())}
