@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 #include <algorithm>
 
@@ -290,6 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
       const uint32_t a_lbo_u = (uint32_t)P.slab_units;            // plane stride, 16-B units
       const uint32_t b_lbo_u = PAIR ? (uint32_t)P.Npad >> 1 : (uint32_t)P.Npad;   // K-group stride = rows held by this CTA
       const uint32_t desc_hi = (128u >> 4) | (1u << 14);          // SBO = 128 B, version 1, no swizzle
+      const uint64_t dhi = (uint64_t)desc_hi << 32;
       const uint32_t a_lo0 = ((smem_u32(a_smem) & 0x3FFFFu) >> 4) | (a_lbo_u << 16);
       const uint32_t b_lo0 = ((smem_u32(b_smem) & 0x3FFFFu) >> 4) | (b_lbo_u << 16);
       const uint32_t a_stage_u = a_stage_bytes >> 4, b_block_u = b_block_bytes >> 4;
@@ -341,28 +343,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
         for (int s = 0; s < spc; ++s) {                       // load of entry i+1 overlaps the issue of MMA i
           const int nbst = (bst + 1 == SB) ? 0 : bst + 1;
           const uint32_t nbph = bph ^ ((bst + 1 == SB) ? 1u : 0u);
-#pragma unroll 1
-          for (int k = 0; k < bpb; ++k) {
+          // one table entry = one weight block: mrep MMAs.  Operand arithmetic stays outside the leader-guarded
+          // statements so that the guard compiles to a predicate on the UTCHMMA instead of a divergent branch.
+          auto issue = [&](auto multi) {
             ++e;
             const ConvMma nxt = *e;                           // one entry past the end is still inside ConvKParams
-            if (k == bpb - 1) {                               // pre-wait what the next stage needs
-              if (s + 1 < spc) wait_b(nbst, nbph);
-              else if (c + 1 < nchunks) { wait_a(nast, naph); wait_b(nbst, nbph); }
-            }
-            if (leader) {
-              const uint32_t acc_flag = keep_mask | ((cur.meta >> 16) ^ 1u);
-              uint32_t a_lo = a_st_lo + (uint32_t)cur.a_off, d_col = tmem_base + (cur.meta & 0xffffu);
-              if (PAIR) umma2_bf16(d_col, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc_flag);
-              else umma_bf16(d_col, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc_flag);
+            const uint32_t acc_flag = keep_mask | ((cur.meta >> 16) ^ 1u);
+            uint32_t a_lo = a_st_lo + (uint32_t)cur.a_off, d_col = tmem_base + (cur.meta & 0xffffu);
+            const uint64_t adesc = dhi | a_lo, bdesc = dhi | b_lo;
+            if (leader) { if (PAIR) umma2_bf16(d_col, adesc, bdesc, idesc, acc_flag); else umma_bf16(d_col, adesc, bdesc, idesc, acc_flag); }
+            if (decltype(multi)::value) {
               for (int i = 1; i < mrep; ++i) {               // the same weight block feeds the other M blocks
                 a_lo += a_mstride; d_col += acc_mstride;
-                if (PAIR) umma2_bf16(d_col, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc_flag);
-                else umma_bf16(d_col, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc_flag);
+                const uint64_t adesc_i = dhi | a_lo;
+                if (leader) { if (PAIR) umma2_bf16(d_col, adesc_i, bdesc, idesc, acc_flag); else umma_bf16(d_col, adesc_i, bdesc, idesc, acc_flag); }
               }
             }
             b_lo += b_block_u;
             cur = nxt;
+          };
+          if (mrep == 1) {
+#pragma unroll 1
+            for (int k = 0; k < bpb - 1; ++k) issue(std::false_type{});
+          } else {
+#pragma unroll 1
+            for (int k = 0; k < bpb - 1; ++k) issue(std::true_type{});
           }
+          // pre-wait what the next stage needs, then the last block of this stage
+          if (s + 1 < spc) wait_b(nbst, nbph);
+          else if (c + 1 < nchunks) { wait_a(nast, naph); wait_b(nbst, nbph); }
+          if (mrep == 1) issue(std::false_type{}); else issue(std::true_type{});
           if (leader) { if (PAIR) umma2_commit(&b_empty[bst]); else umma_commit(&b_empty[bst]); }
           bst = nbst; bph = nbph;
           if (bst == 0) b_lo = b_lo0;
