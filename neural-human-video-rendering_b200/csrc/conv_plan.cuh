@@ -53,7 +53,6 @@ struct ConvKParams {
   // mrep MMAs), `q_mstride` linear positions / `a_mstride` slab units apart.  xtiles > 0: the blocks are the same
   // 128-pixel row segment of mrep consecutive output rows ("stacked"); xtiles == 0: mrep*128 consecutive positions.
   int32_t mrep, a_mstride, q_mstride, xtiles, acc_mstride;
-  int32_t dephase_cycles;  // experiment: CTAs in the second slot of an SM (first wave) start their MMAs this much later
   int32_t pair;            // 1: launched as clusters of two CTAs running cta_group::2 MMAs (weights packed per CTA half)
   ConvRun runs[kMaxRuns];
   ConvMma mma[kMaxMma + 1];   // +1: the issue loop prefetches one entry ahead

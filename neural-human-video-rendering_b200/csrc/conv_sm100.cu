@@ -304,15 +304,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
       const bool leader = elect_one();
       // chunk -> weight stage -> MMA.  All ring bookkeeping sits at stage granularity (bpb divides the MMAs of a
       // chunk by construction); the innermost loop is: load table entry, two adds, tcgen05.mma.
-      if (P.dephase_cycles > 0) {       // experiment (NHVR_CONV_DEPHASE=<cycles>): break the lock-step of the two co-resident CTAs
-        const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-        unsigned nsm;
-        asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsm));
-        if (lin >= nsm && lin < 2 * nsm) {
-          const long long until = clock64() + P.dephase_cycles;
-          while (clock64() < until) {}
-        }
-      }
       long long wa = 0, wb = 0;
       const long long t_mma0 = trace ? clock64() : 0;
       // The barrier wait of the NEXT weight stage (and slab chunk) is issued before the LAST MMA of the current stage:
@@ -1026,7 +1017,6 @@ extern "C" int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const 
     return cudaLaunchKernelEx(&cfg, conv_shiftgemm_kernel<true>, K);
   };
   K.trace = nullptr;
-  { static const char* dp = std::getenv("NHVR_CONV_DEPHASE"); K.dephase_cycles = dp ? std::atoi(dp) : 0; }
   if (std::getenv("NHVR_CONV_TRACE")) {     // diagnostics: per-CTA cycle breakdown printed to stderr (synchronises)
     const size_t nct = (size_t)grid.x * grid.y * grid.z;
     cudaMalloc(&K.trace, nct * 64);
