@@ -184,6 +184,70 @@ __global__ void __launch_bounds__(256, 4) in_apply_kernel(const __grid_constant_
   }
 }
 
+// Row formulation: one warp per destination
+// row, lanes stride over the columns, four columns per lane in flight.  No division, the source row is resolved once per
+// row (mirror / zero halo rows), per unit only the column mirror remains.
+template <bool HAS_RES>
+__global__ void __launch_bounds__(256, 4) in_apply_rows_kernel(const __grid_constant__ ApplyParams P) {
+  const ActGeom& g = P.dg;
+  const int np = blockIdx.y;
+  const int n = np / g.C8, p = np - n * g.C8;
+  const float4* st4 = reinterpret_cast<const float4*>(P.stats + ((int64_t)n * g.C8 + p) * 16);
+  const float4 q0 = __ldg(st4), q1 = __ldg(st4 + 1), q2 = __ldg(st4 + 2), q3 = __ldg(st4 + 3);
+  const uint4* raw = P.raw + ((int64_t)n * P.rg.C8 + p) * P.rg.plane_units;
+  const uint4* res = HAS_RES ? P.res + ((int64_t)n * P.sg.C8 + p) * P.sg.plane_units : nullptr;
+  uint4* dst = P.dst + (int64_t)np * g.plane_units;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float scale[8], shift[8];
+  {
+    const float sv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float mean = sv[2 * e] * P.inv_hw;
+      const float var = fmaxf(sv[2 * e + 1] * P.inv_hw - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + P.eps);
+      scale[e] = rstd;
+      shift[e] = -mean * rstd;
+    }
+  }
+  const bool reflect = g.halo != NHVR_HALO_ZERO;
+  constexpr int COLS = 5;            // 160 columns per pass: the 130-wide (128^2) rows take one pass, 258 two, 518 four
+  const int Hq = g.Hp >> 1, Wq = g.Wp >> 1;
+  for (int yy = blockIdx.x * 8 + warp; yy < g.Hp; yy += gridDim.x * 8) {
+    int y = yy - g.pad_t;
+    bool row_ok = (y >= 0) & (y < g.H);
+    if (!row_ok && reflect) { y = reflect_idx(y, g.H); row_ok = (y >= 0) & (y < g.H); }
+    const uint4* rrow = raw + (int64_t)(y + P.rg.pad_t) * P.rg.Wp + P.rg.pad_l;
+    const uint4* srow = HAS_RES ? res + (int64_t)(y + P.sg.pad_t) * P.sg.Wp + P.sg.pad_l : nullptr;
+    // destination row: plain, or the two column-parity planes of the 4-way split format
+    const int64_t d_even = g.split ? ((int64_t)(((yy & 1) << 1) | 0) * Hq + (yy >> 1)) * Wq : (int64_t)yy * g.Wp;
+    const int64_t d_odd = g.split ? ((int64_t)(((yy & 1) << 1) | 1) * Hq + (yy >> 1)) * Wq : 0;
+    for (int xx0 = lane; xx0 < g.Wp; xx0 += 32 * COLS) {
+      ApplyItem it[COLS];
+#pragma unroll
+      for (int j = 0; j < COLS; ++j) {
+        const int xx = xx0 + 32 * j;
+        int x = xx - g.pad_l;
+        bool ok = row_ok && xx < g.Wp;
+        if (ok && ((x < 0) | (x >= g.W))) {
+          if (reflect) { x = reflect_idx(x, g.W); ok = (x >= 0) & (x < g.W); } else ok = false;
+        }
+        it[j].live = xx < g.Wp;
+        it[j].ok = ok;
+        it[j].du = g.split ? ((xx & 1) ? d_odd : d_even) + (xx >> 1) : d_even + xx;
+        it[j].r = make_uint4(0, 0, 0, 0);
+        it[j].s = make_uint4(0, 0, 0, 0);
+        if (ok) {
+          it[j].r = __ldg(rrow + x);
+          if (HAS_RES) it[j].s = __ldg(srow + x);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < COLS; ++j) apply_emit<HAS_RES>(P, scale, shift, dst, it[j]);
+    }
+  }
+}
+
 static inline int grid_x_for(int64_t work_items, int planes) {
   // ~4 waves of 148 SMs x 8 resident CTAs, split over the plane dimension
   const int64_t want = std::max<int64_t>(1, (int64_t)148 * 8 * 4 / std::max(1, planes));
@@ -271,7 +335,18 @@ extern "C" int nhvr_in_apply(const void* raw, const nhvr_act_desc* raw_desc, con
   if (gx > cap) gx = (int)cap;                                            // ... unless that is more than ~4 waves of CTAs
   if (const char* e = std::getenv("NHVR_APPLY_GX")) gx = std::max(1, std::atoi(e));
   dim3 grid(gx, planes);
-  if (P.res) in_apply_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  static const char* rows_env = std::getenv("NHVR_APPLY_ROWS");
+  const bool rows = !P.rg.split && !(residual && P.sg.split) && !(rows_env && std::atoi(rows_env) == 0);     // sources are never split today
+  if (rows) {
+    // 8 rows per block pass; ~4 passes per block, capped to a few waves of CTAs
+    // 8 rows per block pass: about four passes per block, but at least two waves of CTAs (few-plane layers), at most
+    // one pass per block
+    int gy = std::max((P.dg.Hp + 31) / 32, (2 * 148 * 8 + planes - 1) / std::max(1, planes));
+    gy = std::max(1, std::min(gy, (P.dg.Hp + 7) / 8));
+    dim3 grid_r(gy, planes);
+    if (P.res) in_apply_rows_kernel<true><<<grid_r, 256, 0, (cudaStream_t)stream>>>(P);
+    else in_apply_rows_kernel<false><<<grid_r, 256, 0, (cudaStream_t)stream>>>(P);
+  } else if (P.res) in_apply_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
   else in_apply_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
   count_launch();
   cudaError_t e = cudaGetLastError();
