@@ -338,11 +338,9 @@ extern "C" int nhvr_in_apply(const void* raw, const nhvr_act_desc* raw_desc, con
   static const char* rows_env = std::getenv("NHVR_APPLY_ROWS");
   const bool rows = !P.rg.split && !(residual && P.sg.split) && !(rows_env && std::atoi(rows_env) == 0);     // sources are never split today
   if (rows) {
-    // 8 rows per block pass; ~4 passes per block, capped to a few waves of CTAs
-    // 8 rows per block pass: about four passes per block, but at least two waves of CTAs (few-plane layers), at most
-    // one pass per block
-    int gy = std::max((P.dg.Hp + 31) / 32, (2 * 148 * 8 + planes - 1) / std::max(1, planes));
-    gy = std::max(1, std::min(gy, (P.dg.Hp + 7) / 8));
+    // one destination row per warp (8 per block): measured best of 3 / 5 / 9 / 13 / 17 / 33 / 65 row blocks per plane
+    int gy = std::max(1, (P.dg.Hp + 7) / 8);
+    { static const char* e = std::getenv("NHVR_APPLY_GY"); if (e && std::atoi(e) > 0) gy = std::min(std::atoi(e), gy); }
     dim3 grid_r(gy, planes);
     if (P.res) in_apply_rows_kernel<true><<<grid_r, 256, 0, (cudaStream_t)stream>>>(P);
     else in_apply_rows_kernel<false><<<grid_r, 256, 0, (cudaStream_t)stream>>>(P);
