@@ -515,6 +515,137 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const __grid_constant
   }
 }
 
+// Row formulation of both passes (PASS 0: the two reductions, PASS 1: apply): one warp per interior row y, the padded
+// rows that fold onto it are resolved once per row, lanes stride over x with kBwdCols columns in flight (primary dX tap,
+// raw and skip loads are issued before anything is consumed; the mirrored extra taps only exist on the border).
+constexpr int kBwdCols = 4;
+
+template <int PASS>
+__global__ void __launch_bounds__(256, 2) in_bwd_rows_kernel(const __grid_constant__ InBwdParams P) {
+  const int64_t np = blockIdx.y;
+  const int n = (int)(np / P.C8), p = (int)(np - (int64_t)n * P.C8);
+  const FoldGeom& f = P.f;
+  const ActGeom& g = P.gg;
+  float scale[8], shift[8], m1[8], m2[8];
+  fwd_norm_params(P, np, scale, shift);
+  if (PASS == 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { m1[e] = P.sums[np * 16 + 2 * e] * P.inv_hw; m2[e] = P.sums[np * 16 + 2 * e + 1] * P.inv_hw; }
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint4* dxp = P.dx + np * (int64_t)f.Hp * f.Wp;
+  const uint4* rawp = P.raw + np * (int64_t)f.H * f.W;
+  const uint4* skp = P.skip ? P.skip + np * (int64_t)f.H * f.W : nullptr;
+  uint4* gp = PASS == 1 ? P.g + ((int64_t)n * g.C8 + p) * g.plane_units : nullptr;
+  uint4* dyo = (PASS == 1 && P.dy_out) ? P.dy_out + np * (int64_t)f.H * f.W : nullptr;
+  const int Hq = g.Hp >> 1, Wq = g.Wp >> 1;
+  // PASS 0 walks the interior rows, PASS 1 every row of the gradient format (halo rows are written as zeros)
+  const int nrows = PASS == 1 ? g.Hp : f.H;
+  for (int rr = blockIdx.x * 8 + warp; rr < nrows; rr += gridDim.x * 8) {
+    const int y = PASS == 1 ? rr - g.pad_t : rr;
+    const bool row_in = (y >= 0) & (y < f.H);
+    // padded rows of dX that fold onto interior row y
+    int y0 = y + f.pad_t, y1 = -1;
+    if (row_in && f.reflect) {
+      if (y >= 1 && y <= f.pad_t) y1 = f.pad_t - y;
+      else { const int yb = 2 * (f.H - 1) - y + f.pad_t; if (y <= f.H - 2 && yb < f.Hp) y1 = yb; }
+    }
+    const uint4* d0 = dxp + (int64_t)y0 * f.Wp;
+    const uint4* d1 = dxp + (int64_t)(y1 < 0 ? 0 : y1) * f.Wp;
+    const uint4* rrow = rawp + (int64_t)y * f.W;
+    const uint4* srow = skp ? skp + (int64_t)y * f.W : nullptr;
+    int64_t o_even = 0, o_odd = 0;
+    if (PASS == 1) {
+      o_even = g.split ? ((int64_t)(((rr & 1) << 1) | 0) * Hq + (rr >> 1)) * Wq : (int64_t)rr * g.Wp;
+      o_odd = g.split ? ((int64_t)(((rr & 1) << 1) | 1) * Hq + (rr >> 1)) * Wq : 0;
+    }
+    const int ncols = PASS == 1 ? g.Wp : f.W;
+    for (int c0 = lane; c0 < ncols; c0 += 32 * kBwdCols) {
+      uint4 a[kBwdCols], r[kBwdCols], sk[kBwdCols];
+      int xs[kBwdCols], x1s[kBwdCols];
+      bool ok[kBwdCols], live[kBwdCols];
+#pragma unroll
+      for (int j = 0; j < kBwdCols; ++j) {
+        const int cc = c0 + 32 * j;
+        const int x = PASS == 1 ? cc - g.pad_l : cc;
+        live[j] = cc < ncols;
+        ok[j] = live[j] && row_in && x >= 0 && x < f.W;
+        xs[j] = x;
+        x1s[j] = -1;
+        a[j] = make_uint4(0, 0, 0, 0); r[j] = a[j]; sk[j] = a[j];
+        if (ok[j]) {
+          if (f.reflect) {
+            if (x >= 1 && x <= f.pad_l) x1s[j] = f.pad_l - x;
+            else { const int xb = 2 * (f.W - 1) - x + f.pad_l; if (x <= f.W - 2 && xb < f.Wp) x1s[j] = xb; }
+          }
+          a[j] = __ldg(d0 + x + f.pad_l);
+          r[j] = __ldg(rrow + x);
+          if (srow) sk[j] = __ldg(srow + x);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kBwdCols; ++j) {
+        if (!live[j]) continue;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (ok[j]) {
+          float dy[8], t[8], rv[8];
+          unpack8(a[j], dy, P.f16);
+          if (x1s[j] >= 0) { unpack8(__ldg(d0 + x1s[j]), t, P.f16);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dy[e] += t[e]; }
+          if (y1 >= 0) {
+            unpack8(__ldg(d1 + xs[j] + f.pad_l), t, P.f16);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dy[e] += t[e];
+            if (x1s[j] >= 0) { unpack8(__ldg(d1 + x1s[j]), t, P.f16);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) dy[e] += t[e]; }
+          }
+          if (srow) { unpack8(sk[j], t, P.f16);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dy[e] += t[e]; }
+          unpack8(r[j], rv, P.f16);
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float z = fmaf(rv[e], scale[e], shift[e]);
+            const float gz = dy[e] * act_grad(z, P.act);
+            if (PASS == 0) { s1[e] += gz; s2[e] += gz * z; }
+            else v[e] = scale[e] * (gz - m1[e] - z * m2[e]);
+          }
+          if (PASS == 1) {
+            o = pack8(v, P.f16);
+            if (dyo) dyo[(int64_t)y * f.W + xs[j]] = pack8(dy, P.f16);
+          }
+        }
+        if (PASS == 1) {
+          const int cc = c0 + 32 * j;
+          gp[g.split ? ((cc & 1) ? o_odd : o_even) + (cc >> 1) : o_even + cc] = o;
+        }
+      }
+    }
+  }
+  if (PASS == 0) {
+    __shared__ float sh[16][8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float a = s1[e], b = s2[e];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+      if (lane == 0) { sh[2 * e][warp] = a; sh[2 * e + 1][warp] = b; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+      atomicAdd(P.sums + np * 16 + threadIdx.x, t);
+    }
+  }
+}
+
 // backward of  x_next = pad(act(conv + bias))  (a layer WITHOUT normalisation, e.g. the discriminator's first):
 // g = dY * act'(y) with y read back from the stored activation; dbias[c] += sum g  (scaled like g)
 struct ActBwdExtra {
@@ -662,6 +793,15 @@ extern "C" int nhvr_in_bwd(const void* dx, int32_t dx_H, int32_t dx_W, int32_t p
   const int planes = P.N * P.C8;
   cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)planes * 16 * sizeof(float), s);
   if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
+  static const char* rows_env = std::getenv("NHVR_BWD_ROWS");
+  if (!(rows_env && std::atoi(rows_env) == 0)) {
+    // reduce: ~4 rows per warp (fewer atomics per plane), apply: one row per warp
+    in_bwd_rows_kernel<0><<<dim3(std::max(1, (P.f.H + 31) / 32), planes), 256, 0, s>>>(P);
+    NHVR_POST();
+    in_bwd_rows_kernel<1><<<dim3(std::max(1, (P.gg.Hp + 7) / 8), planes), 256, 0, s>>>(P);
+    NHVR_POST();
+    return NHVR_OK;
+  }
   in_bwd_reduce_kernel<<<dim3(grid_x_for((int64_t)P.f.H * P.f.W, planes), planes), 256, 0, s>>>(P);
   NHVR_POST();
   in_bwd_apply_kernel<<<dim3(grid_x_for((int64_t)P.gg.Hp * P.gg.Wp, planes), planes), 256, 0, s>>>(P);
