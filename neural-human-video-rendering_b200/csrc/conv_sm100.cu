@@ -776,7 +776,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   // M replication (profiles/r01_conv_ablation.md): a tile of mrep M blocks streams the layer's packed weights once
   // instead of once per 128 positions and amortises the per-CTA prologue.  Candidates keep two CTAs per SM
   // (<= 256 TMEM columns, <= 112 KB).
-  int mrep = 1, want_split = 1;
+  int mrep = 1;
   bool stacked = false;
   bool ok = false;
   const bool plain = (d->flags & 1) || rowmode || d->kind == NHVR_CONV_TRANSPOSE || std::getenv("NHVR_CONV_TUNE");
@@ -806,12 +806,12 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
         tile_n(m, ws);
         if (K.tmem_cols <= 256) ok = try_fit(kSmemTwoPerSm);
         else if (force_m) ok = try_fit(kSmemOnePerSm);
-        if (ok) { mrep = m; stacked = stk; want_split = ws; }
+        if (ok) { mrep = m; stacked = stk; }
       }
     }
   }
   if (!ok) {
-    mrep = 1; stacked = false; want_split = 1;
+    mrep = 1; stacked = false;
     st0 = build_geometry(1, false);
     if (st0 == NHVR_OK) st0 = layout_runs(1, false);
     if (st0 != NHVR_OK) { delete p; return st0; }
@@ -846,7 +846,6 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
     if (!ok) ok = try_fit(kSmemOnePerSm);
     if (!ok) { delete p; return NHVR_ERR_SMEM; }
   }
-  const int b_block = Npad * 32;
 
   // ---- jobs (grouped by accumulator so that "first" is well defined)
   std::vector<Tap> staps = taps;
@@ -895,7 +894,6 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   ActGeom gin = make_geom(in);
   K.in_plane_units = gin.plane_units;
   p->tiles_per_img = count_tiles(mrep, stacked);
-  (void)want_split;
 
   PackParams& PP = p->pp;
   PP.Cin = gemm_k; PP.Cout = gemm_n; PP.kh = d->kh; PP.kw = d->kw;

@@ -42,3 +42,10 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     rate = v[0] / (v[1] * 1e-3)
     print("%-12s n=%4d  %8.2f ms  %5.1f%%  %s" % (k, v[2], v[1], 100 * v[1] / tot, ("%.0f TFLOP/s" % (rate / 1e12)) if k in ("conv", "wgrad") else ("%.0f GB/s" % (rate / 1e9))))
 print("sum of bracketed launches: %.2f ms" % tot)
+if "--launches" in sys.argv:
+    for i, (kind, work, a, b) in enumerate(recs):
+        ms = a.elapsed_time(b)
+        if kind in ("conv", "wgrad"):
+            print("%3d %-8s %8.1f us  work=%.3e  %7.1f TFLOP/s" % (i, kind, ms * 1e3, work, work / ms / 1e9))
+        else:
+            print("%3d %-8s %8.1f us  work=%.3e  %7.1f GB/s" % (i, kind, ms * 1e3, work, work / ms / 1e6))
