@@ -15,7 +15,7 @@ there is no fallback: a CPU tensor or a missing library raises.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence
 
 import torch
 import torch.nn as nn

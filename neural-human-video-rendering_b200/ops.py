@@ -4,7 +4,7 @@ texture lookup, composite.  torch is used only to own device memory and to name 
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 

@@ -7,7 +7,6 @@ usage: python tools/torch_gpu_baseline.py [clips] [steps]     (prints one JSON l
 """
 import json
 import sys
-import time
 
 import torch
 import torch.nn as nn
