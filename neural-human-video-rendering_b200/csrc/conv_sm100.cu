@@ -794,6 +794,9 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
     if (force_m > 1) mmax = force_m;
     // reads of the last tile run past the image into the tail slack of the buffer
     while (mmax > 1 && (int64_t)(mmax - 1) * K.Wrow + 2 * kTileM > kActSlackUnits) --mmax;
+    // experiment: NHVR_CONV_PAIR=2 also pairs M-replicated layers (N >= 64): each CTA then reads A + B/2 per MMA
+    { const char* pe = std::getenv("NHVR_CONV_PAIR");
+      pair = (pe && std::atoi(pe) == 2 && nacc == 1 && Npad >= 64 && (Npad % 16) == 0) ? 1 : 0; }
     for (int m = mmax; m >= 2 && !ok; --m) {
       const int xt = (K.Wv + kTileM - 1) / kTileM;
       const bool prefer_stk = d->kind != NHVR_CONV_DGRAD_S1 && xt * kTileM * 10 <= K.Wv * 11;
@@ -811,6 +814,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
     }
   }
   if (!ok) {
+    pair = 0;
     mrep = 1; stacked = false;
     st0 = build_geometry(1, false);
     if (st0 == NHVR_OK) st0 = layout_runs(1, false);
