@@ -52,6 +52,10 @@ struct WgParams {
   int32_t S;                       // stages
   int32_t tmem_cols;
   int32_t f16;
+  // Tap folding (stride-1 convs with <= 16 input channels, the 7x7 stems): N-group j of the B descriptor is the SAME
+  // 8-channel plane shifted by j positions (SBO = 16 bytes, overlapping reads), so ONE MMA of N = 64 covers the kw
+  // filter columns of a filter row; taps[].tap = r * 16 + plane.
+  int32_t fold, kw;
   ConvRun xruns[kMaxRuns];
   ConvRun gruns[4];
   WgTap taps[kWgMaxTaps];
@@ -131,10 +135,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     // instruction descriptor: D f32, A/B 16-bit, BOTH MN-major (bits 15, 16), N = nci, M = 128
-    const uint32_t idesc = make_idesc_16(kTileM, (uint32_t)P.nci, P.f16) | (1u << 15) | (1u << 16);
+    const int Nf = P.fold ? 64 : P.nci;                      // accumulator columns per tap
+    const uint32_t idesc = make_idesc_16(kTileM, (uint32_t)Nf, P.f16) | (1u << 15) | (1u << 16);
     // MN-major un-swizzled descriptor: LBO = 128 B (next group of 8 positions along K), SBO = plane stride
     const uint32_t g_hi = (((uint32_t)P.gslab_units) & 0x3FFFu) | (1u << 14);
-    const uint32_t x_hi = (((uint32_t)P.xslab_units) & 0x3FFFu) | (1u << 14);
+    const uint32_t x_hi = ((P.fold ? 1u : (uint32_t)P.xslab_units) & 0x3FFFu) | (1u << 14);   // fold: next N group = next position
     const uint32_t lbo_field = (128u >> 4) << 16;
     const bool leader = elect_one();
     int st = 0;
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       const uint32_t x_lo0 = (((smem_u32(smem + (size_t)st * stage_bytes) + g_stage_bytes) & 0x3FFFFu) >> 4) | lbo_field;
       for (int t = 0; t < ntaps; ++t) {
         const WgTap tp = P.taps[tap0 + t];
-        const uint32_t d_tmem = tmem_base + (uint32_t)(t * P.nci);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(t * Nf);
 #pragma unroll
         for (int k = 0; k < kTileM / 16; ++k) {            // 16 positions (K) per MMA
           const uint64_t adesc = ((uint64_t)g_hi << 32) | (g_lo0 + (uint32_t)tp.g_off + (uint32_t)(k * 16));
@@ -171,6 +176,32 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     tc_fence_after();
     if (c_end > c_begin) {
       for (int t = 0; t < ntaps; ++t) {
+        if (P.fold) {
+          // columns n = s * 8 + c of fold tap (r, plane): workspace entry [tap r*kw+s][co][plane*8 + c]
+          const int code = P.taps[tap0 + t].tap, r = code >> 4, pl = code & 15;
+          for (int gcol = 0; gcol < 64; gcol += 16) {
+            uint32_t vr[16];
+            tmem_ld16(t_lane + (uint32_t)(t * 64 + gcol), vr);
+            tmem_ld_wait();
+            if (co < P.CoutP) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int sft = (gcol >> 3) + h;
+                if (sft < P.kw) {
+                  float* dst = P.ws + ((int64_t)(r * P.kw + sft) * P.CoutP + co) * P.CinP + pl * 8;
+#pragma unroll
+                  for (int i = 0; i < 8; i += 4) {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(__uint_as_float(vr[h * 8 + i])),
+                                 "f"(__uint_as_float(vr[h * 8 + i + 1])), "f"(__uint_as_float(vr[h * 8 + i + 2])),
+                                 "f"(__uint_as_float(vr[h * 8 + i + 3]))
+                                 : "memory");
+                  }
+                }
+              }
+            }
+          }
+          continue;
+        }
         float* dst = P.ws + ((int64_t)P.taps[tap0 + t].tap * P.CoutP + co) * P.CinP + ci_blk * P.nci;   // filter-tap order
         for (int gcol = 0; gcol < P.nci; gcol += 16) {
           uint32_t vr[16];
@@ -303,11 +334,40 @@ extern "C" int nhvr_wgrad_plan_create(const nhvr_conv_desc* fwd, nhvr_wgrad_plan
   W.C8x = xg.C8; W.C8g = gg.C8;
   W.CoutP = wg_round_up(fwd->Cout, kTileM);
   W.CinP = xg.C8 * 8;
+  W.fold = 0; W.kw = fwd->kw;
 
+  // ---- tap folding for narrow inputs (the 7x7 stems: 3 or 9 input channels).  The plain lowering issues kh*kw MMAs of
+  // N = 16 per 16 positions (issue-bound, 13-76 TFLOP/s measured) and needs several passes over the data because
+  // kh*kw accumulators do not fit TMEM; folded, a filter row is ONE MMA of N = 64 per input plane.
+  const int real_planes = (fwd->Cin + 7) / 8;
+  const bool fold = fwd->kind == NHVR_CONV && fwd->stride == 1 && real_planes <= 2 && fwd->kw >= 5 && fwd->kw <= 8 &&
+                    !(std::getenv("NHVR_WGRAD_FOLD") && std::atoi(std::getenv("NHVR_WGRAD_FOLD")) == 0);
+  int nci = 0, best_groups = 1, best_S = 1;
+  if (fold) {
+    // own X slab: one run per filter row, 8 extra positions for the shifted N groups (the 8th group is discarded)
+    const int run_len = kTileM + 8;
+    W.nxruns = fwd->kh;
+    for (int r = 0; r < fwd->kh; ++r) W.xruns[r] = ConvRun{r * K.Wrow, run_len, r * run_len};
+    W.xslab_units = fwd->kh * run_len;
+    W.ntaps_total = fwd->kh * real_planes;
+    const int g_off = W.taps[0].g_off;            // stride 1: a single G offset
+    for (int r = 0; r < fwd->kh; ++r)
+      for (int pl = 0; pl < real_planes; ++pl) {
+        WgTap& t = W.taps[r * real_planes + pl];
+        t.x_off = r * run_len + pl * W.xslab_units;
+        t.g_off = g_off;
+        t.tap = r * 16 + pl;
+      }
+    W.fold = 1;
+    nci = real_planes * 8;                        // X planes staged per CTA
+    best_groups = (W.ntaps_total * 64 + 511) / 512;
+    const size_t stage = (size_t)16 * gslab * 16 + (size_t)real_planes * W.xslab_units * 16;
+    best_S = (int)std::min<size_t>(4, (size_t)(210 * 1024) / stage);
+    if (best_S < 1) { nhvr_conv_plan_destroy(fp); delete p; return NHVR_ERR_SMEM; }
+  } else {
   // ---- N (input channels per CTA), tap groups (ntaps_grp * nci <= 512 TMEM columns) and pipeline depth.
   // Cost model per (chunk, all input channels): tensor time ~ ntaps * (CinP/nci) * 8 MMAs * cycles(nci), operand
   // staging ~ ngroups * (CinP/nci) * stage_bytes / ~24 B per cycle; a stage must fit at least twice.
-  int nci = 0, best_groups = 1, best_S = 1;
   double best_cost = 1e30;
   for (int cand : {64, 48, 32, 16}) {
     if (W.CinP % cand) continue;
@@ -323,13 +383,14 @@ extern "C" int nhvr_wgrad_plan_create(const nhvr_conv_desc* fwd, nhvr_wgrad_plan
     if (S < 2) cost *= 2.0;                     // no overlap of staging and MMAs
     if (cost < best_cost) { best_cost = cost; nci = cand; best_groups = ngroups; best_S = S; }
   }
+  }
   if (!nci) { nhvr_conv_plan_destroy(fp); delete p; return NHVR_ERR_SMEM; }
   W.nci = nci; W.nci8 = nci / 8;
   p->n_tap_groups = best_groups;
   W.ntaps_grp = (W.ntaps_total + best_groups - 1) / best_groups;        // balanced groups
-  int cols = 32; while (cols < W.ntaps_grp * nci) cols <<= 1;
+  int cols = 32; while (cols < W.ntaps_grp * (fold ? 64 : nci)) cols <<= 1;
   W.tmem_cols = cols;
-  W.n_ci_blocks = W.CinP / nci;
+  W.n_ci_blocks = fold ? 1 : W.CinP / nci;
   p->n_co_blocks = W.CoutP / kTileM;
 
   // ---- stages and K split: whole waves of 148 CTAs (one CTA per SM: TMEM / shared memory bound)
@@ -350,7 +411,7 @@ extern "C" int nhvr_wgrad_plan_create(const nhvr_conv_desc* fwd, nhvr_wgrad_plan
   }
   W.chunks_per_cta = (W.nchunks_total + best_split - 1) / best_split;
   p->nsplit_k = (W.nchunks_total + W.chunks_per_cta - 1) / W.chunks_per_cta;
-  p->ws_bytes = (size_t)W.ntaps_total * W.CoutP * W.CinP * sizeof(float);
+  p->ws_bytes = (size_t)(fold ? fwd->kh * fwd->kw : W.ntaps_total) * W.CoutP * W.CinP * sizeof(float);
   nhvr_conv_plan_destroy(fp);
   *out = p;
   return NHVR_OK;

@@ -170,6 +170,8 @@ int main(int argc, char** argv) {
       {"c3s1 32->48 w200", NHVR_CONV, 32, 48, 3, 1, 1, 2, 10, 200, Z},
       {"c3s1 192->192", NHVR_CONV, 192, 192, 3, 1, 1, 2, 24, 40, R},
       {"c7s1 6->48 stem", NHVR_CONV, 6, 48, 7, 1, 3, 1, 40, 72, R},
+      {"c7s1 9->48 stem 2 planes", NHVR_CONV, 9, 48, 7, 1, 3, 2, 33, 150, R},
+      {"c5s1 3->20 fold k5", NHVR_CONV, 3, 20, 5, 1, 2, 1, 30, 41, Z},
       {"c7s1 48->4 head", NHVR_CONV, 48, 4, 7, 1, 3, 1, 40, 72, R},
       {"c7s1 64->73 uvhead", NHVR_CONV, 64, 73, 7, 1, 3, 1, 24, 40, R},
       {"c3s2 48->96 down", NHVR_CONV, 48, 96, 3, 2, 1, 2, 32, 48, Z},
@@ -192,6 +194,9 @@ int main(int argc, char** argv) {
         {"PERF wgrad c7 64->73 256^2 b16", NHVR_CONV, 64, 73, 7, 1, 3, 16, 256, 256, R},
         {"PERF wgrad c3s2 64->128 256^2 b16", NHVR_CONV, 64, 128, 3, 2, 1, 16, 256, 256, Z},
         {"PERF wgrad ct 128->64 128^2 b16", NHVR_CONV_TRANSPOSE, 128, 64, 3, 2, 1, 16, 128, 128, Z},
+        {"PERF wgrad c7 3->64 512^2 b8 (stem)", NHVR_CONV, 3, 64, 7, 1, 3, 8, 512, 512, R},
+        {"PERF wgrad c7 9->48 512^2 b8 (stem)", NHVR_CONV, 9, 48, 7, 1, 3, 8, 512, 512, R},
+        {"PERF wgrad c7 48->4 512^2 b8 (head)", NHVR_CONV, 48, 4, 7, 1, 3, 8, 512, 512, R},
     };
     int pi = 100;
     for (auto& c : perf) {
