@@ -72,7 +72,11 @@ typedef struct nhvr_conv_desc {
   int32_t in_extra_rows; /* extra zero rows below the input's bottom halo (gradient buffers shared with wgrad) */
   int32_t in_extra_cols; /* extra zero columns right of the input's right halo (same purpose)                 */
   int32_t out_h, out_w;  /* NHVR_CONV_TRANSPOSE only: output size override (0 = 2H x 2W for k3, 2H-2 for k4)  */
-  int32_t flags;         /* bit 0: never use the row-mode lowering (wide kernels with few output channels)    */
+  int32_t flags;         /* bit 0: never use the row-mode lowering (wide kernels with few output channels)
+                            bit 2: the input may use the single-plane tap-paired format (Cin <= 8 stride-1 convs:
+                                   K group 1 of every MMA is the same plane one pixel to the right, so an MMA covers
+                                   two filter columns).  Changes nhvr_conv_input_desc (C8 = 1): set it only when
+                                   nothing else (e.g. a wgrad plan) reads the same input buffer                   */
 } nhvr_conv_desc;
 
 typedef struct nhvr_conv_plan nhvr_conv_plan;   /* opaque, host memory only */

@@ -53,6 +53,7 @@ struct ConvKParams {
   // mrep MMAs), `q_mstride` linear positions / `a_mstride` slab units apart.  xtiles > 0: the blocks are the same
   // 128-pixel row segment of mrep consecutive output rows ("stacked"); xtiles == 0: mrep*128 consecutive positions.
   int32_t mrep, a_mstride, q_mstride, xtiles, acc_mstride;
+  int32_t a_lbo_units;     // K-group stride of the A descriptor: the slab plane stride, or 1 (tap pairing: next pixel)
   int32_t pair;            // 1: launched as clusters of two CTAs running cta_group::2 MMAs (weights packed per CTA half)
   ConvRun runs[kMaxRuns];
   ConvMma mma[kMaxMma + 1];   // +1: the issue loop prefetches one entry ahead
@@ -71,6 +72,7 @@ struct PackParams {
   int32_t f16;
   int32_t flip;                // dgrad of a stride-1 conv: taps mirrored (r,s) -> (kh-1-r, kw-1-s)
   int32_t rowmode, Cp;         // row mode: job_tap = r*8 + accumulator, column n = s*Cp + co
+  int32_t kfold;               // tap pairing: K group kp of a block = filter column job_tap%kw + kp, channels 0..7
   int32_t pair, bpb;           // CTA-pair layout: [stage of bpb blocks][rank][bpb][2][Npad/2][8]
   int16_t job_tap[kMaxJobs];   // r*kw + s of each job
 };

@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
     // descriptors are advanced incrementally in 16-byte units, ring positions by counters (no div/mod).
     {
       const uint32_t idesc = make_idesc_16(PAIR ? 2 * kTileM : kTileM, (uint32_t)P.Npad, P.f16);
-      const uint32_t a_lbo_u = (uint32_t)P.slab_units;            // plane stride, 16-B units
+      const uint32_t a_lbo_u = (uint32_t)P.a_lbo_units;           // K-group stride: plane stride (or 1: tap pairing)
       const uint32_t b_lbo_u = PAIR ? (uint32_t)P.Npad >> 1 : (uint32_t)P.Npad;   // K-group stride = rows held by this CTA
       const uint32_t desc_hi = (128u >> 4) | (1u << 14);          // SBO = 128 B, version 1, no swizzle
       const uint64_t dhi = (uint64_t)desc_hi << 32;
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
 // consumption order (chunk, job, k-step); see header comment.
 __global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
   const int64_t total = (int64_t)P.nsplit * P.nblocks_padded * 2 * P.Npad;
-  const int qsteps = P.kcp >> 1;
+  const int qsteps = P.kfold ? 1 : P.kcp >> 1;
   const int nblocks = P.nchunks * P.njobs * qsteps;
   for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (int64_t)gridDim.x * blockDim.x) {
     const int nrow = (int)(u % P.Npad);
@@ -502,10 +502,14 @@ __global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
         co = (sfl < P.kw) ? (ncol - sfl * P.Cp) : P.Cout;       // columns beyond kw*Cp are padding
         tap = r * P.kw + min(sfl, P.kw - 1);
       }
+      if (P.kfold) {                         // K group kp = the next filter column of the same 8-channel plane
+        if (P.job_tap[j] % P.kw + kp >= P.kw) co = P.Cout;
+        else tap += kp;
+      }
       float vals[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const int ci = (c * P.kcp + 2 * qq + kp) * 8 + e;
+        const int ci = P.kfold ? e : (c * P.kcp + 2 * qq + kp) * 8 + e;
         float val = 0.f;
         if (ci < P.Cin && co < P.Cout) {
           const int64_t idx = P.transposed ? (((int64_t)ci * P.Cout + co) * (P.kh * P.kw) + tap)
@@ -550,7 +554,19 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   ConvKParams& K = p->kp;
   int gemm_k = d->Cin, gemm_n = d->Cout;          // dgrad swaps them
   if (d->kind == NHVR_CONV_DGRAD_S1) { gemm_k = d->Cout; gemm_n = d->Cin; }
-  const int C8 = round_up((gemm_k + 7) / 8, 2);   // K = 16 per MMA -> an even number of planes
+  int C8 = round_up((gemm_k + 7) / 8, 2);   // K = 16 per MMA -> an even number of planes
+  // Tap pairing (flag bit 2, <= 8 input channels, e.g. the 3-channel pose stem): ONE plane; K group 1 of every MMA is the
+  // same plane one pixel to the right (LBO = 16 bytes), so an MMA covers two filter columns: kh*ceil(kw/2) MMAs instead
+  // of kh*kw on half the slab bytes.
+  bool kfold = false;
+  {
+    const int Cp_row = d->Cout <= 8 ? 8 : round_up(d->Cout, 16);
+    const bool row_ok = !(d->flags & 1) && d->kw >= 5 && d->kw <= 8 && d->kw * Cp_row <= 128 && !std::getenv("NHVR_NO_ROWMODE") &&
+                        d->epilogue != NHVR_EPI_BIAS_ACT_P8;
+    kfold = (d->flags & 4) && !(d->flags & 1) && d->kind == NHVR_CONV && d->stride == 1 && d->Cin <= 8 && d->kw >= 2 && !row_ok &&
+            !(std::getenv("NHVR_CONV_KFOLD") && std::atoi(std::getenv("NHVR_CONV_KFOLD")) == 0);
+    if (kfold) C8 = 1;
+  }
   K.C8in = C8;
   nhvr_act_desc& in = p->in_desc;
   in.N = d->N; in.C8 = C8; in.H = d->H; in.W = d->W; in.halo = d->halo; in.split = 0;
@@ -598,9 +614,9 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
         K.rowmode = 1; K.Cp = Cp_row; K.kw = d->kw;
         K.tile_step = kTileM - (d->kw - 1);
       } else {
-        for (int r = 0; r < d->kh + xrows; ++r) run_specs.push_back({r * Wp, L + d->kw - 1});
+        for (int r = 0; r < d->kh + xrows; ++r) run_specs.push_back({r * Wp, L + d->kw - 1 + (kfold ? 1 : 0)});
         for (int r = 0; r < d->kh; ++r)
-          for (int s = 0; s < d->kw; ++s) taps.push_back({r, s, 0, r * d->kw + s});
+          for (int s = 0; s < d->kw; s += (kfold ? 2 : 1)) taps.push_back({r, s, 0, r * d->kw + s});
       }
       K.Wrow = Wp; K.Hv = Ho; K.Wv = Wo; K.oys = K.oxs = 1;
     } else if (d->kind == NHVR_CONV_DGRAD_S1) {
@@ -746,11 +762,11 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   auto try_fit = [&](long limit) -> bool {
     const int b_block = Npad * 32;
     long best_score = -1;
-    for (int cand = 8; cand >= 2; cand -= 2) {
+    for (int cand = kfold ? 1 : 8; cand >= (kfold ? 1 : 2); cand -= 2) {
       if (C8 % cand) continue;
       const int nch = C8 / cand;
       const int sa = std::min(2, nch);
-      const int bpc = (int)taps.size() * cand / 2;          // MMA blocks per chunk
+      const int bpc = kfold ? (int)taps.size() : (int)taps.size() * cand / 2;          // MMA blocks per chunk
       if (bpc > kMaxMma) continue;
       for (int dv = 8; dv >= 1; --dv) {                      // blocks per B stage: a divisor of bpc, stage <= 24 KB
         if (bpc % dv || (long)dv * b_block > (pair ? 49152 : 24576)) continue;
@@ -879,14 +895,16 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   K.kcp = kcp; K.SA = SA; K.bpb = bpb; K.SB = SB;
   K.pair = pair;
   K.nchunks = C8 / kcp;
-  K.mmas_per_chunk = K.njobs * (kcp / 2);
+  const int ksteps = kfold ? 1 : kcp / 2;
+  K.mmas_per_chunk = K.njobs * ksteps;
+  K.a_lbo_units = kfold ? 1 : slab;
   K.stages_per_chunk = K.mmas_per_chunk / bpb;           // bpb divides mmas_per_chunk by construction
   K.nblocks = K.nchunks * K.mmas_per_chunk;
   K.nbstages = K.nchunks * K.stages_per_chunk;
   const int nblocks_padded = K.nblocks;
   for (int j = 0; j < K.njobs; ++j)
-    for (int q = 0; q < kcp / 2; ++q) {
-      ConvMma& m = K.mma[j * (kcp / 2) + q];
+    for (int q = 0; q < ksteps; ++q) {
+      ConvMma& m = K.mma[j * ksteps + q];
       m.a_off = jobs[j].a_off + 2 * q * slab;
       m.meta = (uint32_t)(jobs[j].acc * Npad) | ((jobs[j].first && q == 0) ? 0x10000u : 0u);
     }
@@ -909,6 +927,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   PP.kcp = kcp; PP.nchunks = K.nchunks; PP.njobs = K.njobs; PP.Npad = Npad; PP.nsplit = nsplit;
   PP.nblocks_padded = nblocks_padded;
   PP.pair = pair; PP.bpb = bpb;
+  PP.kfold = kfold ? 1 : 0;
   *out = p;
   return NHVR_OK;
 }

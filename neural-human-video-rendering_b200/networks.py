@@ -89,7 +89,7 @@ class _ChainEngine:
             else:
                 epi, act = capi.EPI_BIAS_ACT_P8, L["act"]        # conv + bias + activation, no norm (D layer 0)
             plan = ops.ConvPlan(capi.CONV_TRANSPOSE if p.transposed else capi.CONV, p.cin, p.cout, p.k, p.stride, p.pad,
-                                N, h, w, L["halo"], epi, act)
+                                N, h, w, L["halo"], epi, act, allow_tap_pairing=not train)
             self.plans.append(plan)
             h, w = plan.Ho, plan.Wo
         self.out = torch.empty(N, out_channels, h, w, dtype=torch.float32, device=device)

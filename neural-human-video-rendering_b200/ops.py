@@ -94,8 +94,11 @@ class ConvPlan:
     """One conv layer lowered to the tcgen05 shift-GEMM kernel (nhvr_conv_plan_*)."""
 
     def __init__(self, kind, Cin, Cout, k, stride, pad, N, H, W, halo, epilogue, act=capi.ACT_NONE, in_extra_rows=0,
-                 in_extra_cols=0, out_hw=(0, 0)):
+                 in_extra_cols=0, out_hw=(0, 0), allow_tap_pairing: bool = False):
+        """allow_tap_pairing: flag bit 2 of nhvr_conv_desc - the input may use the single-plane tap-paired format
+        (only when no wgrad plan reads the same input buffer, i.e. inference engines)."""
         d = ConvDesc()
+        d.flags = 4 if allow_tap_pairing else 0
         d.in_extra_rows, d.in_extra_cols = in_extra_rows, in_extra_cols
         d.out_h, d.out_w = out_hw
         d.kind, d.Cin, d.Cout, d.kh, d.kw, d.stride, d.pad = kind, Cin, Cout, k, k, stride, pad

@@ -116,7 +116,7 @@ def test_texture_sample_parity(cuda_dev, N, H, W, S, Ctex, mask):
 
 
 
-def _conv_case(dev, kind, cin, cout, k, stride, pad, N, H, W, halo, epi, act, env=None):
+def _conv_case(dev, kind, cin, cout, k, stride, pad, N, H, W, halo, epi, act, env=None, tap_pairing=False):
     """One conv through the C-ABI (pack -> plan -> conv) against torch.nn.functional on the 16-bit-rounded operands.
     Returns (max abs err / max|ref|, statistics rel err, plan info)."""
     import torch.nn.functional as F
@@ -126,7 +126,7 @@ def _conv_case(dev, kind, cin, cout, k, stride, pad, N, H, W, halo, epi, act, en
         old[kk] = os.environ.get(kk)
         os.environ[kk] = vv
     try:
-        plan = ops.ConvPlan(kind, cin, cout, k, stride, pad, N, H, W, halo, epi, act)
+        plan = ops.ConvPlan(kind, cin, cout, k, stride, pad, N, H, W, halo, epi, act, allow_tap_pairing=tap_pairing)
     finally:
         for kk, vv in old.items():
             if vv is None:
@@ -200,6 +200,26 @@ def test_conv_lowering_variants(cuda_dev, name, env, kind, cin, cout, k, stride,
     tol = 2e-3 if epi == "RAW_STATS" else 2e-4
     assert err <= tol, (name, err, info)
     assert stat_err <= 2e-3, (name, stat_err)
+
+
+
+@pytest.mark.parametrize("cin,cout,k,pad,N,H,W,halo,epi", [
+    (3, 64, 7, 3, 2, 224, 128, "R", "RAW_STATS"),        # the pose stem: odd kw (the 8th column is a zero weight), M-replicated
+    (3, 64, 7, 3, 1, 40, 72, "R", "RAW_STATS"),          # same, small: one M block
+    (6, 24, 4, 2, 1, 33, 41, "Z", "BIAS_ACT_F32"),       # even kw, zero padding
+    (8, 16, 3, 1, 2, 20, 150, "R", "RAW_STATS"),         # all eight channel slots used
+])
+def test_conv_tap_pairing(cuda_dev, cin, cout, k, pad, N, H, W, halo, epi):
+    """Single-plane tap-paired input format of the narrow-input stems (K group 1 = the next pixel): same result as
+    the two-plane lowering, against torch on identically rounded operands."""
+    from nhvr_b200 import capi
+    args = (cuda_dev, capi.CONV, cin, cout, k, 1, pad, N, H, W, capi.HALO_REFLECT if halo == "R" else capi.HALO_ZERO,
+            getattr(capi, "EPI_" + epi), capi.ACT_NONE)
+    err, stat_err, info = _conv_case(*args, tap_pairing=True)
+    assert info["kcp"] == 1 and info["njobs"] == k * ((k + 1) // 2), info
+    assert err <= (2e-3 if epi == "RAW_STATS" else 2e-4) and stat_err <= 2e-3, (err, stat_err, info)
+    err2, _, info2 = _conv_case(*args, tap_pairing=False)
+    assert info2["kcp"] == 2 and err2 <= (2e-3 if epi == "RAW_STATS" else 2e-4)
 
 
 def test_texture_sample_matches_numpy_loops(cuda_dev):
