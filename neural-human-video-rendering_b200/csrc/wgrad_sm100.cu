@@ -56,6 +56,9 @@ struct WgParams {
   // 8-channel plane shifted by j positions (SBO = 16 bytes, overlapping reads), so ONE MMA of N = 64 covers the kw
   // filter columns of a filter row; taps[].tap = r * 16 + plane.
   int32_t fold, kw;
+  // Row folding on the M side (<= 8 output channels, the RGB+mask head): M group j of A is gradient plane 0 shifted UP
+  // by j rows (a separate bulk copy per group), so ONE MMA per X plane covers all kh x kw taps: D[(r,co)][(s,ci)].
+  int32_t mfold, kh, g_row_units;
   ConvRun xruns[kMaxRuns];
   ConvRun gruns[4];
   WgTap taps[kWgMaxTaps];
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 
   const int c_begin = split * P.chunks_per_cta;
   const int c_end = min(c_begin + P.chunks_per_cta, P.nchunks_total);
-  const int g_planes = min(16, P.C8g - co_blk * 16);      // planes that exist; the rest of the slab stays stale
+  const int g_planes = P.mfold ? P.kh : min(16, P.C8g - co_blk * 16);      // planes that exist; the rest of the slab stays stale
                                                            // (rows of D that are never written out)
   if (warp == 0 || warp == 2 || warp == 3) {
     // ------------------------------------------------------------------ producers: G and X slabs of a chunk
@@ -120,7 +123,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         const uint4* ximg = P.x + ((int64_t)n * P.C8x + ci_blk * P.nci8) * P.x_plane_units + q0;
         for (int i = pid; i < ncopy_g; i += 3) {
           const int pl = i / P.ngruns, r = i - pl * P.ngruns;
-          bulk_g2s(gdst + ((size_t)pl * P.gslab_units + P.gruns[r].s_off) * 16, gimg + (int64_t)pl * P.g_plane_units + P.gruns[r].g_off,
+          const int64_t poff = P.mfold ? -(int64_t)pl * P.g_row_units : (int64_t)pl * P.g_plane_units;
+          bulk_g2s(gdst + ((size_t)pl * P.gslab_units + P.gruns[r].s_off) * 16, gimg + poff + P.gruns[r].g_off,
                    (uint32_t)P.gruns[r].len * 16u, &full[st]);
         }
         for (int i = pid; i < ncopy_x; i += 3) {
@@ -178,12 +182,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       for (int t = 0; t < ntaps; ++t) {
         if (P.fold) {
           // columns n = s * 8 + c of fold tap (r, plane): workspace entry [tap r*kw+s][co][plane*8 + c]
-          const int code = P.taps[tap0 + t].tap, r = code >> 4, pl = code & 15;
+          const int code = P.taps[tap0 + t].tap, pl = code & 15;
+          const int r = P.mfold ? (m >> 3) : (code >> 4);                 // mfold: D row m = r * 8 + co
+          const int co = P.mfold ? (m & 7) : co_blk * kTileM + m;
+          const bool row_ok = !P.mfold || r < P.kh;          // (the TMEM loads below are warp-collective: no early exit)
           for (int gcol = 0; gcol < 64; gcol += 16) {
             uint32_t vr[16];
             tmem_ld16(t_lane + (uint32_t)(t * 64 + gcol), vr);
             tmem_ld_wait();
-            if (co < P.CoutP) {
+            if (co < P.CoutP && row_ok) {
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const int sft = (gcol >> 3) + h;
@@ -283,8 +290,12 @@ extern "C" int nhvr_wgrad_plan_create(const nhvr_conv_desc* fwd, nhvr_wgrad_plan
   // K runs over 128-position tiles: the round-up of the last tile must read ZERO gradient, so every (parity)
   // plane of the gradient buffer carries `extra` additional zero rows below the dgrad conv's own bottom halo
   const int extra = (kTileM - 1 + K.Wrow - 1) / K.Wrow;
+  // row folding on the M side (see WgParams::mfold): the position loop runs kh-1 rows further, so the gradient buffer
+  // carries kh-1 more zero rows at the bottom (the dgrad plan accepts the taller descriptor)
+  const bool mfold = fwd->kind == NHVR_CONV && fwd->stride == 1 && fwd->Cout <= 8 && fwd->Cin <= 64 && fwd->kh <= 16 &&
+                     fwd->kw >= 2 && fwd->kw <= 8 && !(std::getenv("NHVR_WGRAD_FOLD") && std::atoi(std::getenv("NHVR_WGRAD_FOLD")) == 0);
   if (fwd->kind == NHVR_CONV && fwd->stride == 1) {
-    g.pad_t = fwd->kh - 1; g.pad_b = fwd->kh - 1 + extra; g.pad_l = fwd->kw - 1; g.pad_r = 0;
+    g.pad_t = fwd->kh - 1; g.pad_b = fwd->kh - 1 + extra + (mfold ? fwd->kh - 1 : 0); g.pad_l = fwd->kw - 1; g.pad_r = 0;
     const int pitch = fp->Wo + fwd->kw - 1;
     if (pitch != K.Wrow) { nhvr_conv_plan_destroy(fp); delete p; return NHVR_ERR_SHAPE; }
     g_off_of_acc[0] = (fwd->kh - 1) * pitch + (fwd->kw - 1);
@@ -343,7 +354,29 @@ extern "C" int nhvr_wgrad_plan_create(const nhvr_conv_desc* fwd, nhvr_wgrad_plan
   const bool fold = fwd->kind == NHVR_CONV && fwd->stride == 1 && real_planes <= 2 && fwd->kw >= 5 && fwd->kw <= 8 &&
                     !(std::getenv("NHVR_WGRAD_FOLD") && std::atoi(std::getenv("NHVR_WGRAD_FOLD")) == 0);
   int nci = 0, best_groups = 1, best_S = 1;
-  if (fold) {
+  W.mfold = 0; W.kh = fwd->kh; W.g_row_units = K.Wrow;
+  if (mfold) {
+    // A: kh row-shifted copies of gradient plane 0 (one 128-position run each); B: X row 0 with the kw column shifts folded
+    // into N (as below); one accumulator of 64 columns per X plane.  The position loop runs kh-1 rows past the last valid
+    // one (G shifted up by r rows pairs X row y with G row y - r), which the gradient buffer covers with kh-1 more zero rows.
+    const int run_len = kTileM + 8;
+    W.nxruns = 1;
+    W.xruns[0] = ConvRun{0, run_len, 0};
+    W.xslab_units = run_len;
+    W.ngruns = 1;
+    W.gruns[0] = ConvRun{g_off_of_acc[0], kTileM, 0};
+    W.gslab_units = kTileM;
+    W.ntaps_total = real_planes;
+    for (int pl = 0; pl < real_planes; ++pl) {
+      WgTap& t = W.taps[pl];
+      t.x_off = pl * W.xslab_units; t.g_off = 0; t.tap = pl;
+    }
+    W.fold = 1; W.mfold = 1;
+    nci = real_planes * 8;
+    best_groups = 1;
+    const size_t stage = (size_t)16 * W.gslab_units * 16 + (size_t)real_planes * W.xslab_units * 16;
+    best_S = (int)std::min<size_t>(4, (size_t)(210 * 1024) / stage);
+  } else if (fold) {
     // own X slab: one run per filter row, 8 extra positions for the shifted N groups (the 8th group is discarded)
     const int run_len = kTileM + 8;
     W.nxruns = fwd->kh;
@@ -388,9 +421,9 @@ extern "C" int nhvr_wgrad_plan_create(const nhvr_conv_desc* fwd, nhvr_wgrad_plan
   W.nci = nci; W.nci8 = nci / 8;
   p->n_tap_groups = best_groups;
   W.ntaps_grp = (W.ntaps_total + best_groups - 1) / best_groups;        // balanced groups
-  int cols = 32; while (cols < W.ntaps_grp * (fold ? 64 : nci)) cols <<= 1;
+  int cols = 32; while (cols < W.ntaps_grp * (W.fold ? 64 : nci)) cols <<= 1;
   W.tmem_cols = cols;
-  W.n_ci_blocks = fold ? 1 : W.CinP / nci;
+  W.n_ci_blocks = W.fold ? 1 : W.CinP / nci;
   p->n_co_blocks = W.CoutP / kTileM;
 
   // ---- stages and K split: whole waves of 148 CTAs (one CTA per SM: TMEM / shared memory bound)
@@ -398,7 +431,11 @@ extern "C" int nhvr_wgrad_plan_create(const nhvr_conv_desc* fwd, nhvr_wgrad_plan
   W.S = best_S;
   p->smem_bytes = best_S * stage + (2 * best_S + 1) * 8 + 16 + 128;
   W.tiles_per_img = fp->tiles_per_img;
-  W.nchunks_total = fp->tiles_per_img * fwd->N;
+  if (W.mfold) {
+    const int64_t last_q = (int64_t)(K.Hv - 1) * K.Wrow + K.Wv + (int64_t)(fwd->kh - 1) * K.Wrow;
+    W.tiles_per_img = (int)((last_q + kTileM - 1) / kTileM);
+  }
+  W.nchunks_total = W.tiles_per_img * fwd->N;
   const int ctas_other = p->n_co_blocks * W.n_ci_blocks * p->n_tap_groups;
   int best_split = 1;
   double best_t = 1e30;
@@ -411,7 +448,7 @@ extern "C" int nhvr_wgrad_plan_create(const nhvr_conv_desc* fwd, nhvr_wgrad_plan
   }
   W.chunks_per_cta = (W.nchunks_total + best_split - 1) / best_split;
   p->nsplit_k = (W.nchunks_total + W.chunks_per_cta - 1) / W.chunks_per_cta;
-  p->ws_bytes = (size_t)(fold ? fwd->kh * fwd->kw : W.ntaps_total) * W.CoutP * W.CinP * sizeof(float);
+  p->ws_bytes = (size_t)(W.fold ? fwd->kh * fwd->kw : W.ntaps_total) * W.CoutP * W.CinP * sizeof(float);
   nhvr_conv_plan_destroy(fp);
   *out = p;
   return NHVR_OK;
