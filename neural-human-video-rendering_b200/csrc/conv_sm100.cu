@@ -99,8 +99,9 @@ NHVR_DEVINL void emit16(const ConvKParams& P, const float (&v)[16], int c0, bool
       lo.z = pack2(v[4], v[5], P.f16);  lo.w = pack2(v[6], v[7], P.f16);
       hi.x = pack2(v[8], v[9], P.f16);  hi.y = pack2(v[10], v[11], P.f16);
       hi.z = pack2(v[12], v[13], P.f16); hi.w = pack2(v[14], v[15], P.f16);
-      if ((c0 >> 3) < P.Cout8) o[u0] = lo;
-      if ((c0 >> 3) + 1 < P.Cout8) o[u0 + pstride] = hi;
+      const uint64_t keep = l2_policy_evict_last();      // read back once by the IN-apply / gradient pass that follows
+      if ((c0 >> 3) < P.Cout8) st_hint(o + u0, lo, keep);
+      if ((c0 >> 3) + 1 < P.Cout8) st_hint(o + u0 + pstride, hi, keep);
     }
     if (P.epilogue == NHVR_EPI_RAW_STATS && !(P.debug & 16)) {
       float s[16], ss[16];

@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(256, 4) in_apply_rows_kernel(const __grid_cons
     }
   }
   const bool reflect = g.halo != NHVR_HALO_ZERO;
+  const uint64_t once = l2_policy_evict_first();      // the raw tensor is dead after this pass
   constexpr int COLS = 5;            // 160 columns per pass: the 130-wide (128^2) rows take one pass, 258 two, 518 four
   const int Hq = g.Hp >> 1, Wq = g.Wp >> 1;
   for (int yy = blockIdx.x * 8 + warp; yy < g.Hp; yy += gridDim.x * 8) {
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(256, 4) in_apply_rows_kernel(const __grid_cons
         it[j].r = make_uint4(0, 0, 0, 0);
         it[j].s = make_uint4(0, 0, 0, 0);
         if (ok) {
-          it[j].r = __ldg(rrow + x);
+          it[j].r = ld_hint(rrow + x, once);
           if (HAS_RES) it[j].s = __ldg(srow + x);
         }
       }
