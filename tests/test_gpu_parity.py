@@ -304,6 +304,31 @@ def test_pipeline_stage_parity(cuda_dev):
             prev = o["out"]
 
 
+
+def test_pipeline_1024_laplace_stage_parity(cuda_dev):
+    """BASELINE configs[4] shape: 1024 x 1024 with the 6-channel pose input (2D + LaplaceProj) and background refinement;
+    one teacher-forced step of every stage against the oracle on the same inputs (width 1030 rows: M replication is
+    capped by the buffer slack, 4 x 128-pixel segments per row plus a remainder)."""
+    from nhvr_b200 import ops
+    kw = dict(pose_nc=6, tex_nc=3, size=1024, atlas_size=64, ngf_global=16, n_downsample_global=2, n_blocks_global=1,
+              ngf_translate=16, n_downsample_translate=2, n_blocks_translate=1, ngf_bg=16, n_downsample_bg=2, n_blocks_bg=1)
+    pipe, ref = _pair_pipeline(cuda_dev, kw, seed=23)
+    torch.manual_seed(5)
+    pose = torch.tanh(torch.nn.functional.interpolate(torch.randn(1, 6, 32, 32, device=cuda_dev), size=1024, mode="bilinear") * 2)
+    prev = torch.rand(1, 3, 1024, 1024, device=cuda_dev) * 2 - 1
+    with torch.no_grad():
+        bg_r = ref.refine_bg()
+        assert (pipe.refine_bg() - bg_r).abs().max().item() <= 2e-2
+        o = ref.render_frame(pose, prev, bg_r)
+        uvp = pipe.netTransG(pose)
+        assert (uvp - o["uvp"]).abs().max().item() <= 2e-2 * max(1.0, o["uvp"].abs().max().item())
+        tex, part, texel = ops.texture_sample(o["uvp"].contiguous(), pipe.atlas_channels_last(), 3, True)
+        assert torch.equal(part, o["part"]) and torch.equal(texel, o["texel"])
+        assert (tex - o["tex"]).abs().max().item() <= 1e-4
+        fgm = pipe.netG(o["tex"].contiguous(), pose, prev)
+        assert (fgm - o["fgm"]).abs().max().item() <= 2e-2 and psnr(fgm, o["fgm"]) >= 45.0
+
+
 def test_pipeline_free_running(cuda_dev):
     """Whole path free-running (its own UV-generator output feeds the lookup, its own frames feed back),
     eager and CUDA-graph.  16-bit UV-generator error (~1e-2 of a texel range) is multiplied by the texture
