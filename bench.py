@@ -330,7 +330,7 @@ def main():
         tms = float(tt.item()) / KT
         eng = [e for v in netT._engines.values() if isinstance(v, list) for e in v][0]
         fwd_flops = eng.flops
-        train = {"workload": "configs[1]: UV generator pre-train fwd+bwd+Adam, %dx%d, batch %d/GPU, synthetic DensePose targets%s"
+        train = {"workload": "configs[1]: UV generator pre-train fwd+bwd+Adam, %dx%d, batch %d/GPU, 3-channel pose map (--input_nc 3, REF pretrainTrans.sh), synthetic DensePose targets%s"
                              % (TS, TS, TB, ", NCCL gradient all-reduce" if world > 1 else ""),
                  "steps_per_s": 1000.0 / tms, "ms_per_step": tms, "samples_per_s": world * TB * 1000.0 / tms,
                  "conv_tflops_fwd_dgrad_wgrad": 3.0 * fwd_flops / (tms * 1e-3) / 1e12, "final_loss": float(last)}
