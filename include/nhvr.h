@@ -13,7 +13,7 @@
  *  - there is no CPU fallback: on a device that is not compute capability 10.x every compute
  *    entry point returns NHVR_ERR_ARCH.
  *
- * Activation layout "P8" (planar-by-8 bf16): [N][C8][Hp][Wp][8] where C8 = ceil(C/8) and one
+ * Activation layout "P8" (planar-by-8, 16-bit elements: fp16 or bf16, see nhvr_set_operand_dtype): [N][C8][Hp][Wp][8] where C8 = ceil(C/8) and one
  * 16-byte unit holds 8 consecutive channels of one pixel.  Hp/Wp include a halo that the WRITER
  * fills (zeros or mirror = ReflectionPad2d), so the conv kernel never pads.  `split`=1 stores the
  * padded image as four row/column-parity sub-images, which turns a stride-2 conv into unit shifts.
@@ -55,6 +55,9 @@ typedef struct nhvr_act_desc {
   int32_t pad_t, pad_l, pad_b, pad_r;
   int32_t split;     /* 0 plain, 1 four-way parity split (Hp, Wp rounded up to even) */
   int32_t halo;      /* NHVR_HALO_* : how a writer must fill the halo */
+  int32_t hilo;      /* 0: one 16-bit value per element.  1: split precision - every value v is stored as the pair
+                        hi = rn16(v), lo = rn16(v - hi) (22 significant bits with fp16 operands).  C8 then counts PHYSICAL
+                        planes = 2 x the logical plane count, in groups of four: [hi 2g, hi 2g+1, lo 2g, lo 2g+1]. */
 } nhvr_act_desc;
 
 /* One convolution layer.  Replaces nn.Conv2d / nn.ConvTranspose2d (+ the ReflectionPad2d in front)
@@ -73,6 +76,14 @@ typedef struct nhvr_conv_desc {
   int32_t in_extra_cols; /* extra zero columns right of the input's right halo (same purpose)                 */
   int32_t out_h, out_w;  /* NHVR_CONV_TRANSPOSE only: output size override (0 = 2H x 2W for k3, 2H-2 for k4)  */
   int32_t flags;         /* bit 0: never use the row-mode lowering (wide kernels with few output channels)
+                            bit 4: RAW_STATS sums are centred on the shift the caller stored in slot 2 of the statistics record
+                                   (nhvr_stem_stat_shift; first layers, where |mean| >> std on stick-figure pose maps)
+                            bit 3: split precision ("3 x fp16"): the input is a hilo activation (nhvr_act_desc.hilo), the
+                                   weights are packed as hi + lo blocks and every K step issues three MMAs
+                                   (x_hi*w_hi + x_hi*w_lo + x_lo*w_hi) into the same fp32 accumulator; a RAW_STATS output
+                                   is written as a hilo activation too.  fp32-class results at 3x the tensor work: used by
+                                   the UV generator, whose output error is multiplied by the texture gradient in the lookup
+                                   (inference only: no dgrad / wgrad plans for it)
                             bit 2: the input may use the single-plane tap-paired format (Cin <= 8 stride-1 convs:
                                    K group 1 of every MMA is the same plane one pixel to the right, so an MMA covers
                                    two filter columns).  Changes nhvr_conv_input_desc (C8 = 1): set it only when
@@ -87,11 +98,16 @@ const char* nhvr_strerror(int status);
 const char* nhvr_last_cuda_error(void);
 int nhvr_arch_ok(void);                 /* 0 iff the current device is compute capability 10.x */
 /* 16-bit element type of P8 activations and packed weights (the tcgen05 kind::f16 operands):
- * 0 = bf16 (default), 1 = IEEE fp16 (same tensor throughput, 3 more mantissa bits, saturating
- * conversion).  Process-wide; buffers and packed weights written under one setting must be consumed
- * under the same setting. */
+ * 0 = bf16, 1 = IEEE fp16 (same tensor throughput, 3 more mantissa bits; the Python host selects fp16 by
+ * default, see capi.DEFAULT_OPERAND).  fp16 conversions do NOT saturate: a value beyond 65504 becomes inf,
+ * propagates, and is reported through nhvr_set_overflow_flag.  Process-wide; buffers and packed weights
+ * written under one setting must be consumed under the same setting. */
 int nhvr_set_operand_dtype(int is_f16);
 int nhvr_get_operand_dtype(void);
+/* Range guard of the 16-bit path: `flag` (device int32, caller-owned, may be NULL to disable) is OR-ed with 1 by
+ * the InstanceNorm apply / backward kernels whenever they read a non-finite 16-bit value (an fp16 overflow of a conv
+ * output or gradient).  Process-wide; the host reads it at a synchronisation point of its choice. */
+int nhvr_set_overflow_flag(int32_t* flag);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t nhvr_launch_count(void);
 
@@ -122,19 +138,28 @@ int nhvr_conv_plan_info(const nhvr_conv_plan* p, int32_t* info, int32_t n);
 /* w: fp32, Conv2d layout [Cout][Cin][kh][kw] or ConvTranspose2d layout [Cin][Cout][kh][kw]. */
 int nhvr_conv_pack_weights(const nhvr_conv_plan* p, const float* w, void* packed, void* stream);
 /* out / stats / bias meaning depends on the plan's epilogue:
- *  RAW_STATS    : out = P8 [N][Cout8][Ho][Wo] (no halo, Cout8 = ceil(Cout/8) rounded up to even); stats = float [N][Cout8*8][2], must be zeroed
- *                 by the caller (sum, sum of squares over H*W, accumulated with atomics); bias unused
+ *  RAW_STATS    : out = P8 [N][Cout8][Ho][Wo] (no halo, Cout8 = ceil(Cout/8) rounded up to even); stats = double [N][Cout8*8][4]
+ *                 = {sum (x-s), sum (x-s)^2, s, unused} per channel over H*W, zeroed by the caller (s = 0: plain sums) and
+ *                 optionally centred with nhvr_stem_stat_shift before the conv; fp32 per-tile partial sums are merged with fp64
+ *                 atomics, so that the variance keeps its digits when |mean| >> std; bias unused
  *                 (a bias in front of an affine-free InstanceNorm cancels exactly).
  *  BIAS_ACT_F32 : out = float [N][Cout][Ho][Wo]; bias = float [Cout] or NULL.
  *  BIAS_ACT_P8  : out = P8 in out_desc's format (interior only is written); bias as above. */
 int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const void* packed_w, const float* bias,
-                      void* out, const nhvr_act_desc* out_desc, float* stats, void* stream);
+                      void* out, const nhvr_act_desc* out_desc, double* stats, void* stream);
+
+/* Centring shift of a FIRST layer's statistics: writes s[n][co] = sum_ci (sum_taps w[co][ci][tap]) * mean(src[n][ci]) (sampled
+ * mean) into slot 2 of the zeroed statistics record, i.e. the conv output wherever the input is flat.  Stick-figure pose maps
+ * (keypoints/*.json rasterised, start.sh:9,24) are ~98 % background: the stem output is c + small with mean^2/var up to 250,
+ * and un-centred sums lose 2-3 digits of the variance.  w: fp32 [Cout][Cin][taps]; src as in nhvr_pack_nchw (Cin <= 32). */
+int nhvr_stem_stat_shift(const float* w, int32_t Cout, int32_t Cin, int32_t taps, const float* const* src, const int32_t* src_c,
+                         int32_t nsrc, int32_t N, int32_t H, int32_t W, double* stats, void* stream);
 
 /* ---- InstanceNorm2d(affine=False) apply + activation (+ residual) + halo write ----
  * Replaces nn.InstanceNorm2d + nn.ReLU/LeakyReLU (+ the ResnetBlock skip add, + the next layer's
- * ReflectionPad2d / zero padding).  raw: P8 un-padded; stats as produced by RAW_STATS; residual
+ * ReflectionPad2d / zero padding).  raw: P8 un-padded; stats: the RAW_STATS record [N][C8*8][4]; residual
  * (nullable) is read at the interior of res_desc; dst is written completely, halo included. */
-int nhvr_in_apply(const void* raw, const nhvr_act_desc* raw_desc, const float* stats, float eps, int32_t act,
+int nhvr_in_apply(const void* raw, const nhvr_act_desc* raw_desc, const double* stats, float eps, int32_t act,
                   const void* residual, const nhvr_act_desc* res_desc,
                   void* dst, const nhvr_act_desc* dst_desc, void* stream);
 
@@ -187,7 +212,7 @@ int nhvr_composite_bwd(const float* fgm, const float* bg, int32_t bg_batched, co
  * Writes g (gradient w.r.t. raw) in g_desc's format, halo zeroed; dy_out (nullable) receives the folded
  * total gradient of the un-padded output; sums is a float [N][C8*8][2] scratch. */
 int nhvr_in_bwd(const void* dx, int32_t dx_H, int32_t dx_W, int32_t pad_t, int32_t pad_l, int32_t reflect,
-                const void* skip, const void* raw, const nhvr_act_desc* raw_desc, const float* stats, float eps,
+                const void* skip, const void* raw, const nhvr_act_desc* raw_desc, const double* stats, float eps,
                 int32_t act, float* sums, void* g, const nhvr_act_desc* g_desc, void* dy_out, void* stream);
 /* same for a layer WITHOUT normalisation (conv + bias + activation): g = dY * act'(y), y read from the stored
  * activation yact (P8 in y_desc's format); dbias float [C8*8] (zeroed by the caller) += per-channel sums of g */

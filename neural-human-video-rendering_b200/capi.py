@@ -24,7 +24,7 @@ EPI_RAW_STATS, EPI_BIAS_ACT_F32, EPI_BIAS_ACT_P8, EPI_RAW_P8 = 0, 1, 2, 3
 
 class ActDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
-                ("N", "C8", "H", "W", "pad_t", "pad_l", "pad_b", "pad_r", "split", "halo")]
+                ("N", "C8", "H", "W", "pad_t", "pad_l", "pad_b", "pad_r", "split", "halo", "hilo")]
 
     def copy(self) -> "ActDesc":
         d = ActDesc()
@@ -47,8 +47,11 @@ SYMBOLS = {
     "nhvr_launch_count": (C.c_uint64, []),
     "nhvr_set_operand_dtype": (C.c_int, [C.c_int]),
     "nhvr_get_operand_dtype": (C.c_int, []),
+    "nhvr_set_overflow_flag": (C.c_int, [_P]),
     "nhvr_act_bytes": (C.c_size_t, [C.POINTER(ActDesc)]),
     "nhvr_pack_nchw": (C.c_int, [C.POINTER(_P), C.POINTER(C.c_int32), C.c_int32, _P, C.POINTER(ActDesc), _P]),
+    "nhvr_stem_stat_shift": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_int32, _P, _P]),
     "nhvr_unpack_nchw": (C.c_int, [_P, C.POINTER(ActDesc), _P, C.c_int32, _P]),
     "nhvr_conv_plan_create": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(_P)]),
     "nhvr_conv_plan_destroy": (None, [_P]),
@@ -153,6 +156,29 @@ def stream_ptr() -> int:
 
 def ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
+
+
+_ovf = {}
+
+
+def overflow_flag(device=None) -> torch.Tensor:
+    """The device int32 the kernels OR with 1 when they read a non-finite 16-bit value (an fp16 overflow of a conv
+    output or gradient; include/nhvr.h nhvr_set_overflow_flag).  One flag per device, registered on first use."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _ovf:
+        _ovf[idx] = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", idx))
+        check(load().nhvr_set_overflow_flag(_ovf[idx].data_ptr()), "nhvr_set_overflow_flag")
+    return _ovf[idx]
+
+
+def check_overflow(device=None, what: str = "") -> None:
+    """Synchronising read of the range guard: raises if a 16-bit conv output / gradient overflowed since the last check."""
+    flag = overflow_flag(device)
+    if int(flag.item()) != 0:
+        flag.zero_()
+        raise NhvrError("16-bit operand overflow%s: a conv output or gradient exceeded the %s range (|x| > 65504 for fp16); "
+                        "use NHVR_OPERAND=bf16 or rescale the weights" % ((" in " + what) if what else "", operand_dtype()))
 
 
 def launch_count() -> int:

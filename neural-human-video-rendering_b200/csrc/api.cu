@@ -11,6 +11,8 @@ static char g_last_err[256] = "";
 static int g_arch_state = -1;   // -1 unknown, 0 bad, 1 ok
 static int g_operand_f16 = 0;
 int operand_f16() { return g_operand_f16; }
+static int32_t* g_overflow_flag = nullptr;
+int32_t* overflow_flag() { return g_overflow_flag; }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -54,3 +56,5 @@ extern "C" uint64_t nhvr_launch_count(void) { return nhvr::g_launches.load(); }
 
 extern "C" int nhvr_set_operand_dtype(int is_f16) { nhvr::g_operand_f16 = is_f16 ? 1 : 0; return NHVR_OK; }
 extern "C" int nhvr_get_operand_dtype(void) { return nhvr::g_operand_f16; }
+
+extern "C" int nhvr_set_overflow_flag(int32_t* flag) { nhvr::g_overflow_flag = flag; return NHVR_OK; }

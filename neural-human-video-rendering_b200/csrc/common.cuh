@@ -205,6 +205,12 @@ NHVR_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 
+// 32 lanes x 4 consecutive fp32 columns (no wait: several loads can be in flight before one tmem_ld_wait)
+NHVR_DEVINL void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+
 // Shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleaved" canonical layout):
 //   element (row r, 16-byte K-chunk k) lives at  start + (r%8)*16 + (r/8)*SBO + k*LBO.
 // Bit layout (sm_100 tcgen05 "matrix descriptor"): [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4,
@@ -227,10 +233,10 @@ __host__ __device__ inline uint32_t make_idesc_16(uint32_t M, uint32_t N, int f1
 }
 
 // 16-bit operand element type of the whole path: bf16 (f16 == 0) or IEEE fp16 (f16 != 0).  Both feed
-// tcgen05.mma kind::f16 at the same rate; fp16 keeps 3 more mantissa bits (conversion saturates).
+// tcgen05.mma kind::f16 at the same rate; fp16 keeps 3 more mantissa bits.
 NHVR_DEVINL uint32_t pack2(float lo, float hi, int f16) {
   uint32_t r;
-  if (f16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  if (f16) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));     // no saturation: overflow -> inf, flagged downstream
   else     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
@@ -241,6 +247,25 @@ NHVR_DEVINL float unpack_lo(uint32_t v, int f16) {
 NHVR_DEVINL float unpack_hi(uint32_t v, int f16) {
   if (f16) { __half2 h = *reinterpret_cast<__half2*>(&v); return __high2float(h); }
   return __uint_as_float(v & 0xFFFF0000u);
+}
+
+// a 16-byte unit of eight 16-bit values holds an inf / NaN (exponent field all ones)?
+NHVR_DEVINL bool unit_nonfinite(const uint4& u, int f16) {
+  const uint32_t m = f16 ? 0x7C007C00u : 0x7F807F80u;
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t e = w[i] & m;
+    bad |= ((e & 0xFFFFu) == (m & 0xFFFFu)) | ((e >> 16) == (m >> 16));
+  }
+  return bad;
+}
+
+// split precision: (a, b) -> hi = rn16 pair, lo = rn16 of the remainders (v = hi + lo to ~22 bits with fp16)
+NHVR_DEVINL void split_hilo(float a, float b, int f16, uint32_t& hi, uint32_t& lo) {
+  hi = pack2(a, b, f16);
+  lo = pack2(a - unpack_lo(hi, f16), b - unpack_hi(hi, f16), f16);
 }
 
 }  // namespace nhvr

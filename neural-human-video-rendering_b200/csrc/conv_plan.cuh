@@ -31,7 +31,8 @@ struct ConvKParams {
   const uint4* w;
   const float* bias;
   void* out;
-  float* stats;
+  double* stats;           // [N][Cout8*8][2] sum / sum of squares (fp64: E[x^2] - mean^2 must survive |mean| >> std)
+  const float* acc_scale;  // split precision: device scalar 2^-s multiplied into the accumulators (nullptr: none)
   long long* trace;        // NHVR_CONV_TRACE: per-CTA cycle counters (nullptr in production)
   int64_t in_plane_units;
   int64_t w_split_units;   // packed-weight units per N-split
@@ -48,12 +49,15 @@ struct ConvKParams {
   ActGeom og;              // BIAS_ACT_P8 destination
   int32_t mmas_per_chunk, stages_per_chunk;
   int32_t tile_step;       // linear positions a CTA advances by: 128, or 128-(kw-1) in row mode
+  int32_t xstep;           // stacked tiles: columns a tile advances by (128, or 128-(kw-1) in row mode)
   int32_t rowmode, Cp, kw; // row mode: accumulator column n = s*Cp + co, outputs = shifted sums over s (epilogue)
   // M replication: one CTA owns `mrep` 128-position blocks that share every weight block (one smem B tile feeds
   // mrep MMAs), `q_mstride` linear positions / `a_mstride` slab units apart.  xtiles > 0: the blocks are the same
   // 128-pixel row segment of mrep consecutive output rows ("stacked"); xtiles == 0: mrep*128 consecutive positions.
   int32_t mrep, a_mstride, q_mstride, xtiles, acc_mstride;
   int32_t a_lbo_units;     // K-group stride of the A descriptor: the slab plane stride, or 1 (tap pairing: next pixel)
+  int32_t stat_centred;    // RAW_STATS sums are centred on stats[n][c][2] (conv desc flag bit 4)
+  int32_t out_hilo;        // RAW outputs are written as a split-precision (hilo) activation
   int32_t pair;            // 1: launched as clusters of two CTAs running cta_group::2 MMAs (weights packed per CTA half)
   ConvRun runs[kMaxRuns];
   ConvMma mma[kMaxMma + 1];   // +1: the issue loop prefetches one entry ahead
@@ -67,12 +71,14 @@ namespace nhvr {
 struct PackParams {
   const float* w;
   uint4* dst;
+  float* tail;                 // split precision: {max|w| (bits), 2^-s} behind the packed blocks
   int32_t Cin, Cout, kh, kw, transposed;
   int32_t kcp, nchunks, njobs, Npad, nsplit, nblocks_padded;
   int32_t f16;
   int32_t flip;                // dgrad of a stride-1 conv: taps mirrored (r,s) -> (kh-1-r, kw-1-s)
   int32_t rowmode, Cp;         // row mode: job_tap = r*8 + accumulator, column n = s*Cp + co
   int32_t kfold;               // tap pairing: K group kp of a block = filter column job_tap%kw + kp, channels 0..7
+  int32_t split3;              // split precision: blocks (hi*w_hi, hi*w_lo, lo*w_hi) per group of four physical planes
   int32_t pair, bpb;           // CTA-pair layout: [stage of bpb blocks][rank][bpb][2][Npad/2][8]
   int16_t job_tap[kMaxJobs];   // r*kw + s of each job
 };

@@ -66,6 +66,10 @@ NHVR_DEVINL float warp_colsum16(const float (&v)[16], int lane) {
 // bias + activation on 16 consecutive output channels.  The switch sits OUTSIDE the per-channel loops: a per-element
 // switch compiles to an indirect branch per value and serialises the epilogue (measured: 13.5 K cycles per 128 x 80
 // block of the UV head, profiles/r01_conv_ablation.md).
+// tanh / sigmoid through one ex2 + one reciprocal (absolute error ~1e-7: cancellation only where the result is ~0)
+NHVR_DEVINL float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+NHVR_DEVINL float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
 NHVR_DEVINL void bias_act16(const float (&v)[16], const float* sb, int act, int c0, int Cout, float (&t)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) t[i] = v[i] + sb[i];
@@ -77,15 +81,17 @@ NHVR_DEVINL void bias_act16(const float (&v)[16], const float* sb, int act, int 
     for (int i = 0; i < 16; ++i) t[i] = t[i] > 0.f ? t[i] : 0.2f * t[i];
   } else if (act == NHVR_ACT_TANH) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) t[i] = tanhf(t[i]);
+    for (int i = 0; i < 16; ++i) t[i] = tanh_fast(t[i]);
   } else if (act == NHVR_ACT_TANH_SIGMOID_LAST) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) t[i] = (c0 + i == Cout - 1) ? 1.f / (1.f + __expf(-t[i])) : tanhf(t[i]);
+    for (int i = 0; i < 16; ++i) t[i] = (c0 + i == Cout - 1) ? sigmoid_fast(t[i]) : tanh_fast(t[i]);
   }
 }
 
 // one 16-channel group of one output pixel: raw P8 store (+ InstanceNorm statistics), or bias + activation.
 // sb: this group's 16 bias values in shared memory (zeros beyond Cout / without bias).
+// V: kernel variant (0 = standard layers; 1 = also split-precision (hilo) raw outputs and centred statistics)
+template <int V>
 NHVR_DEVINL void emit16(const ConvKParams& P, const float (&v)[16], int c0, bool valid, int n, int Y, int X, int g_local, int lane,
                         float* s_stats, const float* sb) {
   if (P.debug & 64) valid = valid && (v[0] == 123456.f);
@@ -100,13 +106,40 @@ NHVR_DEVINL void emit16(const ConvKParams& P, const float (&v)[16], int c0, bool
       hi.x = pack2(v[8], v[9], P.f16);  hi.y = pack2(v[10], v[11], P.f16);
       hi.z = pack2(v[12], v[13], P.f16); hi.w = pack2(v[14], v[15], P.f16);
       const uint64_t keep = l2_policy_evict_last();      // read back once by the IN-apply / gradient pass that follows
-      if ((c0 >> 3) < P.Cout8) st_hint(o + u0, lo, keep);
-      if ((c0 >> 3) + 1 < P.Cout8) st_hint(o + u0 + pstride, hi, keep);
+      if (V && P.out_hilo) {
+        // split-precision raw output: planes [hi 2g, hi 2g+1, lo 2g, lo 2g+1] of channel group g = c0 / 16
+        // (Cout8 is even, so both logical planes of the group exist); `lo`, `hi` above are the rounded halves
+        uint4 l0, l1;
+        l0.x = pack2(v[0] - unpack_lo(lo.x, P.f16), v[1] - unpack_hi(lo.x, P.f16), P.f16);
+        l0.y = pack2(v[2] - unpack_lo(lo.y, P.f16), v[3] - unpack_hi(lo.y, P.f16), P.f16);
+        l0.z = pack2(v[4] - unpack_lo(lo.z, P.f16), v[5] - unpack_hi(lo.z, P.f16), P.f16);
+        l0.w = pack2(v[6] - unpack_lo(lo.w, P.f16), v[7] - unpack_hi(lo.w, P.f16), P.f16);
+        l1.x = pack2(v[8] - unpack_lo(hi.x, P.f16), v[9] - unpack_hi(hi.x, P.f16), P.f16);
+        l1.y = pack2(v[10] - unpack_lo(hi.y, P.f16), v[11] - unpack_hi(hi.y, P.f16), P.f16);
+        l1.z = pack2(v[12] - unpack_lo(hi.z, P.f16), v[13] - unpack_hi(hi.z, P.f16), P.f16);
+        l1.w = pack2(v[14] - unpack_lo(hi.w, P.f16), v[15] - unpack_hi(hi.w, P.f16), P.f16);
+        if ((c0 >> 3) < P.Cout8) {
+          const int64_t uh = (((int64_t)n * 2 * P.Cout8 + ((c0 >> 4) << 2)) * P.Ho + Y) * P.Wo + X;
+          st_hint(o + uh, lo, keep);
+          st_hint(o + uh + pstride, hi, keep);
+          st_hint(o + uh + 2 * pstride, l0, keep);
+          st_hint(o + uh + 3 * pstride, l1, keep);
+        }
+      } else {
+        if ((c0 >> 3) < P.Cout8) st_hint(o + u0, lo, keep);
+        if ((c0 >> 3) + 1 < P.Cout8) st_hint(o + u0 + pstride, hi, keep);
+      }
     }
     if (P.epilogue == NHVR_EPI_RAW_STATS && !(P.debug & 16)) {
       float s[16], ss[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { s[i] = valid ? v[i] : 0.f; ss[i] = s[i] * s[i]; }
+      if (V && P.stat_centred) {               // first layers only: sums centred on the shift held in sb (nhvr_stem_stat_shift)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { s[i] = valid ? v[i] - sb[i] : 0.f; ss[i] = s[i] * s[i]; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { s[i] = valid ? v[i] : 0.f; ss[i] = s[i] * s[i]; }
+      }
       const float cs = warp_colsum16(s, lane);
       const float css = warp_colsum16(ss, lane);
       const int col = g_local * 16 + (lane >> 1);
@@ -149,8 +182,10 @@ constexpr int kThreads = 384;       // warps 0-3: roles, warps 4-11: epilogue
 // per MMA (the measured ceiling of the single-CTA kernel: profiles/r01_conv_ablation.md) drops from
 // A + 2*B to A + B bytes.  The leader (rank 0) issues the MMAs; the peer's MMA warp relays its local "stage full"
 // events to the leader's barriers; commits are multicast to both CTAs; each CTA drains its own 128 TMEM lanes.
-template <bool PAIR>
-__global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __grid_constant__ ConvKParams P) {
+// V = 1 adds the rarely used paths (split precision: accumulator scale + hilo raw output; centred stem statistics; the
+// shuffle epilogue of the row-mode RGB head) so that their registers and code do not weigh on the standard layers.
+template <bool PAIR, int V>
+__global__ void __launch_bounds__(kThreads, V ? 2 : 1) conv_shiftgemm_kernel(const __grid_constant__ ConvKParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   // warp index through a shuffle: provably warp-uniform, so the role branches and everything inside them (ring
   // counters, descriptors, table reads) stay on the uniform datapath instead of R2UR round trips per MMA
@@ -162,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
   int64_t q0;
   if (P.xtiles) {
     const int yg = blockIdx.x / P.xtiles;
-    ty0 = yg * P.mrep; tx0 = (blockIdx.x - yg * P.xtiles) * kTileM;
+    ty0 = yg * P.mrep; tx0 = (blockIdx.x - yg * P.xtiles) * P.xstep;
     q0 = (int64_t)ty0 * P.Wrow + tx0;
   } else {
     q0 = (int64_t)blockIdx.x * P.tile_step;
@@ -205,7 +240,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
     for (int i = threadIdx.x - 128; i < P.Npad * 2 * P.nacc; i += 256) s_stats[i] = 0.f;
     for (int i = threadIdx.x - 128; i < P.Npad; i += 256) {
       const int c = split * P.Npad + i;
-      s_bias[i] = (P.bias && c < P.Cout) ? __ldg(P.bias + c) : 0.f;
+      // RAW_STATS: no bias (it cancels in the InstanceNorm); the slot holds the statistics shift of this channel
+      // (stats[n][c][2], 0 unless the caller centred the sums, see nhvr_stem_stat_shift)
+      if (P.epilogue == NHVR_EPI_RAW_STATS) s_bias[i] = (V && P.stat_centred && c < P.Cout8 * 8) ? (float)P.stats[((int64_t)n * P.Cout8 * 8 + c) * 4 + 2] : 0.f;
+      else s_bias[i] = (P.bias && c < P.Cout) ? __ldg(P.bias + c) : 0.f;
     }
   }
   tc_fence_before();
@@ -326,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
       wait_b(0, 0);
       tc_fence_after();
       for (int c = 0; c < nchunks; ++c) {
+        if (SA == 1 && c > 0) wait_a(0, aph);                   // single slab stage: refilled only after the commit below
         const uint32_t a_st_lo = a_lo0 + (uint32_t)ast * a_stage_u;
         const uint32_t keep_mask = (c == 0) ? 0u : 1u;          // chunk 0: the first MMA of an accumulator overwrites
         const int nast = (ast + 1 == SA) ? 0 : ast + 1;
@@ -363,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
           }
           // pre-wait what the next stage needs, then the last block of this stage
           if (s + 1 < spc) wait_b(nbst, nbph);
-          else if (c + 1 < nchunks) { wait_a(nast, naph); wait_b(nbst, nbph); }
+          else if (c + 1 < nchunks) { if (SA > 1) wait_a(nast, naph); wait_b(nbst, nbph); }
           if (mrep == 1) issue(std::false_type{}); else issue(std::true_type{});
           if (leader) { if (PAIR) umma2_commit(&b_empty[bst]); else umma_commit(&b_empty[bst]); }
           bst = nbst; bph = nbph;
@@ -390,12 +429,120 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
     const int cout_off = split * P.Npad;
     const int ngroups = P.Npad >> 4;
 
+    // split precision: the packed weights carry a power-of-two scale (conv_pack_weights_kernel); undo it on the accumulators
+    const bool scaled = V && P.acc_scale != nullptr;
+    const float accs = scaled ? __ldg(P.acc_scale) : 1.f;
     mbar_wait_warp(acc_full, 0);
     tc_fence_after();
     if (trace && threadIdx.x == 128) trace[4] = clock64() - t_entry;
 
-    if (P.rowmode) {
-      // ---- row mode: accumulator column n = s*Cp + co holds Z[m][s][co]; output Y[m][co] = sum_s Z[m+s][s][co].
+    if (V && P.rowmode && P.Cp == 8) {
+      // ---- row mode, <= 8 output channels (the RGB + mask head): accumulator column s*8 + co of block `rep` holds
+      // Z[m][s][co] (filter column s un-shifted); output Y[m][co] = sum_s Z[m+s][s][co].  Row m+s lives in lane
+      // lane+s of the same warp (register shuffle) or, past lane 31, in the first kw-1 lanes of the next warp, which
+      // publish those values through a small double-buffered shared-memory window.  The two epilogue halves (warps 4-7 /
+      // 8-11) take alternate M blocks of the tile.
+      if (!(P.debug & 8)) {
+        const int kw = P.kw;                                 // 5..8 -> at most 7 neighbour rows
+        const int nco = min(P.Cout, 8);
+        const int xsz = 3 * 7 * 7 * nco;                     // [warp 3][lane 7][s-1 7][co nco] floats per buffer
+        float* X = s_bias + P.Npad + half * 2 * xsz;         // two buffers per epilogue half
+        const bool valid_x = (x < P.Wv) && (m < P.xstep);
+        int it = 0;
+        for (int rep = half; rep < P.mrep; rep += 2, ++it) {
+          float* Xb = X + (it & 1) * xsz;
+          float acc[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+          // phase A: own column 0, in-warp neighbours by shuffle, and the values the previous warp needs go to shared memory
+          if (nco <= 4) {
+            // <= 4 real output channels: seven 4-column TMEM loads in flight, one wait
+            uint32_t zr[8][4];
+#pragma unroll
+            for (int sft = 0; sft < 8; ++sft)
+              if (sft < kw) tmem_ld4(t_lane + (uint32_t)(rep * P.acc_mstride + sft * 8), zr[sft]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int sft = 0; sft < 8; ++sft) {
+              if (sft < kw) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  if (c < nco) {
+                    const float zv = __uint_as_float(zr[sft][c]) * accs;
+                    if (sft == 0) acc[c] += zv;
+                    else {
+                      const float up = __shfl_down_sync(0xffffffffu, zv, sft);
+                      if (lane + sft <= 31) acc[c] += up;
+                      if (we > 0 && lane < sft) Xb[(((we - 1) * 7 + lane) * 7 + (sft - 1)) * nco + c] = zv;
+                    }
+                  }
+                }
+              }
+            }
+          } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j * 2 < kw) {
+              uint32_t vr[16];
+              tmem_ld16(t_lane + (uint32_t)(rep * P.acc_mstride + j * 16), vr);
+              tmem_ld_wait();
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const int sft = 2 * j + h2;                    // filter column of these 8 accumulator columns
+                if (sft < kw) {
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {
+                    if (c < nco) {
+                      const float zv = __uint_as_float(vr[h2 * 8 + c]) * accs;
+                      if (sft == 0) acc[c] += zv;
+                      else {
+                        const float up = __shfl_down_sync(0xffffffffu, zv, sft);
+                        if (lane + sft <= 31) acc[c] += up;
+                        if (we > 0 && lane < sft) Xb[(((we - 1) * 7 + lane) * 7 + (sft - 1)) * nco + c] = zv;
+                      }
+                    }
+                  }
+                }
+              }
+            }
+          }
+          }
+          if (half == 0) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
+          // phase B: rows past lane 31 come from the next warp's first lanes
+          if (we < 3) {
+            for (int sft = 32 - lane; sft < kw; ++sft) {       // empty unless lane > 32 - kw
+              if (sft >= 1) {
+                const float* xs = Xb + ((we * 7 + (lane + sft - 32)) * 7 + (sft - 1)) * nco;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                  if (c < nco) acc[c] += xs[c];
+              }
+            }
+          }
+          const int yr = y + rep;
+          if (P.epilogue == NHVR_EPI_BIAS_ACT_F32) {           // the RGB (+ mask) head: only the nco real channels are finished
+            if (valid_x && yr < P.Hv) {
+              const int64_t plane = (int64_t)P.Ho * P.Wo;
+              float* o = reinterpret_cast<float*>(P.out) + ((int64_t)n * P.Cout * P.Ho + yr) * P.Wo + x;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                if (c < nco) {
+                  float t = acc[c] + s_bias[c];
+                  if (P.act == NHVR_ACT_RELU) t = fmaxf(t, 0.f);
+                  else if (P.act == NHVR_ACT_LRELU02) t = t > 0.f ? t : 0.2f * t;
+                  else if (P.act == NHVR_ACT_TANH) t = tanh_fast(t);
+                  else if (P.act == NHVR_ACT_TANH_SIGMOID_LAST) t = (c == P.Cout - 1) ? sigmoid_fast(t) : tanh_fast(t);
+                  o[c * plane] = t;
+                }
+              }
+            }
+          } else {
+            emit16<V>(P, acc, 0, valid_x && yr < P.Hv, n, yr, x, 0, lane, s_stats, s_bias);
+          }
+        }
+      }
+    } else if (P.rowmode) {
+      // ---- row mode, generic (Cp >= 16, one M block): accumulator column n = s*Cp + co holds Z[m][s][co]; output Y[m][co] = sum_s Z[m+s][s][co].
       // Warps 4-7 exchange one 16-column chunk at a time through shared memory (row m reads row m+s).
       if (half == 0 && !(P.debug & 8)) {
         float* S = s_bias + P.Npad;                         // [128][17] floats
@@ -413,7 +560,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
             tmem_ld16(t_lane + (uint32_t)(a * P.Npad + (n0 - a * P.Npad)), vr);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) S[m * 17 + i] = __uint_as_float(vr[i]);
+            for (int i = 0; i < 16; ++i) S[m * 17 + i] = __uint_as_float(vr[i]) * accs;
             asm volatile("bar.sync 2, 128;" ::: "memory");
             if (P.Cp >= 16) {
               if (m + j < kTileM) {
@@ -433,7 +580,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");
           }
-          emit16(P, acc, cg * 16, valid, n, y, x, cg, lane, s_stats, s_bias + cg * 16);
+          emit16<V>(P, acc, cg * 16, valid, n, y, x, cg, lane, s_stats, s_bias + cg * 16);
         }
       }
     } else {
@@ -453,18 +600,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
           tmem_ld16(t_lane + (uint32_t)(rep * P.acc_mstride + a * P.Npad + g * 16), vr);
           tmem_ld_wait();
           float v[16];
+          if (scaled) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(vr[i]);
-          emit16(P, v, cout_off + g * 16, valid, n, Y, X, g, lane, s_stats, s_bias + g * 16);
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(vr[i]) * accs;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(vr[i]);
+          }
+          emit16<V>(P, v, cout_off + g * 16, valid, n, Y, X, g, lane, s_stats, s_bias + g * 16);
         }
       }
     }
     }
     if (P.epilogue == NHVR_EPI_RAW_STATS) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      float* gs = P.stats + ((int64_t)n * P.Cout8 * 8 + cout_off) * 2;
+      // per-CTA partial sums (fp32, <= a few hundred values each) are merged in fp64: the variance E[x^2] - mean^2 of a
+      // nearly constant channel (stick-figure pose maps: mean^2 / var ~ 250 at the stem) cancels 2-3 digits
+      double* gs = P.stats + ((int64_t)n * P.Cout8 * 8 + cout_off) * 4;       // {sum, sum of squares, shift, -} per channel
       const int lim = (P.rowmode ? P.Cout8 * 8 : min(P.Npad, P.Cout8 * 8 - cout_off)) * 2;
-      for (int i = threadIdx.x - 128; i < lim; i += 256) atomicAdd(gs + i, s_stats[i]);
+      for (int i = threadIdx.x - 128; i < lim; i += 256) atomicAdd(gs + (i >> 1) * 4 + (i & 1), (double)s_stats[i]);
     }
   }
 
@@ -480,9 +634,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_shiftgemm_kernel(const __gri
 // -------------------------------------------------------------------------------------------------
 // weight packing: OIHW (or IOHW for transposed) fp32 -> per-MMA blocks [2][Npad][8] bf16 in
 // consumption order (chunk, job, k-step); see header comment.
+// split precision: |w| max over the weight tensor (float bits compare like unsigned integers for non-negative values)
+__global__ void conv_weight_absmax_kernel(const float* __restrict__ w, int64_t n, uint32_t* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(out, __float_as_uint(m));
+}
+
 __global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
   const int64_t total = (int64_t)P.nsplit * P.nblocks_padded * 2 * P.Npad;
-  const int qsteps = P.kfold ? 1 : P.kcp >> 1;
+  // split precision: the lo parts of N(0, 0.02)-sized weights would be fp16 subnormals (18-19 significant bits instead
+  // of 22), so the whole tensor is scaled by a power of two that puts max|w| into [8192, 16384); the conv epilogue
+  // multiplies the accumulators by the inverse (exact).  tail = {max|w| bits, 2^-s} behind the packed blocks.
+  float wscale = 1.f;
+  if (P.split3) {
+    const float amax = __uint_as_float(*reinterpret_cast<const uint32_t*>(P.tail));
+    const int sh = amax > 0.f ? 13 - ilogbf(amax) : 0;
+    wscale = ldexpf(1.f, sh);
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.tail[1] = ldexpf(1.f, -sh);
+  }
+  // MMAs per (chunk, tap): kcp/2 plane pairs; split precision: 3 per group of four physical planes (hi*hi, hi*lo, lo*hi)
+  const int qsteps = P.kfold ? 1 : (P.split3 ? 3 * (P.kcp >> 2) : P.kcp >> 1);
   const int nblocks = P.nchunks * P.njobs * qsteps;
   for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (int64_t)gridDim.x * blockDim.x) {
     const int nrow = (int)(u % P.Npad);
@@ -508,19 +682,27 @@ __global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
         else tap += kp;
       }
       float vals[8];
+      // split precision: block qq = 3*g + t of a chunk covers logical planes 2*(c*kcp/4 + g) + kp; t == 1 carries w_lo
+      const int lplane = P.split3 ? 2 * (c * (P.kcp >> 2) + qq / 3) + kp : c * P.kcp + 2 * qq + kp;
+      const bool w_lo = P.split3 && (qq % 3) == 1;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const int ci = P.kfold ? e : (c * P.kcp + 2 * qq + kp) * 8 + e;
+        const int ci = P.kfold ? e : lplane * 8 + e;
         float val = 0.f;
         if (ci < P.Cin && co < P.Cout) {
           const int64_t idx = P.transposed ? (((int64_t)ci * P.Cout + co) * (P.kh * P.kw) + tap)
                                            : (((int64_t)co * P.Cin + ci) * (P.kh * P.kw) + tap);
-          val = P.w[idx];
+          val = P.w[idx] * wscale;
         }
         vals[e] = val;
       }
       packed[0] = pack2(vals[0], vals[1], P.f16); packed[1] = pack2(vals[2], vals[3], P.f16);
       packed[2] = pack2(vals[4], vals[5], P.f16); packed[3] = pack2(vals[6], vals[7], P.f16);
+      if (w_lo) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          packed[i] = pack2(vals[2 * i] - unpack_lo(packed[i], P.f16), vals[2 * i + 1] - unpack_hi(packed[i], P.f16), P.f16);
+      }
     }
     int64_t du = u;
     if (P.pair) {              // [split][stage][rank][block in stage][k-group][N/2 rows]
@@ -556,6 +738,10 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   int gemm_k = d->Cin, gemm_n = d->Cout;          // dgrad swaps them
   if (d->kind == NHVR_CONV_DGRAD_S1) { gemm_k = d->Cout; gemm_n = d->Cin; }
   int C8 = round_up((gemm_k + 7) / 8, 2);   // K = 16 per MMA -> an even number of planes
+  // split precision (flag bit 3): hilo input, C8 counts PHYSICAL planes (groups of four), three MMAs per K step
+  const bool split3 = (d->flags & 8) != 0;
+  if (split3 && d->kind == NHVR_CONV_DGRAD_S1) { delete p; return NHVR_ERR_UNSUPPORTED; }
+  if (split3) C8 *= 2;
   // Tap pairing (flag bit 2, <= 8 input channels, e.g. the 3-channel pose stem): ONE plane; K group 1 of every MMA is the
   // same plane one pixel to the right (LBO = 16 bytes), so an MMA covers two filter columns: kh*ceil(kw/2) MMAs instead
   // of kh*kw on half the slab bytes.
@@ -564,13 +750,14 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
     const int Cp_row = d->Cout <= 8 ? 8 : round_up(d->Cout, 16);
     const bool row_ok = !(d->flags & 1) && d->kw >= 5 && d->kw <= 8 && d->kw * Cp_row <= 128 && !std::getenv("NHVR_NO_ROWMODE") &&
                         d->epilogue != NHVR_EPI_BIAS_ACT_P8;
-    kfold = (d->flags & 4) && !(d->flags & 1) && d->kind == NHVR_CONV && d->stride == 1 && d->Cin <= 8 && d->kw >= 2 && !row_ok &&
+    kfold = (d->flags & 4) && !split3 && !(d->flags & 1) && d->kind == NHVR_CONV && d->stride == 1 && d->Cin <= 8 && d->kw >= 2 && !row_ok &&
             !(std::getenv("NHVR_CONV_KFOLD") && std::atoi(std::getenv("NHVR_CONV_KFOLD")) == 0);
     if (kfold) C8 = 1;
   }
   K.C8in = C8;
   nhvr_act_desc& in = p->in_desc;
   in.N = d->N; in.C8 = C8; in.H = d->H; in.W = d->W; in.halo = d->halo; in.split = 0;
+  in.hilo = split3 ? 1 : 0;
 
   struct Tap { int run_key; int shift; int acc; int tap; };
   std::vector<Tap> taps;
@@ -605,11 +792,13 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
       rowmode = !(d->flags & 1) && d->kw >= 5 && d->kw <= 8 && d->kw * Cp_row <= 128 && !std::getenv("NHVR_NO_ROWMODE") &&
                 d->epilogue != NHVR_EPI_BIAS_ACT_P8;
       if (rowmode) {
-        if (mrep != 1) return NHVR_ERR_UNSUPPORTED;
+        // M replication in row mode: `mrep` consecutive output rows of the same 128-column segment ("stacked") share
+        // their input rows (kh + mrep - 1 slab rows instead of mrep * kh); shuffle epilogue, <= 8 output channels only
+        if (mrep != 1 && !(stacked && Cp_row == 8)) return NHVR_ERR_UNSUPPORTED;
         const int ntot = d->kw * Cp_row;
         nacc = (ntot + 255) / 256;
         row_npad = round_up((ntot + nacc - 1) / nacc, 16);
-        for (int r = 0; r < d->kh; ++r) run_specs.push_back({r * Wp, kTileM});
+        for (int r = 0; r < d->kh + xrows; ++r) run_specs.push_back({r * Wp, kTileM});
         for (int r = 0; r < d->kh; ++r)
           for (int a = 0; a < nacc; ++a) taps.push_back({r, 0, a, r * 8 + a});
         K.rowmode = 1; K.Cp = Cp_row; K.kw = d->kw;
@@ -687,6 +876,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
       return NHVR_ERR_UNSUPPORTED;
     }
     if ((int)taps.size() > kMaxJobs) return NHVR_ERR_UNSUPPORTED;
+    K.xstep = rowmode ? kTileM - (d->kw - 1) : kTileM;
     return NHVR_OK;
   };
 
@@ -737,7 +927,8 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
         for (int i = 1; i < mrep; ++i)
           if (key_soff[t.run_key + i * key_stride] - key_soff[t.run_key] != i * K.a_mstride) return NHVR_ERR_UNSUPPORTED;
     }
-    if (stacked) K.xtiles = (K.Wv + kTileM - 1) / kTileM;
+    K.xstep = rowmode ? kTileM - (d->kw - 1) : kTileM;
+    if (stacked) K.xtiles = (K.Wv + K.xstep - 1) / K.xstep;
     return NHVR_OK;
   };
 
@@ -758,32 +949,38 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   int pair = 0;
   auto smem_need = [&](int kcp_, int sa, int dv, int sb) -> long {
     return (long)sa * kcp_ * slab * 16 + (long)sb * dv * Npad * (pair ? 16 : 32) + (long)(3 * sa + 3 * sb + 1) * 8 + 8 + (long)Npad * 8 * nacc +
-           (long)Npad * 4 + (rowmode ? 8704 : 0) + 128;
+           (long)Npad * 4 + (rowmode ? (K.Cp == 8 ? 2L * 2 * 3 * 7 * 7 * std::min(gemm_n, 8) * 4 : 8704L) : 0) + 128;
   };
   auto try_fit = [&](long limit) -> bool {
     const int b_block = Npad * 32;
     long best_score = -1;
     for (int cand = kfold ? 1 : 8; cand >= (kfold ? 1 : 2); cand -= 2) {
       if (C8 % cand) continue;
+      if (split3 && (cand & 3)) continue;                     // hi/lo groups of four physical planes stay in one chunk
       const int nch = C8 / cand;
-      const int sa = std::min(2, nch);
-      const int bpc = kfold ? (int)taps.size() : (int)taps.size() * cand / 2;          // MMA blocks per chunk
+      const int bpc = kfold ? (int)taps.size() : split3 ? (int)taps.size() * 3 * (cand / 4) : (int)taps.size() * cand / 2;   // MMA blocks per chunk
       if (bpc > kMaxMma) continue;
-      for (int dv = 8; dv >= 1; --dv) {                      // blocks per B stage: a divisor of bpc, stage <= 24 KB
-        if (bpc % dv || (long)dv * b_block > (pair ? 49152 : 24576)) continue;
-        int sb = 6;
-        while (sb >= 2 && smem_need(cand, sa, dv, sb) > limit) --sb;
-        if (sb < 2) continue;
-        // score: weight bytes in flight, mild preference for >= 3 stages and for fewer, larger chunks
-        const long score = (long)std::min(sb, 4) * dv * b_block + (sb >= 3 ? 4096 : 0) + cand * 64;
-        if (score > best_score) { best_score = score; kcp = cand; SA = sa; bpb = dv; SB = sb; }
-        break;
+      // split precision doubles the slab bytes of a chunk (hi + lo planes) while tripling its MMAs: a single slab stage
+      // (the co-resident CTA covers the refill) is allowed there when two stages do not leave room for the weight ring
+      bool found = false;
+      for (int sa = std::min(2, nch); sa >= (split3 ? 1 : std::min(2, nch)) && !found; --sa) {
+        for (int dv = 8; dv >= 1; --dv) {                      // blocks per B stage: a divisor of bpc, stage <= 24 KB
+          if (bpc % dv || (long)dv * b_block > (pair ? 49152 : 24576)) continue;
+          int sb = 6;
+          while (sb >= 2 && smem_need(cand, sa, dv, sb) > limit) --sb;
+          if (sb < 2) continue;
+          // score: weight bytes in flight, mild preference for >= 3 stages and for fewer, larger chunks
+          const long score = (long)std::min(sb, 4) * dv * b_block + (sb >= 3 ? 4096 : 0) + cand * 64 - ((sa < 2 && nch > 1) ? 16384 : 0);
+          if (score > best_score) { best_score = score; kcp = cand; SA = sa; bpb = dv; SB = sb; }
+          found = true;
+          break;
+        }
       }
     }
     return best_score >= 0;
   };
   auto count_tiles = [&](int mrep, bool stacked) -> int {
-    if (stacked) return ((K.Hv + mrep - 1) / mrep) * ((K.Wv + kTileM - 1) / kTileM);
+    if (stacked) return ((K.Hv + mrep - 1) / mrep) * ((K.Wv + K.xstep - 1) / K.xstep);
     const int64_t last_q = (int64_t)(K.Hv - 1) * K.Wrow + K.Wv;   // one past the last valid linear position
     return (int)((last_q + K.tile_step - 1) / K.tile_step);
   };
@@ -799,6 +996,21 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   const bool plain = (d->flags & 1) || rowmode || d->kind == NHVR_CONV_TRANSPOSE || std::getenv("NHVR_CONV_TUNE");
   int force_m = 0, force_split = 0;
   if (const char* e = std::getenv("NHVR_CONV_MREP")) std::sscanf(e, "%d,%d", &force_m, &force_split);
+  if (rowmode && K.Cp == 8 && force_m != 1 && !std::getenv("NHVR_CONV_TUNE")) {
+    // row mode (RGB + mask head): 2-4 stacked output rows per tile, two CTAs per SM
+    int mmax = force_m > 1 ? force_m : 4;
+    while (mmax > 1 && (int64_t)(mmax - 1) * K.Wrow + 2 * kTileM > kActSlackUnits) --mmax;
+    for (int m = mmax; m >= 2 && !ok; --m) {
+      if (build_geometry(m, true) != NHVR_OK) continue;
+      if (m * nacc * row_npad > 256) continue;
+      K.xstep = kTileM - (d->kw - 1);
+      if (!force_m && (int64_t)count_tiles(m, true) * d->N < 148) continue;
+      if (layout_runs(m, true) != NHVR_OK) continue;
+      tile_n(m, 1);
+      ok = try_fit(kSmemTwoPerSm);
+      if (ok) { mrep = m; stacked = true; }
+    }
+  }
   if (!plain && force_m != 1) {
     const int n16 = round_up(gemm_n, 16);
     // measured (profiles/r01_conv_ablation.md): splitting wide outputs over two CTAs to make room for a second M block
@@ -854,7 +1066,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
       pair = eligible && (pe ? std::atoi(pe) != 0 : (Npad > 128 && Npad <= 192)) ? 1 : 0;
     }
     const int b_block = Npad * 32;
-    if (const char* tune = std::getenv("NHVR_CONV_TUNE")) {   // experiments: "kcp,SA,bpb,SB"
+    if (const char* tune = split3 ? nullptr : std::getenv("NHVR_CONV_TUNE")) {   // experiments: "kcp,SA,bpb,SB"
       int a, b, c, e;
       if (std::sscanf(tune, "%d,%d,%d,%d", &a, &b, &c, &e) == 4 && a >= 2 && (a % 2) == 0 && C8 % a == 0 && b >= 1 && c >= 1 && e >= 2 &&
           ((int)taps.size() * a / 2) % c == 0 && (int)taps.size() * a / 2 <= kMaxMma) {
@@ -896,7 +1108,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   K.kcp = kcp; K.SA = SA; K.bpb = bpb; K.SB = SB;
   K.pair = pair;
   K.nchunks = C8 / kcp;
-  const int ksteps = kfold ? 1 : kcp / 2;
+  const int ksteps = kfold ? 1 : split3 ? 3 * (kcp / 4) : kcp / 2;
   K.mmas_per_chunk = K.njobs * ksteps;
   K.a_lbo_units = kfold ? 1 : slab;
   K.stages_per_chunk = K.mmas_per_chunk / bpb;           // bpb divides mmas_per_chunk by construction
@@ -906,11 +1118,13 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   for (int j = 0; j < K.njobs; ++j)
     for (int q = 0; q < ksteps; ++q) {
       ConvMma& m = K.mma[j * ksteps + q];
-      m.a_off = jobs[j].a_off + 2 * q * slab;
+      // A planes of step q inside the chunk slab: plane pair q, or (split precision) hi, hi, lo of group q / 3
+      const int aplane = split3 ? 4 * (q / 3) + ((q % 3) == 2 ? 2 : 0) : 2 * q;
+      m.a_off = jobs[j].a_off + aplane * slab;
       m.meta = (uint32_t)(jobs[j].acc * Npad) | ((jobs[j].first && q == 0) ? 0x10000u : 0u);
     }
   K.w_split_units = (int64_t)nblocks_padded * 2 * Npad;
-  p->weight_bytes = (size_t)nsplit * K.w_split_units * 16;
+  p->weight_bytes = (size_t)nsplit * K.w_split_units * 16 + (split3 ? 16 : 0);   // split precision: + {max|w|, 2^-s} tail
   p->smem_bytes = (size_t)smem_need(kcp, SA, bpb, SB);
 
   if (!(d->kind == NHVR_CONV && d->stride == 2)) in.pad_b += d->in_extra_rows;   // plain formats: only the plane stride grows
@@ -929,6 +1143,9 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   PP.nblocks_padded = nblocks_padded;
   PP.pair = pair; PP.bpb = bpb;
   PP.kfold = kfold ? 1 : 0;
+  PP.split3 = split3 ? 1 : 0;
+  K.stat_centred = (d->flags & 16) ? 1 : 0;
+  K.out_hilo = (split3 && (d->epilogue == NHVR_EPI_RAW_STATS || d->epilogue == NHVR_EPI_RAW_P8)) ? 1 : 0;
   *out = p;
   return NHVR_OK;
 }
@@ -991,6 +1208,15 @@ extern "C" int nhvr_conv_pack_weights(const nhvr_conv_plan* p, const float* w, v
   PP.dst = reinterpret_cast<uint4*>(packed);
   const int64_t total = (int64_t)PP.nsplit * PP.nblocks_padded * 2 * PP.Npad;
   const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+  PP.tail = nullptr;
+  if (PP.split3) {
+    PP.tail = reinterpret_cast<float*>(reinterpret_cast<uint4*>(packed) + total);
+    cudaError_t e0 = cudaMemsetAsync(PP.tail, 0, 16, (cudaStream_t)stream);
+    if (e0 != cudaSuccess) { note_cuda_error(e0); return NHVR_ERR_CUDA; }
+    const int64_t nw = (int64_t)p->d.Cin * p->d.Cout * p->d.kh * p->d.kw;
+    conv_weight_absmax_kernel<<<(int)std::min<int64_t>((nw + 255) / 256, 148 * 4), 256, 0, (cudaStream_t)stream>>>(w, nw, reinterpret_cast<uint32_t*>(PP.tail));
+    count_launch();
+  }
   conv_pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(PP);
   count_launch();
   cudaError_t e = cudaGetLastError();
@@ -999,7 +1225,7 @@ extern "C" int nhvr_conv_pack_weights(const nhvr_conv_plan* p, const float* w, v
 }
 
 extern "C" int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const void* packed_w, const float* bias,
-                                 void* out, const nhvr_act_desc* out_desc, float* stats, void* stream) {
+                                 void* out, const nhvr_act_desc* out_desc, double* stats, void* stream) {
   if (!p || !in || !packed_w || !out) return NHVR_ERR_NULL;
   if ((((uintptr_t)in | (uintptr_t)packed_w | (uintptr_t)out) & 15) != 0) return NHVR_ERR_ALIGN;
   if (!arch_ok_cached()) return NHVR_ERR_ARCH;
@@ -1017,17 +1243,23 @@ extern "C" int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const 
   K.bias = bias;
   K.out = out;
   K.stats = stats;
+  K.acc_scale = p->pp.split3 ? reinterpret_cast<const float*>(reinterpret_cast<const uint4*>(packed_w) + (int64_t)p->nsplit * K.w_split_units) + 1 : nullptr;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_shiftgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_shiftgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_shiftgemm_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_shiftgemm_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_shiftgemm_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_shiftgemm_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
     attr_set = true;
   }
   dim3 grid(K.pair ? (p->tiles_per_img + 1) & ~1 : p->tiles_per_img, p->d.N, p->nsplit);   // pairs: an even number of tiles
+  // variant 1 = the layers that need the special epilogue paths (see the kernel header)
+  const bool special = K.acc_scale != nullptr || K.out_hilo || K.stat_centred || (K.rowmode && K.Cp == 8);
   auto launch = [&]() -> cudaError_t {
     if (!K.pair) {
-      conv_shiftgemm_kernel<false><<<grid, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(K);
+      if (special) conv_shiftgemm_kernel<false, 1><<<grid, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(K);
+      else conv_shiftgemm_kernel<false, 0><<<grid, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(K);
       return cudaGetLastError();
     }
     cudaLaunchConfig_t cfg = {};
@@ -1036,7 +1268,8 @@ extern "C" int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const 
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, conv_shiftgemm_kernel<true>, K);
+    if (special) return cudaLaunchKernelEx(&cfg, conv_shiftgemm_kernel<true, 1>, K);
+    return cudaLaunchKernelEx(&cfg, conv_shiftgemm_kernel<true, 0>, K);
   };
   K.trace = nullptr;
   if (std::getenv("NHVR_CONV_TRACE")) {     // diagnostics: per-CTA cycle breakdown printed to stderr (synchronises)

@@ -13,6 +13,7 @@ extern void note_cuda_error(cudaError_t e);
 extern void count_launch();
 extern int arch_ok_cached();
 extern int operand_f16();
+extern int32_t* overflow_flag();
 
 // map a padded destination coordinate to its logical source; returns false for "write zeros"
 NHVR_DEVINL bool dst_to_src(const ActGeom& g, int yy, int xx, int& y, int& x) {
@@ -37,8 +38,11 @@ struct PackParams2 {
 
 __global__ void __launch_bounds__(256) pack_nchw_kernel(const __grid_constant__ PackParams2 P) {
   const ActGeom& g = P.g;
-  const int np = blockIdx.y;              // n * C8 + p
-  const int n = np / g.C8, p = np - n * g.C8;
+  const int np = blockIdx.y;              // n * C8 + physical plane
+  const int n = np / g.C8, pp = np - n * g.C8;
+  // split precision: physical planes come in groups [hi 2g, hi 2g+1, lo 2g, lo 2g+1]
+  const int p = g.hilo ? ((pp >> 2) << 1) | (pp & 1) : pp;      // logical plane
+  const bool lo_part = g.hilo && (pp & 2);
   const int64_t HW = (int64_t)g.H * g.W;
   const int total = g.Hp * g.Wp;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -67,6 +71,14 @@ __global__ void __launch_bounds__(256) pack_nchw_kernel(const __grid_constant__ 
     uint4 o;
     o.x = pack2(v[0], v[1], P.f16); o.y = pack2(v[2], v[3], P.f16);
     o.z = pack2(v[4], v[5], P.f16); o.w = pack2(v[6], v[7], P.f16);
+    if (lo_part) {
+      uint4 l;
+      l.x = pack2(v[0] - unpack_lo(o.x, P.f16), v[1] - unpack_hi(o.x, P.f16), P.f16);
+      l.y = pack2(v[2] - unpack_lo(o.y, P.f16), v[3] - unpack_hi(o.y, P.f16), P.f16);
+      l.z = pack2(v[4] - unpack_lo(o.z, P.f16), v[5] - unpack_hi(o.z, P.f16), P.f16);
+      l.w = pack2(v[6] - unpack_lo(o.w, P.f16), v[7] - unpack_hi(o.w, P.f16), P.f16);
+      o = l;
+    }
     P.dst[(int64_t)np * g.plane_units + plane_unit(g, yy, xx)] = o;
   }
 }
@@ -74,29 +86,65 @@ __global__ void __launch_bounds__(256) pack_nchw_kernel(const __grid_constant__ 
 __global__ void __launch_bounds__(256) unpack_nchw_kernel(const uint4* __restrict__ src, ActGeom g, float* __restrict__ dst,
                                                           int C, int f16) {
   const int np = blockIdx.y;
-  const int n = np / g.C8, p = np - n * g.C8;
+  const int n = np / g.C8, pp = np - n * g.C8;
+  if (g.hilo && (pp & 2)) return;                                 // lo planes are read together with their hi plane
+  const int p = g.hilo ? ((pp >> 2) << 1) | (pp & 1) : pp;        // logical plane
   const int64_t HW = (int64_t)g.H * g.W;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
     const int y = i / g.W, x = i - y * g.W;
-    const uint4 u = src[(int64_t)np * g.plane_units + plane_unit(g, y + g.pad_t, x + g.pad_l)];
+    const int64_t at = (int64_t)np * g.plane_units + plane_unit(g, y + g.pad_t, x + g.pad_l);
+    const uint4 u = src[at];
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t wl[4] = {0, 0, 0, 0};
+    if (g.hilo) { const uint4 l = src[at + 2 * g.plane_units]; wl[0] = l.x; wl[1] = l.y; wl[2] = l.z; wl[3] = l.w; }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = p * 8 + e;
-      if (c < C) dst[((int64_t)n * C + c) * HW + i] = (e & 1) ? unpack_hi(w[e >> 1], f16) : unpack_lo(w[e >> 1], f16);
+      float val = (e & 1) ? unpack_hi(w[e >> 1], f16) : unpack_lo(w[e >> 1], f16);
+      if (g.hilo) val += (e & 1) ? unpack_hi(wl[e >> 1], f16) : unpack_lo(wl[e >> 1], f16);
+      if (c < C) dst[((int64_t)n * C + c) * HW + i] = val;
     }
+  }
+}
+
+NHVR_DEVINL void unpack8(const uint4& u, float (&v)[8], int f16) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = (e & 1) ? unpack_hi(w[e >> 1], f16) : unpack_lo(w[e >> 1], f16);
+}
+NHVR_DEVINL uint4 pack8(const float (&v)[8], int f16) {
+  uint4 o;
+  o.x = pack2(v[0], v[1], f16); o.y = pack2(v[2], v[3], f16);
+  o.z = pack2(v[4], v[5], f16); o.w = pack2(v[6], v[7], f16);
+  return o;
+}
+
+// (sum, sum of squares) in fp64 -> fp32 (rstd, -mean * rstd) of 8 channels.  mean and variance are formed in fp64: with
+// |mean| >> std the difference E[x^2] - mean^2 cancels leading digits that fp32 sums do not have.
+// Statistics record of one channel: {sum (x - s), sum (x - s)^2, s, unused} with s the (optional) centring shift.
+NHVR_DEVINL void norm_params8(const double* __restrict__ st, float inv_hw, float eps, float (&scale)[8], float (&shift)[8]) {
+  const double2* s2 = reinterpret_cast<const double2*>(st);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const double2 q = s2[2 * e], r = s2[2 * e + 1];
+    const double m0 = q.x * (double)inv_hw;                 // mean of x - s
+    const double var = fmax(q.y * (double)inv_hw - m0 * m0, 0.0);
+    const float rstd = rsqrtf((float)var + eps);
+    scale[e] = rstd;
+    shift[e] = -(float)(m0 + r.x) * rstd;
   }
 }
 
 struct ApplyParams {
   const uint4* raw;      // P8 un-padded [N][C8][H][W]
-  const float* stats;    // [N][C8*8][2]
+  const double* stats;   // [N][C8*8][2] fp64 sums
   const uint4* res;      // nullable
   uint4* dst;
   ActGeom rg, sg, dg;    // raw, residual, destination geometry
   float eps, inv_hw;
   int32_t act;
   int32_t f16;
+  int32_t* ovf;          // nullable: OR-ed with 1 when a non-finite raw value is read (nhvr_set_overflow_flag)
 };
 
 // Latency-bound gather: the statistics loads, and two destination units per thread and pass, are in flight before
@@ -150,8 +198,7 @@ __global__ void __launch_bounds__(256, 4) in_apply_kernel(const __grid_constant_
   const ActGeom& g = P.dg;
   const int np = blockIdx.y;
   const int n = np / g.C8, p = np - n * g.C8;
-  const float4* st4 = reinterpret_cast<const float4*>(P.stats + ((int64_t)n * g.C8 + p) * 16);
-  const float4 q0 = __ldg(st4), q1 = __ldg(st4 + 1), q2 = __ldg(st4 + 2), q3 = __ldg(st4 + 3);
+  const double* st = P.stats + ((int64_t)n * g.C8 + p) * 32;
   const int total = g.Hp * g.Wp;
   const int stride = gridDim.x * blockDim.x;
   const uint4* raw = P.raw + ((int64_t)n * P.rg.C8 + p) * P.rg.plane_units;
@@ -162,17 +209,7 @@ __global__ void __launch_bounds__(256, 4) in_apply_kernel(const __grid_constant_
   apply_fetch<HAS_RES>(P, g, raw, res, i0, total, a0);
   apply_fetch<HAS_RES>(P, g, raw, res, i0 + stride, total, a1);
   float scale[8], shift[8];
-  {
-    const float sv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float mean = sv[2 * e] * P.inv_hw;
-      const float var = fmaxf(sv[2 * e + 1] * P.inv_hw - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + P.eps);
-      scale[e] = rstd;
-      shift[e] = -mean * rstd;
-    }
-  }
+  norm_params8(st, P.inv_hw, P.eps, scale, shift);
   while (i0 < total) {
     i0 += 2 * stride;
     ApplyItem b0, b1;
@@ -187,33 +224,55 @@ __global__ void __launch_bounds__(256, 4) in_apply_kernel(const __grid_constant_
 // Row formulation: one warp per destination
 // row, lanes stride over the columns, four columns per lane in flight.  No division, the source row is resolved once per
 // row (mirror / zero halo rows), per unit only the column mirror remains.
-template <bool HAS_RES>
-__global__ void __launch_bounds__(256, 4) in_apply_rows_kernel(const __grid_constant__ ApplyParams P) {
+// HILO: split-precision activations (nhvr_act_desc.hilo): raw, residual and destination all carry hi + lo planes; the
+// value is rebuilt in fp32, normalised, and split again (the residual stream of a ResnetBlock keeps ~22 bits).
+template <bool HAS_RES, bool HILO>
+__global__ void __launch_bounds__(256, HILO ? 2 : 4) in_apply_rows_kernel(const __grid_constant__ ApplyParams P) {
   const ActGeom& g = P.dg;
-  const int np = blockIdx.y;
-  const int n = np / g.C8, p = np - n * g.C8;
-  const float4* st4 = reinterpret_cast<const float4*>(P.stats + ((int64_t)n * g.C8 + p) * 16);
-  const float4 q0 = __ldg(st4), q1 = __ldg(st4 + 1), q2 = __ldg(st4 + 2), q3 = __ldg(st4 + 3);
-  const uint4* raw = P.raw + ((int64_t)n * P.rg.C8 + p) * P.rg.plane_units;
-  const uint4* res = HAS_RES ? P.res + ((int64_t)n * P.sg.C8 + p) * P.sg.plane_units : nullptr;
-  uint4* dst = P.dst + (int64_t)np * g.plane_units;
+  const int np = blockIdx.y;                                  // n * (logical planes) + logical plane
+  const int CL = HILO ? g.C8 >> 1 : g.C8;
+  const int n = np / CL, p = np - n * CL;
+  const int ph = HILO ? hilo_plane(p) : p;                    // physical (hi) plane; the lo plane is 2 further
+  const double* st = P.stats + ((int64_t)n * CL + p) * 32;
+  const uint4* raw = P.raw + ((int64_t)n * P.rg.C8 + ph) * P.rg.plane_units;
+  const uint4* res = HAS_RES ? P.res + ((int64_t)n * P.sg.C8 + ph) * P.sg.plane_units : nullptr;
+  uint4* dst = P.dst + ((int64_t)n * g.C8 + ph) * g.plane_units;
+  const int64_t raw_lo = 2 * P.rg.plane_units, res_lo = 2 * P.sg.plane_units, dst_lo = 2 * g.plane_units;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float scale[8], shift[8];
-  {
-    const float sv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float mean = sv[2 * e] * P.inv_hw;
-      const float var = fmaxf(sv[2 * e + 1] * P.inv_hw - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + P.eps);
-      scale[e] = rstd;
-      shift[e] = -mean * rstd;
-    }
+  // mean / variance are formed in fp64 (see norm_params8) by 8 lanes, one channel each, and broadcast through shared
+  // memory: the fp64 pipe is narrow, 256 threads repeating the same 8 channels cost ~10 % of this kernel
+  __shared__ float s_norm[24];
+  if (threadIdx.x < 8) {
+    const double2 q = reinterpret_cast<const double2*>(st)[2 * threadIdx.x], r = reinterpret_cast<const double2*>(st)[2 * threadIdx.x + 1];
+    const double m0 = q.x * (double)P.inv_hw;
+    const double var = fmax(q.y * (double)P.inv_hw - m0 * m0, 0.0);
+    const float rstd = rsqrtf((float)var + P.eps);
+    s_norm[threadIdx.x] = rstd;
+    s_norm[8 + threadIdx.x] = -(float)(m0 + r.x) * rstd;
+    s_norm[16 + threadIdx.x] = (q.y + r.x * r.x < 4.29e9) ? 0.f : 1.f;     // range guard: see below
   }
+  __syncthreads();
+  float scale[8], shift[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { scale[e] = s_norm[e]; shift[e] = s_norm[8 + e]; }
   const bool reflect = g.halo != NHVR_HALO_ZERO;
   const uint64_t once = l2_policy_evict_first();      // the raw tensor is dead after this pass
-  constexpr int COLS = 5;            // 160 columns per pass: the 130-wide (128^2) rows take one pass, 258 two, 518 four
+  constexpr int COLS = HILO ? 3 : 5;   // 160 columns per pass: the 130-wide (128^2) rows take one pass, 258 two, 518 four
   const int Hq = g.Hp >> 1, Wq = g.Wp >> 1;
+  // Range guard (nhvr_set_overflow_flag): a 16-bit overflow of the conv output needs |x| > 65504, hence a plane whose
+  // sum of squares (taken from the un-rounded fp32 accumulators) reaches 65504^2.  Only such planes are scanned for
+  // inf / NaN units, in a separate loop so that the common path pays one comparison per block.
+  if (P.ovf) {
+    bool suspect = false;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) suspect |= s_norm[16 + e] != 0.f;
+    if (suspect) {
+      bool bad = false;
+      for (int y = blockIdx.x * 8 + warp; y < g.H; y += gridDim.x * 8)
+        for (int x = lane; x < g.W; x += 32) bad |= unit_nonfinite(raw[(int64_t)(y + P.rg.pad_t) * P.rg.Wp + P.rg.pad_l + x], P.f16);
+      if (bad) atomicOr(P.ovf, 1);
+    }
+  }
   for (int yy = blockIdx.x * 8 + warp; yy < g.Hp; yy += gridDim.x * 8) {
     int y = yy - g.pad_t;
     bool row_ok = (y >= 0) & (y < g.H);
@@ -225,6 +284,7 @@ __global__ void __launch_bounds__(256, 4) in_apply_rows_kernel(const __grid_cons
     const int64_t d_odd = g.split ? ((int64_t)(((yy & 1) << 1) | 1) * Hq + (yy >> 1)) * Wq : 0;
     for (int xx0 = lane; xx0 < g.Wp; xx0 += 32 * COLS) {
       ApplyItem it[COLS];
+      uint4 r2[HILO ? COLS : 1], s2[HILO ? COLS : 1];
 #pragma unroll
       for (int j = 0; j < COLS; ++j) {
         const int xx = xx0 + 32 * j;
@@ -238,14 +298,90 @@ __global__ void __launch_bounds__(256, 4) in_apply_rows_kernel(const __grid_cons
         it[j].du = g.split ? ((xx & 1) ? d_odd : d_even) + (xx >> 1) : d_even + xx;
         it[j].r = make_uint4(0, 0, 0, 0);
         it[j].s = make_uint4(0, 0, 0, 0);
+        if (HILO) { r2[j] = make_uint4(0, 0, 0, 0); s2[j] = make_uint4(0, 0, 0, 0); }
         if (ok) {
           it[j].r = ld_hint(rrow + x, once);
-          if (HAS_RES) it[j].s = __ldg(srow + x);
+          if (HILO) r2[j] = ld_hint(rrow + raw_lo + x, once);
+          if (HAS_RES) { it[j].s = __ldg(srow + x); if (HILO) s2[j] = __ldg(srow + res_lo + x); }
         }
       }
 #pragma unroll
-      for (int j = 0; j < COLS; ++j) apply_emit<HAS_RES>(P, scale, shift, dst, it[j]);
+      for (int j = 0; j < COLS; ++j) {
+        if (!HILO) { apply_emit<HAS_RES>(P, scale, shift, dst, it[j]); continue; }
+        if (!it[j].live) continue;
+        uint4 oh = make_uint4(0, 0, 0, 0), ol = oh;
+        if (it[j].ok) {
+          float xv[8], xl[8], rv[8], rl[8], v[8];
+          unpack8(it[j].r, xv, P.f16); unpack8(r2[HILO ? j : 0], xl, P.f16);
+          if (HAS_RES) { unpack8(it[j].s, rv, P.f16); unpack8(s2[HILO ? j : 0], rl, P.f16); }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float t = fmaf(xv[e] + xl[e], scale[e], shift[e]);
+            if (P.act == NHVR_ACT_RELU) t = fmaxf(t, 0.f);
+            else if (P.act == NHVR_ACT_LRELU02) t = t > 0.f ? t : 0.2f * t;
+            if (HAS_RES) t += rv[e] + rl[e];
+            v[e] = t;
+          }
+          split_hilo(v[0], v[1], P.f16, oh.x, ol.x); split_hilo(v[2], v[3], P.f16, oh.y, ol.y);
+          split_hilo(v[4], v[5], P.f16, oh.z, ol.z); split_hilo(v[6], v[7], P.f16, oh.w, ol.w);
+        }
+        dst[it[j].du] = oh;
+        dst[it[j].du + dst_lo] = ol;
+      }
     }
+  }
+}
+
+// Centring shift of a stem's InstanceNorm statistics: s[n][co] = sum_ci (sum_taps w[co][ci][tap]) * m[n][ci] with m the
+// (sampled) per-channel mean of the input image - the value the conv output takes wherever the input is flat.  Stick-
+// figure pose maps are ~98 % background, so the stem output is c + small with mean^2 / var up to ~250; centred sums
+// keep E[(x-s)^2] - E[x-s]^2 free of that cancellation.  Any s is mathematically valid (it only re-centres the sums).
+struct StemShiftParams {
+  const float* src[4];
+  int32_t src_c[4];
+  int32_t nsrc, Cin, Cout, taps, C8out8;
+  int64_t HW;
+  const float* w;      // [Cout][Cin][taps]
+  double* stats;       // [N][C8out8][4]: slot 2 receives s
+};
+__global__ void __launch_bounds__(256) stem_stat_shift_kernel(const __grid_constant__ StemShiftParams P) {
+  __shared__ float m[32];
+  __shared__ float red[8];
+  const int n = blockIdx.x;
+  const int64_t step = P.HW > 4096 ? P.HW / 4096 : 1;
+  int cbase = 0;
+  for (int s = 0; s < P.nsrc; ++s) {
+    for (int c = 0; c < P.src_c[s]; ++c) {
+      const float* p = P.src[s] + ((int64_t)n * P.src_c[s] + c) * P.HW;
+      float acc = 0.f;
+      int cnt = 0;
+      for (int64_t i = (int64_t)threadIdx.x * step; i < P.HW; i += 256 * step) { acc += __ldg(p + i); ++cnt; }
+      float tot = acc, num = (float)cnt;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { tot += __shfl_xor_sync(0xffffffffu, tot, o); num += __shfl_xor_sync(0xffffffffu, num, o); }
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = tot; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += red[k];
+        const int64_t nsamp = (P.HW + step - 1) / step;
+        if (cbase + c < 32) m[cbase + c] = t / (float)nsamp;
+      }
+      (void)num;
+    }
+    cbase += P.src_c[s];
+  }
+  __syncthreads();
+  for (int co = threadIdx.x; co < P.Cout; co += 256) {
+    float sft = 0.f;
+    for (int ci = 0; ci < P.Cin; ++ci) {
+      const float* wp = P.w + ((int64_t)co * P.Cin + ci) * P.taps;
+      float ws = 0.f;
+      for (int t = 0; t < P.taps; ++t) ws += wp[t];
+      sft += ws * m[ci];
+    }
+    P.stats[((int64_t)n * P.C8out8 + co) * 4 + 2] = (double)sft;
   }
 }
 
@@ -282,10 +418,35 @@ extern "C" int nhvr_pack_nchw(const float* const* src, const int32_t* src_c, int
   P.dst = reinterpret_cast<uint4*>(dst);
   P.g = make_geom(*dst_desc);
   P.f16 = operand_f16();
-  if (csum > P.g.C8 * 8) return NHVR_ERR_SHAPE;
+  if (P.g.hilo && (P.g.C8 & 3)) return NHVR_ERR_SHAPE;
+  if (csum > (P.g.hilo ? P.g.C8 / 2 : P.g.C8) * 8) return NHVR_ERR_SHAPE;
   const int planes = P.g.N * P.g.C8;
   dim3 grid(grid_x_for((int64_t)P.g.Hp * P.g.Wp, planes), planes);
   pack_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
+  return NHVR_OK;
+}
+
+extern "C" int nhvr_stem_stat_shift(const float* w, int32_t Cout, int32_t Cin, int32_t taps, const float* const* src, const int32_t* src_c,
+                                    int32_t nsrc, int32_t N, int32_t H, int32_t W, double* stats, void* stream) {
+  if (!w || !src || !src_c || !stats) return NHVR_ERR_NULL;
+  if (nsrc < 1 || nsrc > 4 || Cin < 1 || Cin > 32 || Cout < 1 || taps < 1 || N < 1 || H < 1 || W < 1) return NHVR_ERR_SHAPE;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  StemShiftParams P;
+  int csum = 0;
+  for (int i = 0; i < 4; ++i) {
+    P.src[i] = i < nsrc ? src[i] : nullptr;
+    P.src_c[i] = i < nsrc ? src_c[i] : 0;
+    if (i < nsrc) { if (!src[i] || src_c[i] <= 0) return NHVR_ERR_NULL; csum += src_c[i]; }
+  }
+  if (csum != Cin) return NHVR_ERR_SHAPE;
+  P.nsrc = nsrc; P.Cin = Cin; P.Cout = Cout; P.taps = taps;
+  P.C8out8 = ((Cout + 7) / 8 + 1) / 2 * 2 * 8;      // channel count of the statistics record: Cout8 (even) * 8
+  P.HW = (int64_t)H * W;
+  P.w = w; P.stats = stats;
+  stem_stat_shift_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(P);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
@@ -296,7 +457,8 @@ extern "C" int nhvr_unpack_nchw(const void* src, const nhvr_act_desc* src_desc, 
   if (!src || !src_desc || !dst) return NHVR_ERR_NULL;
   if (!arch_ok_cached()) return NHVR_ERR_ARCH;
   ActGeom g = make_geom(*src_desc);
-  if (C <= 0 || C > g.C8 * 8) return NHVR_ERR_SHAPE;
+  if (g.hilo && (g.C8 & 3)) return NHVR_ERR_SHAPE;
+  if (C <= 0 || C > (g.hilo ? g.C8 / 2 : g.C8) * 8) return NHVR_ERR_SHAPE;
   const int planes = g.N * ((C + 7) / 8);
   // planes beyond ceil(C/8) hold nothing we need; but blockIdx.y indexes n*C8+p, so launch all
   dim3 grid(grid_x_for((int64_t)g.H * g.W, g.N * g.C8), g.N * g.C8);
@@ -308,7 +470,7 @@ extern "C" int nhvr_unpack_nchw(const void* src, const nhvr_act_desc* src_desc, 
   return NHVR_OK;
 }
 
-extern "C" int nhvr_in_apply(const void* raw, const nhvr_act_desc* raw_desc, const float* stats, float eps, int32_t act,
+extern "C" int nhvr_in_apply(const void* raw, const nhvr_act_desc* raw_desc, const double* stats, float eps, int32_t act,
                              const void* residual, const nhvr_act_desc* res_desc, void* dst,
                              const nhvr_act_desc* dst_desc, void* stream) {
   if (!raw || !raw_desc || !stats || !dst || !dst_desc) return NHVR_ERR_NULL;
@@ -325,11 +487,14 @@ extern "C" int nhvr_in_apply(const void* raw, const nhvr_act_desc* raw_desc, con
   P.sg = residual ? make_geom(*res_desc) : P.dg;
   if (P.rg.N != P.dg.N || P.rg.C8 != P.dg.C8 || P.rg.H != P.dg.H || P.rg.W != P.dg.W) return NHVR_ERR_SHAPE;
   if (residual && (P.sg.N != P.dg.N || P.sg.C8 != P.dg.C8 || P.sg.H != P.dg.H || P.sg.W != P.dg.W)) return NHVR_ERR_SHAPE;
+  const int hilo = P.dg.hilo;
+  if (P.rg.hilo != hilo || (residual && P.sg.hilo != hilo) || (hilo && (P.dg.C8 & 3))) return NHVR_ERR_SHAPE;
+  P.ovf = overflow_flag();
   P.eps = eps;
   P.inv_hw = 1.0f / ((float)P.rg.H * (float)P.rg.W);
   P.act = act;
   P.f16 = operand_f16();
-  const int planes = P.dg.N * P.dg.C8;
+  const int planes = P.dg.N * (hilo ? P.dg.C8 / 2 : P.dg.C8);     // logical planes
   const int64_t units = (int64_t)P.dg.Hp * P.dg.Wp;
   int gx = (int)((units + 256 * 4 - 1) / (256 * 4));                      // two passes of two units per thread ...
   const int64_t cap = std::max<int64_t>(1, (int64_t)148 * 8 * 4 / std::max(1, planes));
@@ -343,8 +508,13 @@ extern "C" int nhvr_in_apply(const void* raw, const nhvr_act_desc* raw_desc, con
     int gy = std::max(1, (P.dg.Hp + 7) / 8);
     { static const char* e = std::getenv("NHVR_APPLY_GY"); if (e && std::atoi(e) > 0) gy = std::min(std::atoi(e), gy); }
     dim3 grid_r(gy, planes);
-    if (P.res) in_apply_rows_kernel<true><<<grid_r, 256, 0, (cudaStream_t)stream>>>(P);
-    else in_apply_rows_kernel<false><<<grid_r, 256, 0, (cudaStream_t)stream>>>(P);
+    if (hilo) {
+      if (P.res) in_apply_rows_kernel<true, true><<<grid_r, 256, 0, (cudaStream_t)stream>>>(P);
+      else in_apply_rows_kernel<false, true><<<grid_r, 256, 0, (cudaStream_t)stream>>>(P);
+    } else if (P.res) in_apply_rows_kernel<true, false><<<grid_r, 256, 0, (cudaStream_t)stream>>>(P);
+    else in_apply_rows_kernel<false, false><<<grid_r, 256, 0, (cudaStream_t)stream>>>(P);
+  } else if (hilo) {
+    return NHVR_ERR_UNSUPPORTED;
   } else if (P.res) in_apply_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
   else in_apply_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
   count_launch();
@@ -376,7 +546,7 @@ struct InBwdParams {
   const uint4* dx;         // P8 [N][C8][Hp][Wp] un-padded buffer
   const uint4* skip;       // nullable, P8 [N][C8][H][W]
   const uint4* raw;        // P8 [N][C8][H][W]
-  const float* stats;      // [N][C8*8][2] forward sums
+  const double* stats;     // [N][C8*8][2] forward sums (fp64)
   float* sums;             // [N][C8*8][2] backward sums (pass 1 out, pass 2 in)
   uint4* g;                // pass 2 out: gradient format
   uint4* dy_out;           // pass 2 out (nullable): folded dY, P8 [N][C8][H][W]
@@ -385,19 +555,8 @@ struct InBwdParams {
   int32_t N, C8;
   float eps, inv_hw;
   int32_t act, f16;
+  int32_t* ovf;            // nullable overflow flag (nhvr_set_overflow_flag)
 };
-
-NHVR_DEVINL void unpack8(const uint4& u, float (&v)[8], int f16) {
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int e = 0; e < 8; ++e) v[e] = (e & 1) ? unpack_hi(w[e >> 1], f16) : unpack_lo(w[e >> 1], f16);
-}
-NHVR_DEVINL uint4 pack8(const float (&v)[8], int f16) {
-  uint4 o;
-  o.x = pack2(v[0], v[1], f16); o.y = pack2(v[2], v[3], f16);
-  o.z = pack2(v[4], v[5], f16); o.w = pack2(v[6], v[7], f16);
-  return o;
-}
 
 // folded gradient of interior pixel (y, x) of plane np
 NHVR_DEVINL void fold_load(const InBwdParams& P, int64_t np, int y, int x, float (&dy)[8]) {
@@ -430,15 +589,7 @@ NHVR_DEVINL void fold_load(const InBwdParams& P, int64_t np, int y, int x, float
 }
 
 NHVR_DEVINL void fwd_norm_params(const InBwdParams& P, int64_t np, float (&scale)[8], float (&shift)[8]) {
-  const float* st = P.stats + np * 16;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const float mean = st[2 * e] * P.inv_hw;
-    const float var = fmaxf(st[2 * e + 1] * P.inv_hw - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + P.eps);
-    scale[e] = rstd;
-    shift[e] = -mean * rstd;
-  }
+  norm_params8(P.stats + np * 32, P.inv_hw, P.eps, scale, shift);
 }
 
 NHVR_DEVINL float act_grad(float z, int act) {
@@ -536,6 +687,7 @@ __global__ void __launch_bounds__(256, 2) in_bwd_rows_kernel(const __grid_consta
   float s1[8], s2[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
+  bool bad = false;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint4* dxp = P.dx + np * (int64_t)f.Hp * f.Wp;
   const uint4* rawp = P.raw + np * (int64_t)f.H * f.W;
@@ -593,6 +745,7 @@ __global__ void __launch_bounds__(256, 2) in_bwd_rows_kernel(const __grid_consta
         uint4 o = make_uint4(0, 0, 0, 0);
         if (ok[j]) {
           float dy[8], t[8], rv[8];
+          if (PASS == 1) bad |= unit_nonfinite(a[j], P.f16);
           unpack8(a[j], dy, P.f16);
           if (x1s[j] >= 0) { unpack8(__ldg(d0 + x1s[j]), t, P.f16);
 #pragma unroll
@@ -629,6 +782,7 @@ __global__ void __launch_bounds__(256, 2) in_bwd_rows_kernel(const __grid_consta
       }
     }
   }
+  if (PASS == 1 && bad && P.ovf) atomicOr(P.ovf, 1);
   if (PASS == 0) {
     __shared__ float sh[16][8];
 #pragma unroll
@@ -753,7 +907,7 @@ __global__ void __launch_bounds__(256) fold_unpack_kernel(const __grid_constant_
 }  // namespace nhvr
 
 static int make_in_bwd(InBwdParams& P, const void* dx, int32_t dx_H, int32_t dx_W, int32_t pad_t, int32_t pad_l, int32_t reflect,
-                       const void* skip, const void* raw, const nhvr_act_desc* raw_desc, const float* stats, float* sums, float eps,
+                       const void* skip, const void* raw, const nhvr_act_desc* raw_desc, const double* stats, float* sums, float eps,
                        int32_t act) {
   if (!dx || !raw_desc) return NHVR_ERR_NULL;
   const ActGeom rg = make_geom(*raw_desc);
@@ -768,6 +922,8 @@ static int make_in_bwd(InBwdParams& P, const void* dx, int32_t dx_H, int32_t dx_
   P.N = rg.N; P.C8 = rg.C8;
   P.eps = eps; P.inv_hw = 1.0f / ((float)rg.H * (float)rg.W);
   P.act = act; P.f16 = operand_f16();
+  P.ovf = overflow_flag();
+  if (rg.hilo) return NHVR_ERR_UNSUPPORTED;          // split precision is a forward-only (inference) format
   return NHVR_OK;
 }
 
@@ -779,7 +935,7 @@ static int make_in_bwd(InBwdParams& P, const void* dx, int32_t dx_H, int32_t dx_
   }
 
 extern "C" int nhvr_in_bwd(const void* dx, int32_t dx_H, int32_t dx_W, int32_t pad_t, int32_t pad_l, int32_t reflect,
-                           const void* skip, const void* raw, const nhvr_act_desc* raw_desc, const float* stats, float eps,
+                           const void* skip, const void* raw, const nhvr_act_desc* raw_desc, const double* stats, float eps,
                            int32_t act, float* sums, void* g, const nhvr_act_desc* g_desc, void* dy_out, void* stream) {
   if (!raw || !stats || !sums || !g || !g_desc) return NHVR_ERR_NULL;
   if (!arch_ok_cached()) return NHVR_ERR_ARCH;

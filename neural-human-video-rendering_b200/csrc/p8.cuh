@@ -12,6 +12,7 @@ struct ActGeom {
   int32_t pad_t, pad_l;
   int32_t Hp, Wp;       // padded (and, if split, even-rounded) extents
   int32_t split, halo;
+  int32_t hilo;         // split precision: C8 counts physical planes in groups [hi, hi, lo, lo]
   int64_t plane_units;  // 16-byte units per (n, plane)
 };
 
@@ -21,7 +22,7 @@ __host__ __device__ inline ActGeom make_geom(const nhvr_act_desc& d) {
   g.pad_t = d.pad_t; g.pad_l = d.pad_l;
   g.Hp = d.H + d.pad_t + d.pad_b;
   g.Wp = d.W + d.pad_l + d.pad_r;
-  g.split = d.split; g.halo = d.halo;
+  g.split = d.split; g.halo = d.halo; g.hilo = d.hilo;
   if (d.split) { g.Hp += g.Hp & 1; g.Wp += g.Wp & 1; }
   g.plane_units = (int64_t)g.Hp * g.Wp;
   return g;
@@ -39,6 +40,9 @@ __host__ __device__ inline int64_t plane_unit(const ActGeom& g, int32_t yy, int3
 __host__ __device__ inline int64_t act_unit(const ActGeom& g, int32_t n, int32_t p, int32_t yy, int32_t xx) {
   return ((int64_t)n * g.C8 + p) * g.plane_units + plane_unit(g, yy, xx);
 }
+
+// split precision: physical plane of logical plane lp (hi part; the lo part is 2 planes further)
+__host__ __device__ inline int32_t hilo_plane(int32_t lp) { return ((lp >> 1) << 2) | (lp & 1); }
 
 // ReflectionPad2d index map: logical coordinate (may be outside [0, n)) -> source inside [0, n)
 __host__ __device__ inline int32_t reflect_idx(int32_t i, int32_t n) {

@@ -72,7 +72,13 @@ class _ChainEngine:
     The last layer has norm=False and writes fp32 NCHW with bias + ``final_act``.
     """
 
-    def __init__(self, chain: List[dict], N: int, H: int, W: int, device, final_act: int, out_channels: int, train: bool = False):
+    def __init__(self, chain: List[dict], N: int, H: int, W: int, device, final_act: int, out_channels: int, train: bool = False,
+                 split3: bool = False):
+        """split3: split-precision inference engine (include/nhvr.h conv flag bit 3): every activation is a hilo pair,
+        every K step three MMAs - fp32-class results at 3x the tensor work (no backward)."""
+        assert not (train and split3), "split precision is an inference format"
+        self.split3 = split3
+        capi.overflow_flag(device)          # registers the range guard (fp16 overflow of a conv output / gradient)
         self.N, self.H, self.W = N, H, W
         self.train, self.final_act, self._bwd, self.busy = train, final_act, None, False
         self.device = device
@@ -89,7 +95,8 @@ class _ChainEngine:
             else:
                 epi, act = capi.EPI_BIAS_ACT_P8, L["act"]        # conv + bias + activation, no norm (D layer 0)
             plan = ops.ConvPlan(capi.CONV_TRANSPOSE if p.transposed else capi.CONV, p.cin, p.cout, p.k, p.stride, p.pad,
-                                N, h, w, L["halo"], epi, act, allow_tap_pairing=not train)
+                                N, h, w, L["halo"], epi, act, allow_tap_pairing=not train, split3=split3,
+                                centred_stats=(i == 0 and self._centres_stem(chain)))
             self.plans.append(plan)
             h, w = plan.Ho, plan.Wo
         self.out = torch.empty(N, out_channels, h, w, dtype=torch.float32, device=device)
@@ -117,7 +124,7 @@ class _ChainEngine:
                 live = chosen
             if i < len(self.plans) - 1 and chain[i].get("norm", True):
                 rd = plan.raw_desc()
-                rkey = (rd.N, rd.C8, rd.H, rd.W)
+                rkey = (rd.N, rd.C8, rd.H, rd.W, rd.hilo)
                 if train:                                   # backward re-reads every layer's raw output
                     self.raw_bufs.append(ops.P8Buffer(rd, device))
                     continue
@@ -127,8 +134,8 @@ class _ChainEngine:
             else:
                 self.raw_bufs.append(None)
         # InstanceNorm statistics: one zero-fill per forward
-        sizes = [N * pl.Cout8 * 8 * 2 if chain[i].get("norm", True) else 0 for i, pl in enumerate(self.plans[:-1])]
-        self.stats_all = torch.zeros(max(1, sum(sizes)), dtype=torch.float32, device=device)
+        sizes = [N * pl.Cout8 * 8 * 4 if chain[i].get("norm", True) else 0 for i, pl in enumerate(self.plans[:-1])]   # {sum, sum sq, shift, -}
+        self.stats_all = torch.zeros(max(1, sum(sizes)), dtype=torch.float64, device=device)     # fp64 sums (include/nhvr.h)
         self.stats: List[torch.Tensor] = []
         off = 0
         for s in sizes:
@@ -136,6 +143,13 @@ class _ChainEngine:
             off += s
         self.flops = sum(pl.flops for pl in self.plans)
         self.weight_versions: Optional[tuple] = None
+
+    @staticmethod
+    def _centres_stem(chain: List[dict]) -> bool:
+        """The first layer's InstanceNorm sums are centred (ops.stem_stat_shift) when it is a normalised, narrow-input conv."""
+        L0 = chain[0]
+        p0 = L0["params"]
+        return bool(L0.get("norm", True)) and not p0.transposed and p0.cin <= 32 and len(chain) > 1
 
     def pack_weights(self) -> None:
         for L, plan in zip(self.chain, self.plans):
@@ -148,8 +162,12 @@ class _ChainEngine:
             self.weight_versions = ver
 
     def run(self, inputs: Sequence[torch.Tensor]) -> torch.Tensor:
+        self.stats_all.zero_()
+        if self._centres_stem(self.chain):
+            # centre the stem's InstanceNorm sums on its response to the flat part of the input (stick-figure pose maps)
+            ops.stem_stat_shift(self.chain[0]["params"].weight, inputs, self.stats[0])
         ops.pack_nchw(inputs, self.in_bufs[0])
-        return self.run_packed()
+        return self.run_packed(zero_stats=False)
 
     # ------------------------------------------------------------------ backward (training engines only)
     def _build_backward(self) -> None:
@@ -278,9 +296,10 @@ class _ChainEngine:
         """Activation that feeds conv i (= output of layer i-1) as NCHW fp32 (D's intermediate features)."""
         return ops.unpack_nchw(self.in_bufs[i], self.chain[i]["params"].cin)
 
-    def run_packed(self) -> torch.Tensor:
+    def run_packed(self, zero_stats: bool = True) -> torch.Tensor:
         """Run the chain assuming in_bufs[0] already holds the packed input."""
-        self.stats_all.zero_()
+        if zero_stats:
+            self.stats_all.zero_()
         res_src: Optional[ops.P8Buffer] = None
         n = len(self.plans)
         for i, (L, plan) in enumerate(zip(self.chain, self.plans)):
@@ -365,6 +384,15 @@ class GlobalGeneratorB200(nn.Module):
             model += [_Slot("Tanh")]
         self.model = nn.Sequential(*model)
         self._engines: Dict[tuple, _ChainEngine] = {}
+        # inference precision: "f16" = one 16-bit operand per value (the global operand type, see capi.DEFAULT_OPERAND);
+        # "split3" = split precision (hi + lo operands, 3 MMAs per K step, fp32-class results)
+        self.precision = "f16"
+
+    def set_precision(self, precision: str) -> "GlobalGeneratorB200":
+        if precision not in ("f16", "split3"):
+            raise NhvrError("precision must be 'f16' or 'split3', got %r" % (precision,))
+        self.precision = precision
+        return self
 
     # ---- chain description -------------------------------------------------------------------
     def _chain(self) -> List[dict]:
@@ -399,13 +427,14 @@ class GlobalGeneratorB200(nn.Module):
             eng.busy = True
             eng.maybe_repack()
             return eng
-        key = (N, H, W, dev.index, train)
+        key = (N, H, W, dev.index, train, self.precision)
         eng = self._engines.get(key)
         if eng is None:
             capi.require_device()
             if dev.type != "cuda":
                 raise NhvrError("GlobalGeneratorB200 parameters must live on a CUDA device (call .cuda()); no CPU path")
-            eng = _ChainEngine(self._chain(), N, H, W, dev, self._final_act(), self.output_nc, train=train)
+            eng = _ChainEngine(self._chain(), N, H, W, dev, self._final_act(), self.output_nc, train=train,
+                               split3=self.precision == "split3")
             self._engines[key] = eng
         eng.maybe_repack()
         return eng
@@ -427,8 +456,9 @@ class GlobalGeneratorB200(nn.Module):
                 params += [Lr["params"].weight, Lr["params"].bias]
             return _ChainFunction.apply(eng, len(xs), 0, *xs, *params)
         eng = self.engine(N, H, W)
-        out = eng.run([t.float() for t in xs])
-        return out
+        # the engine's output buffer is persistent (the step graph reads it in place); callers of the module API get
+        # their own tensor, like every nn.Module of the reference
+        return eng.run([t.float() for t in xs]).clone()
 
 
 def define_G(input_nc, output_nc, ngf, netG="global", n_downsample_global=3, n_blocks_global=9, n_local_enhancers=1,

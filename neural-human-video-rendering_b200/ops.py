@@ -38,7 +38,7 @@ class _prof:
 
 
 def _act_interior_bytes(d: ActDesc) -> float:
-    return float(d.N) * d.C8 * d.H * d.W * 16.0
+    return float(d.N) * d.C8 * d.H * d.W * 16.0          # hilo: C8 is physical, both halves are really moved
 
 
 class P8Buffer:
@@ -55,11 +55,12 @@ class P8Buffer:
         return self.mem.data_ptr()
 
 
-def make_desc(N, C8, H, W, pad=(0, 0, 0, 0), split=0, halo=capi.HALO_ZERO) -> ActDesc:
+def make_desc(N, C8, H, W, pad=(0, 0, 0, 0), split=0, halo=capi.HALO_ZERO, hilo=0) -> ActDesc:
+    """hilo=1: split-precision activation (include/nhvr.h): pass the LOGICAL plane count, C8 becomes physical."""
     d = ActDesc()
-    d.N, d.C8, d.H, d.W = N, C8, H, W
+    d.N, d.C8, d.H, d.W = N, C8 * (2 if hilo else 1), H, W
     d.pad_t, d.pad_l, d.pad_b, d.pad_r = pad
-    d.split, d.halo = split, halo
+    d.split, d.halo, d.hilo = split, halo, hilo
     return d
 
 
@@ -82,6 +83,23 @@ def pack_nchw(srcs: Sequence[torch.Tensor], dst: P8Buffer) -> None:
         check(load().nhvr_pack_nchw(arr, cs, n, dst.ptr, C.byref(dst.desc), stream_ptr()), "nhvr_pack_nchw")
 
 
+def stem_stat_shift(weight: torch.Tensor, srcs: Sequence[torch.Tensor], stats: torch.Tensor) -> None:
+    """nhvr_stem_stat_shift: centre the (zeroed) statistics record of a first layer on the conv output of the flat input."""
+    n = len(srcs)
+    arr = (C.c_void_p * n)()
+    cs = (C.c_int32 * n)()
+    keep = [t.contiguous() for t in srcs]
+    for i, t in enumerate(keep):
+        assert t.dtype == torch.float32 and t.is_cuda
+        arr[i] = t.data_ptr()
+        cs[i] = t.shape[1]
+    w = weight.detach()
+    assert w.is_contiguous() and w.dtype == torch.float32
+    N, _, H, W = keep[0].shape
+    check(load().nhvr_stem_stat_shift(w.data_ptr(), w.shape[0], w.shape[1], w.shape[2] * w.shape[3], arr, cs, n, N, H, W,
+                                      stats.data_ptr(), stream_ptr()), "nhvr_stem_stat_shift")
+
+
 def unpack_nchw(src: P8Buffer, channels: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     d = src.desc
     if out is None:
@@ -94,11 +112,13 @@ class ConvPlan:
     """One conv layer lowered to the tcgen05 shift-GEMM kernel (nhvr_conv_plan_*)."""
 
     def __init__(self, kind, Cin, Cout, k, stride, pad, N, H, W, halo, epilogue, act=capi.ACT_NONE, in_extra_rows=0,
-                 in_extra_cols=0, out_hw=(0, 0), allow_tap_pairing: bool = False):
+                 in_extra_cols=0, out_hw=(0, 0), allow_tap_pairing: bool = False, split3: bool = False, centred_stats: bool = False):
         """allow_tap_pairing: flag bit 2 of nhvr_conv_desc - the input may use the single-plane tap-paired format
-        (only when no wgrad plan reads the same input buffer, i.e. inference engines)."""
+        (only when no wgrad plan reads the same input buffer, i.e. inference engines).
+        split3: flag bit 3 - split precision (hilo input / weights, three MMAs per K step, hilo RAW output)."""
         d = ConvDesc()
-        d.flags = 4 if allow_tap_pairing else 0
+        d.flags = (4 if allow_tap_pairing and not split3 else 0) | (8 if split3 else 0) | (16 if centred_stats else 0)
+        self.split3 = split3
         d.in_extra_rows, d.in_extra_cols = in_extra_rows, in_extra_cols
         d.out_h, d.out_w = out_hw
         d.kind, d.Cin, d.Cout, d.kh, d.kw, d.stride, d.pad = kind, Cin, Cout, k, k, stride, pad
@@ -134,8 +154,8 @@ class ConvPlan:
         return dict(zip(keys, list(arr)))
 
     def raw_desc(self) -> ActDesc:
-        """Descriptor of the RAW_STATS output (un-padded P8)."""
-        return make_desc(self.N, self.Cout8, self.Ho, self.Wo)
+        """Descriptor of the RAW_STATS output (un-padded P8; a hilo activation for split-precision plans)."""
+        return make_desc(self.N, self.Cout8, self.Ho, self.Wo, hilo=1 if self.split3 else 0)
 
     def pack_weights(self, w: torch.Tensor) -> torch.Tensor:
         w = w.detach().contiguous().float()
@@ -149,7 +169,7 @@ class ConvPlan:
     def forward(self, x: P8Buffer, out_ptr: int, bias: Optional[torch.Tensor] = None,
                 out_desc: Optional[ActDesc] = None, stats: Optional[torch.Tensor] = None) -> None:
         assert self.packed is not None, "pack_weights() first"
-        with _prof("conv", self.flops):
+        with _prof("conv3" if self.split3 else "conv", self.flops):
             check(load().nhvr_conv_forward(self.handle, x.ptr, self.packed.data_ptr(), ptr(bias), out_ptr,
                                            C.byref(out_desc) if out_desc is not None else None, ptr(stats), stream_ptr()),
                   "nhvr_conv_forward")

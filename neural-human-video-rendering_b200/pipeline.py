@@ -26,20 +26,38 @@ from .networks import define_G
 
 N_PARTS = 24
 UV_CHANNELS = 25 + 2 * N_PARTS
+PRECISION_PRESETS = {"strict": ("split3", "split3"), "balanced": ("split3", "f16"), "fast": ("f16", "f16")}
 
 
 class RenderPipeline(nn.Module):
     def __init__(self, pose_nc: int = 3, tex_nc: int = 3, size: int = 512, atlas_size: int = 200,
                  ngf_global: int = 48, n_downsample_global: int = 2, n_blocks_global: int = 10,
                  ngf_translate: int = 64, n_downsample_translate: int = 2, n_blocks_translate: int = 5,
-                 ngf_bg: int = 48, n_downsample_bg: int = 2, n_blocks_bg: int = 2, use_mask_texture: bool = True):
+                 ngf_bg: int = 48, n_downsample_bg: int = 2, n_blocks_bg: int = 2, use_mask_texture: bool = True,
+                 precision: str = "strict", uv_precision: Optional[str] = None, g_precision: Optional[str] = None):
+        """precision: inference operand precision preset (measured parity per mode in profiles/):
+          "strict"   UV generator, temporal generator and background net in split precision (3 x fp16 MMAs, fp32-class):
+                     the mode that meets north_star's 2e-2 / 45 dB on the reference's real configuration - default;
+          "balanced" UV generator in split precision, the others fp16: PSNR ~67 dB, max-abs ~2e-2 at the few pixels where
+                     InstanceNorm of a stick-figure pose map produces |z| ~ 25-50 (fp16 is relative precision);
+          "fast"     everything fp16: PSNR >= 50 dB on a texture-like atlas, UV error ~3e-2 (1.5 texels).
+        uv_precision / g_precision ("f16" | "split3") override the preset per network."""
         super().__init__()
+        if precision not in PRECISION_PRESETS:
+            raise ValueError("precision must be one of %s" % sorted(PRECISION_PRESETS))
+        uv_precision = uv_precision or PRECISION_PRESETS[precision][0]
+        g_precision = g_precision or PRECISION_PRESETS[precision][1]
+        self.precision = next((k for k, v in PRECISION_PRESETS.items() if v == (uv_precision, g_precision)), "custom")
         self.pose_nc, self.tex_nc, self.size, self.atlas_size = pose_nc, tex_nc, size, atlas_size
         self.use_mask_texture = use_mask_texture
         self.netTransG = define_G(pose_nc, UV_CHANNELS, ngf_translate, "translate", n_downsample_translate,
                                   n_blocks_translate)
         self.netG = define_G(tex_nc + pose_nc + 3, 4, ngf_global, "temporal", n_downsample_global, n_blocks_global)
         self.netBG = define_G(3, 3, ngf_bg, "bg", n_downsample_bg, n_blocks_bg)
+        self.uv_precision, self.g_precision = uv_precision, g_precision
+        self.netTransG.set_precision(uv_precision)
+        self.netG.set_precision(g_precision)
+        self.netBG.set_precision(g_precision)
         self.atlas = nn.Parameter(torch.empty(N_PARTS, tex_nc, atlas_size, atlas_size).uniform_(-1, 1))
         self.bg = nn.Parameter(torch.empty(3, size, size).uniform_(-1, 1))
         self._atlas_cl: Optional[torch.Tensor] = None
@@ -107,12 +125,17 @@ class RenderPipeline(nn.Module):
         return out
 
     def step_graph(self, B: int, H: int, W: int, use_graph: bool = True) -> "_StepGraph":
-        key = (B, H, W, use_graph)
+        key = (B, H, W, use_graph, self.netTransG.precision, self.netG.precision, self.netBG.precision, self.use_mask_texture)
         g = self._graphs.get(key)
         if g is None:
             g = _StepGraph(self, B, H, W, use_graph)
             self._graphs[key] = g
+        g.refresh()           # weights / atlas / background may have changed since the graph was captured
         return g
+
+    def state_version(self) -> tuple:
+        """Changes whenever a parameter is modified in place or re-assigned (optimizer step, load_state_dict, .to())."""
+        return tuple((p._version, p.data_ptr()) for p in self.parameters())
 
 
 class _StepGraph:
@@ -125,14 +148,23 @@ class _StepGraph:
         self.pose = torch.zeros(B, pipe.pose_nc, H, W, dtype=torch.float32, device=dev)
         self.prev = torch.zeros(B, 3, H, W, dtype=torch.float32, device=dev)
         self.out = self.prev          # the composite writes the next step's previous frame in place
+        # persistent copies the captured graph points at: refreshed IN PLACE when the parameters change (refresh())
         self.bg_refined = pipe.refine_bg()
+        self.atlas_cl = pipe.atlas_channels_last().clone()
         self.engT = pipe.netTransG.engine(B, H, W)
         self.engG = pipe.netG.engine(B, H, W)
+        self._version = pipe.state_version()
         self.tex = torch.empty(B, pipe.tex_nc, H, W, dtype=torch.float32, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._stage = None
         self.launches_per_step = 0
-        if use_graph:
+        self.use_graph = use_graph
+        self._capture()
+
+    def _capture(self) -> None:
+        dev = self.pose.device
+        self.graph = None
+        if self.use_graph:
             # warm up on a side stream (attribute set-up, weight packing), then capture
             s = torch.cuda.Stream(device=dev)
             s.wait_stream(torch.cuda.current_stream())
@@ -157,6 +189,22 @@ class _StepGraph:
 
     def reset(self) -> None:
         self.prev.zero_()
+
+    def refresh(self) -> None:
+        """Re-pack weights, re-evaluate the background net and re-copy the atlas if any parameter changed since the
+        last call (training step, load_state_dict): everything is updated in the buffers the captured graph reads."""
+        ver = self.pipe.state_version()
+        if ver == self._version:
+            return
+        moved = tuple(v[1] for v in ver) != tuple(v[1] for v in self._version)
+        B, H, W = self.pose.shape[0], self.pose.shape[2], self.pose.shape[3]
+        self.engT = self.pipe.netTransG.engine(B, H, W)       # same cached engines; engine() re-packs changed weights
+        self.engG = self.pipe.netG.engine(B, H, W)
+        self.bg_refined.copy_(self.pipe.refine_bg())
+        self.atlas_cl.copy_(self.pipe.atlas_channels_last())
+        self._version = ver
+        if moved and self.graph is not None:
+            self._capture()         # parameters were re-allocated: the captured bias pointers are stale
 
     def _staging(self):
         if self._stage is None:
@@ -224,8 +272,7 @@ class _StepGraph:
     def _body(self) -> None:
         pipe = self.pipe
         uvp = self.engT.run([self.pose])
-        ops.texture_sample(uvp, pipe.atlas_channels_last(), pipe.tex_nc, pipe.use_mask_texture, tex_out=self.tex,
-                           want_indices=False)
+        ops.texture_sample(uvp, self.atlas_cl, pipe.tex_nc, pipe.use_mask_texture, tex_out=self.tex, want_indices=False)
         fgm = self.engG.run([self.tex, self.pose, self.prev])
         ops.composite(fgm, self.bg_refined, out=self.prev)
 

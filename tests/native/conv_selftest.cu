@@ -40,7 +40,7 @@ static int run_case(const Case& c) {
   for (auto& v : h_w) v = bf16r(frand() * 0.1f);
   for (auto& v : h_b) v = frand() * 0.5f;
 
-  float *d_in, *d_w, *d_b, *d_out32, *d_stats;
+  float *d_in, *d_w, *d_b, *d_out32; double* d_stats;
   void *d_p8, *d_wp, *d_raw;
   CK(cudaMalloc(&d_in, in_elems * 4)); CK(cudaMalloc(&d_w, w_elems * 4)); CK(cudaMalloc(&d_b, c.Cout * 4));
   CK(cudaMemcpy(d_in, h_in.data(), in_elems * 4, cudaMemcpyHostToDevice));
@@ -53,7 +53,7 @@ static int run_case(const Case& c) {
   CK(cudaMalloc(&d_out32, out_elems * 4)); CK(cudaMemset(d_out32, 0, out_elems * 4));
   nhvr_act_desc raw_desc{}; raw_desc.N = c.N; raw_desc.C8 = Cout8; raw_desc.H = Ho; raw_desc.W = Wo;
   CK(cudaMalloc(&d_raw, nhvr_act_bytes(&raw_desc))); CK(cudaMemset(d_raw, 0, nhvr_act_bytes(&raw_desc)));
-  CK(cudaMalloc(&d_stats, (size_t)c.N * Cout8 * 8 * 2 * 4)); CK(cudaMemset(d_stats, 0, (size_t)c.N * Cout8 * 8 * 2 * 4));
+  CK(cudaMalloc(&d_stats, (size_t)c.N * Cout8 * 8 * 4 * 8)); CK(cudaMemset(d_stats, 0, (size_t)c.N * Cout8 * 8 * 4 * 8));
 
   const float* srcs[1] = {d_in}; int32_t sc[1] = {c.Cin};
   NK(nhvr_pack_nchw(srcs, sc, 1, d_p8, &in_desc, 0));
@@ -64,7 +64,7 @@ static int run_case(const Case& c) {
   const int iters = 5;
   float ms = 0.f;
   for (int it = 0; it < iters + 1; ++it) {
-    if (c.epi == NHVR_EPI_RAW_STATS) CK(cudaMemsetAsync(d_stats, 0, (size_t)c.N * Cout8 * 8 * 2 * 4, 0));
+    if (c.epi == NHVR_EPI_RAW_STATS) CK(cudaMemsetAsync(d_stats, 0, (size_t)c.N * Cout8 * 8 * 4 * 8, 0));
     if (it == 1) CK(cudaEventRecord(e0, 0));
     if (c.epi == NHVR_EPI_RAW_STATS) NK(nhvr_conv_forward(plan, d_p8, d_wp, nullptr, d_raw, nullptr, d_stats, 0));
     else if (c.epi == NHVR_EPI_BIAS_ACT_F32) NK(nhvr_conv_forward(plan, d_p8, d_wp, d_b, d_out32, nullptr, nullptr, 0));
@@ -76,13 +76,13 @@ static int run_case(const Case& c) {
   CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= iters;
 
   std::vector<float> h_out(out_elems);
-  std::vector<float> h_stats((size_t)c.N * Cout8 * 8 * 2);
+  std::vector<double> h_stats((size_t)c.N * Cout8 * 8 * 4);
   if (c.epi == NHVR_EPI_BIAS_ACT_F32) {
     CK(cudaMemcpy(h_out.data(), d_out32, out_elems * 4, cudaMemcpyDeviceToHost));
   } else {
     NK(nhvr_unpack_nchw(d_raw, &raw_desc, d_out32, c.Cout, 0));
     CK(cudaMemcpy(h_out.data(), d_out32, out_elems * 4, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(h_stats.data(), d_stats, h_stats.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h_stats.data(), d_stats, h_stats.size() * 8, cudaMemcpyDeviceToHost));
   }
 
   // ---- CPU reference
@@ -151,7 +151,7 @@ static int run_case(const Case& c) {
       for (int co = 0; co < c.Cout; ++co) {
         double s = 0, ss = 0;
         for (size_t i = 0; i < (size_t)Ho * Wo; ++i) { const double v = ref[((size_t)n * c.Cout + co) * Ho * Wo + i]; s += v; ss += v * v; }
-        const double gs = h_stats[((size_t)n * Cout8 * 8 + co) * 2], gss = h_stats[((size_t)n * Cout8 * 8 + co) * 2 + 1];
+        const double gs = h_stats[((size_t)n * Cout8 * 8 + co) * 4], gss = h_stats[((size_t)n * Cout8 * 8 + co) * 4 + 1];
         const double e1 = fabs(gs - s) / (1.0 + fabs(s)) , e2 = fabs(gss - ss) / (1.0 + fabs(ss));
         stat_err = fmax(stat_err, fmax(e1, e2));
       }
@@ -224,11 +224,11 @@ int main(int argc, char** argv) {
       if (nhvr_conv_plan_create(&d, &plan) != 0) { printf("%s plan failed\n", c.name); ++fails; continue; }
       nhvr_act_desc in_desc; nhvr_conv_input_desc(plan, &in_desc);
       int Ho, Wo, Cout8; nhvr_conv_output_dims(plan, &Ho, &Wo, &Cout8);
-      void *d_p8, *d_wp, *d_out; float* d_stats;
+      void *d_p8, *d_wp, *d_out; double* d_stats;
       CK(cudaMalloc(&d_p8, nhvr_act_bytes(&in_desc))); CK(cudaMemset(d_p8, 0, nhvr_act_bytes(&in_desc)));
       CK(cudaMalloc(&d_wp, nhvr_conv_weight_bytes(plan))); CK(cudaMemset(d_wp, 0, nhvr_conv_weight_bytes(plan)));
       const size_t ob = (size_t)c.N * Cout8 * 8 * Ho * Wo * 4 + (1 << 20);
-      CK(cudaMalloc(&d_out, ob)); CK(cudaMalloc(&d_stats, (size_t)c.N * Cout8 * 16 * 4)); CK(cudaMemset(d_stats, 0, (size_t)c.N * Cout8 * 16 * 4));
+      CK(cudaMalloc(&d_out, ob)); CK(cudaMalloc(&d_stats, (size_t)c.N * Cout8 * 32 * 8)); CK(cudaMemset(d_stats, 0, (size_t)c.N * Cout8 * 32 * 8));
       cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
       const int iters = (only > 100) ? 3 : 20;
       for (int it = 0; it < iters + 3; ++it) {

@@ -152,10 +152,10 @@ def _conv_case(dev, kind, cin, cout, k, stride, pad, N, H, W, halo, epi, act, en
     stat_err = 0.0
     if epi == capi.EPI_RAW_STATS:
         raw = ops.P8Buffer(plan.raw_desc(), dev)
-        stats = torch.zeros(N * plan.Cout8 * 8 * 2, dtype=torch.float32, device=dev)
+        stats = torch.zeros(N * plan.Cout8 * 8 * 4, dtype=torch.float64, device=dev)
         plan.forward(xin, raw.ptr, stats=stats)
         out = ops.unpack_nchw(raw, cout)
-        st = stats.view(N, plan.Cout8 * 8, 2)[:, :cout].double()
+        st = stats.view(N, plan.Cout8 * 8, 4)[:, :cout, :2].double()
         s_ref = torch.stack([ref.double().sum((2, 3)), (ref.double() ** 2).sum((2, 3))], -1)
         stat_err = ((st - s_ref).abs() / (1.0 + s_ref.abs())).max().item()
     else:
@@ -183,6 +183,9 @@ def _conv_case(dev, kind, cin, cout, k, stride, pad, N, H, W, halo, epi, act, en
     # transposed conv with the N split (4 accumulators x 64 columns), row mode head
     ("convT_split", None, "CONV_TRANSPOSE", 64, 128, 3, 2, 1, 1, 24, 40, "Z", "RAW_STATS", "NONE", dict(nsplit=2)),
     ("rowmode_head", None, "CONV", 48, 4, 7, 1, 3, 1, 40, 150, "R", "BIAS_ACT_F32", "TANH", dict(njobs=7)),
+    # row mode with 4 stacked output rows per tile (shuffle epilogue): ragged right edge (300 = 2 x 122 + 56), 130 rows = 32 x 4 + 2
+    ("rowmode_head_mrep", None, "CONV", 48, 4, 7, 1, 3, 2, 130, 300, "R", "BIAS_ACT_F32", "TANH", dict(njobs=7, slab_min=1200)),
+    ("rowmode_5x5_3out", None, "CONV", 24, 3, 5, 1, 2, 3, 67, 140, "Z", "BIAS_ACT_F32", "NONE", dict(njobs=5)),
 ])
 def test_conv_lowering_variants(cuda_dev, name, env, kind, cin, cout, k, stride, pad, N, H, W, halo, epi, act, expect):
     """Every lowering of the shift-GEMM kernel (CTA pair / M replication / N split / row mode) at a size where the
@@ -331,9 +334,8 @@ def test_pipeline_1024_laplace_stage_parity(cuda_dev):
 
 def test_pipeline_free_running(cuda_dev):
     """Whole path free-running (its own UV-generator output feeds the lookup, its own frames feed back),
-    eager and CUDA-graph.  16-bit UV-generator error (~1e-2 of a texel range) is multiplied by the texture
-    gradient in the lookup, so the end-to-end bound is looser than the per-stage one: PSNR >= 40 dB and
-    max-abs <= 6e-2 on a smooth atlas (measured margins are in DESIGN.md)."""
+    eager and CUDA-graph, small configuration, default ("strict", split precision) mode: north_star's 2e-2 / 45 dB over
+    3 frames (the full-size configuration and the recurrence's own error growth: tests/test_gpu_split3.py)."""
     pipe, ref = _pair_pipeline(cuda_dev, _small_kw())
     poses = torch.rand(3, 3, 64, 64, device=cuda_dev) * 2 - 1
     frames_ref = ref.render_clip(poses)
@@ -341,8 +343,8 @@ def test_pipeline_free_running(cuda_dev):
     for use_graph in (False, True):
         frames = pipe.render_clip(poses, use_graph=use_graph)
         outs.append(frames)
-        assert psnr(frames, frames_ref) >= 40.0, (use_graph, psnr(frames, frames_ref))
-        assert (frames - frames_ref).abs().max().item() <= 6e-2, (use_graph, (frames - frames_ref).abs().max().item())
+        assert psnr(frames, frames_ref) >= 45.0, (use_graph, psnr(frames, frames_ref))
+        assert (frames - frames_ref).abs().max().item() <= 2e-2, (use_graph, (frames - frames_ref).abs().max().item())
     assert (outs[0] - outs[1]).abs().max().item() <= 5e-3          # graph replay == eager up to atomic-order noise
 
 

@@ -28,31 +28,34 @@ def main():
     kw = dict(PIPE_KW); kw["size"] = size
     torch.manual_seed(0)
     ref = RenderModel(**kw).to(dev).eval()
-    poses = synthetic_poses(1, 3)[0].to(dev)
+    NT = 6
+    poses = synthetic_poses(1, NT)[0].to(dev)
     if size != 512:
         poses = torch.nn.functional.interpolate(poses, size=(size, size), mode="bilinear")
     with torch.no_grad():
         bg_r = ref.refine_bg()
         prev = torch.zeros(1, 3, size, size, device=dev)
         refs = []
-        for t in range(3):
+        for t in range(NT):
             r = ref.render_frame(poses[t:t + 1], prev, bg_r)
             prev = r["out"]
             refs.append(r)
-    for mode in ("bf16", "f16"):
-        capi.set_operand_dtype(mode)
-        pipe = RenderPipeline(**kw).to(dev)
+    for mode in ("bf16", "f16", "split3-uv", "split3-all"):
+        capi.set_operand_dtype("bf16" if mode == "bf16" else "f16")
+        prec = {"uv_precision": "split3" if mode.startswith("split3") else "f16", "g_precision": "split3" if mode == "split3-all" else "f16"}
+        pipe = RenderPipeline(**kw, **prec).to(dev)
         pipe.load_state_dict(ref.state_dict())
         with torch.no_grad():
             bg = pipe.refine_bg()
             print("[%s] bg     max-abs %.4e psnr %.1f" % (mode, (bg - bg_r).abs().max().item(), psnr(bg, bg_r)))
             prev = torch.zeros(1, 3, size, size, device=dev)
-            for t in range(3):
+            for t in range(NT):
                 r = pipe.render_frame(poses[t:t + 1], prev, bg)
                 prev = r["out"]
                 o = refs[t]
                 same_part = (r["part"] == o["part"]).float().mean().item()
                 # G_main fed with the ORACLE's inputs isolates the conv chain from upstream argmax flips
+                t0 = time.perf_counter()
                 fgm_iso = pipe.netG(o["tex"].contiguous(), poses[t:t + 1], (refs[t - 1]["out"] if t else torch.zeros_like(prev)))
                 print("[%s] t=%d uvp max-abs %.3e (|ref| max %.2f) | part agree %.5f | tex %.3e | fgm %.3e | fgm(iso) %.3e psnr %.1f | out %.3e psnr %.1f"
                       % (mode, t, (r["uvp"] - o["uvp"]).abs().max().item(), o["uvp"].abs().max().item(), same_part,
