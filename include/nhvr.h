@@ -195,11 +195,12 @@ size_t nhvr_wgrad_workspace_bytes(const nhvr_wgrad_plan* p);
 int nhvr_wgrad(const nhvr_wgrad_plan* p, const void* x, const void* g, void* workspace, float* dw, float scale,
                int32_t accumulate, void* stream);
 
-/* ---- backward of the texture lookup (use_mask_texture variant) and of the composite ----
+/* ---- backward of the texture lookup (both blends: --use_mask_texture of start.sh:18, and the renormalised one
+ * train_start/pretrain_start.sh runs with) and of the composite ----
  * grad_uvp float [N][73][H][W] is fully written; grad_atlas float [24][S][S][Ct4] (channels-last, zeroed by the
  * caller) receives vector reductions. */
 int nhvr_texture_sample_bwd(const float* uvp, const float* atlas, const float* grad_tex, int32_t N, int32_t H, int32_t W,
-                            int32_t S, int32_t Ctex, float* grad_uvp, float* grad_atlas, void* stream);
+                            int32_t S, int32_t Ctex, int32_t use_mask_texture, float* grad_uvp, float* grad_atlas, void* stream);
 /* grad_fgm float [N][4][H][W]; grad_bg float [3][H][W] (summed over the batch) or [N][3][H][W] if bg_batched */
 int nhvr_composite_bwd(const float* fgm, const float* bg, int32_t bg_batched, const float* grad_out, int32_t N, int32_t H,
                        int32_t W, float* grad_fgm, float* grad_bg, void* stream);

@@ -73,7 +73,7 @@ SYMBOLS = {
     "nhvr_texture_sample": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P,
                                       _P, _P]),
     "nhvr_composite": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
-    "nhvr_texture_sample_bwd": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
+    "nhvr_texture_sample_bwd": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     "nhvr_composite_bwd": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     "nhvr_loss_pair_bwd": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_float, C.c_float, _P, C.c_int32, _P, _P]),
     "nhvr_avgpool3s2_bwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),

@@ -208,7 +208,7 @@ namespace nhvr {
 template <int G>
 __global__ void __launch_bounds__(128) texture_sample_bwd_kernel(const float* __restrict__ uvp, const float4* __restrict__ atlas,
                                                                  const float* __restrict__ gtex, int N, int H, int W, int S, int Ctex,
-                                                                 float* __restrict__ guvp, float* __restrict__ gatlas) {
+                                                                 int use_mask, float* __restrict__ guvp, float* __restrict__ gatlas) {
   const int64_t HW = (int64_t)H * W;
   const int64_t total = (int64_t)N * HW;
   const float sm1 = (float)(S - 1);
@@ -228,6 +228,14 @@ __global__ void __launch_bounds__(128) texture_sample_bwd_kernel(const float* __
 #pragma unroll
     for (int k = 0; k < 25; ++k) { lg[k] = __expf(lg[k] - mx); den += lg[k]; }
     const float inv_den = 1.f / den;
+    // without --use_mask_texture the blend is renormalised: tex = S / D with S the masked blend and D = 1 - P0 + 1e-6.
+    // dL/dS = g / D (applied by scaling g here), dL/dD = -(g . S) / D^2 flows into the logits through P0 (below)
+    const float p0 = lg[0] * inv_den;
+    const float invD = use_mask ? 1.f : 1.f / (1.f - p0 + 1e-6f);
+    if (!use_mask) {
+#pragma unroll
+      for (int c = 0; c < 4 * G; ++c) g[c] *= invD;
+    }
     float tdot = 0.f;           // sum_c g_c * tex_c = sum_k P_k a_k
     float a[25];
     a[0] = 0.f;
@@ -277,8 +285,13 @@ __global__ void __launch_bounds__(128) texture_sample_bwd_kernel(const float* __
       gb[(int64_t)(24 + k) * HW] = cu * dfx;
       gb[(int64_t)(48 + k) * HW] = cv2 * dfy;
     }
+    // (g' . S) = tdot with the scaled g'; dL/dD = -tdot / D; dD/dlogit_j = P0 P_j - [j == 0] P0
+    const float gD = use_mask ? 0.f : -tdot * invD;
 #pragma unroll
-    for (int k = 0; k < 25; ++k) gb[(int64_t)k * HW] = lg[k] * inv_den * (a[k] - tdot);
+    for (int k = 0; k < 25; ++k) {
+      const float pj = lg[k] * inv_den;
+      gb[(int64_t)k * HW] = pj * (a[k] - tdot) + gD * p0 * (pj - (k == 0 ? 1.f : 0.f));
+    }
   }
 }
 
@@ -313,7 +326,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const float* __restr
 }  // namespace nhvr
 
 extern "C" int nhvr_texture_sample_bwd(const float* uvp, const float* atlas, const float* grad_tex, int32_t N, int32_t H, int32_t W,
-                                       int32_t S, int32_t Ctex, float* grad_uvp, float* grad_atlas, void* stream) {
+                                       int32_t S, int32_t Ctex, int32_t use_mask_texture, float* grad_uvp, float* grad_atlas, void* stream) {
   if (!uvp || !atlas || !grad_tex || !grad_uvp || !grad_atlas) return NHVR_ERR_NULL;
   if (N <= 0 || H <= 0 || W <= 0 || S < 2 || Ctex <= 0 || Ctex > 20) return NHVR_ERR_SHAPE;
   if ((((uintptr_t)atlas | (uintptr_t)grad_atlas) & 15) != 0) return NHVR_ERR_ALIGN;
@@ -323,7 +336,7 @@ extern "C" int nhvr_texture_sample_bwd(const float* uvp, const float* atlas, con
   const int blocks = (int)std::min<int64_t>((total + 127) / 128, (int64_t)148 * 16 * 8);
   const float4* a4 = reinterpret_cast<const float4*>(atlas);
   cudaStream_t st = (cudaStream_t)stream;
-#define NHVR_LAUNCH_SBWD(GG) texture_sample_bwd_kernel<GG><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, grad_uvp, grad_atlas)
+#define NHVR_LAUNCH_SBWD(GG) texture_sample_bwd_kernel<GG><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, use_mask_texture, grad_uvp, grad_atlas)
   switch (G) {
     case 1: NHVR_LAUNCH_SBWD(1); break;
     case 2: NHVR_LAUNCH_SBWD(2); break;

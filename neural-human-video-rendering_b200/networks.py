@@ -15,6 +15,8 @@ there is no fallback: a CPU tensor or a missing library raises.
 """
 from __future__ import annotations
 
+import math
+import weakref
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -218,8 +220,36 @@ class _ChainEngine:
         self._bwd = B
         self._bwd_versions = None
 
+    def _grad_scale(self, grad_out: torch.Tensor, extra: Dict[int, torch.Tensor]) -> float:
+        """Power-of-two scale that keeps the 16-bit gradient operands in range (max |g| ~ 64), WITHOUT a host
+        synchronisation per step: the maximum is reduced on the device and copied to pinned host memory asynchronously;
+        the scale used now comes from the most recent copy that has completed (the first call waits once).  Gradient
+        magnitudes drift slowly and fp16 leaves 2^10 of headroom above 64; an overflow would raise through the range
+        guard (capi.check_overflow)."""
+        amax = torch.stack([grad_out.abs().max()] + [g.abs().max() for g in extra.values()]).max().float()
+        st = getattr(self, "_amax_state", None)
+        if st is None:
+            st = self._amax_state = {"host": torch.zeros(1, dtype=torch.float32).pin_memory(), "evt": torch.cuda.Event(), "S": None,
+                                     "pending": False}
+        if st["pending"] and (st["S"] is None or st["evt"].query()):
+            st["evt"].synchronize()
+            a = float(st["host"][0])
+            if a > 0.0 and math.isfinite(a):
+                st["S"] = 2.0 ** round(math.log2(64.0 / a))
+            st["pending"] = False
+        if not st["pending"]:
+            st["host"].copy_(amax.reshape(1), non_blocking=True)
+            st["evt"].record()
+            st["pending"] = True
+        if st["S"] is None:                                  # very first backward of this engine: one blocking read
+            st["evt"].synchronize()
+            a = float(st["host"][0])
+            st["S"] = 2.0 ** round(math.log2(64.0 / a)) if (a > 0.0 and math.isfinite(a)) else 1.0
+            st["pending"] = False
+        return st["S"]
+
     def backward(self, grad_out: Optional[torch.Tensor], need_input_grad: bool, in_channels: int,
-                 extra_grads: Optional[Dict[int, torch.Tensor]] = None):
+                 extra_grads: Optional[Dict[int, torch.Tensor]] = None, need_weight_grad: bool = True):
         """Gradients of the chain: (input_grad NCHW fp32 or None, [dW per layer], [db per layer or None]).
 
         extra_grads[i] (i >= 1): additional gradient w.r.t. the activation that feeds conv i (the discriminator's
@@ -238,9 +268,7 @@ class _ChainEngine:
         if grad_out is None:
             grad_out = torch.zeros_like(self.out)
         grad_out = grad_out.contiguous().float()
-        # static gradient scale: keeps 16-bit gradient operands in range (fp16), exact power of two
-        amax = float(max([grad_out.abs().max()] + [g.abs().max() for g in extra_grads.values()]))
-        S = 1.0 if amax == 0.0 or not (amax == amax) else 2.0 ** round(__import__("math").log2(64.0 / amax))
+        S = self._grad_scale(grad_out, extra_grads)       # exact power of two, no per-step host sync
         inv_S = 1.0 / S
         self._last_S = S
         g_pre = ops.head_bwd(self.out, grad_out, self.final_act, S)
@@ -252,9 +280,10 @@ class _ChainEngine:
         input_grad = None
         for i in range(L - 1, -1, -1):
             Lr, plan = self.chain[i], self.plans[i]
-            dW = torch.empty_like(Lr["params"].weight, dtype=torch.float32)
-            B["wplans"][i].run(self.in_bufs[i], B["G"][i], B["ws"], dW, inv_S)
-            dWs[i] = dW
+            if need_weight_grad:                             # frozen discriminator under the generator loss: input grads only
+                dW = torch.empty_like(Lr["params"].weight, dtype=torch.float32)
+                B["wplans"][i].run(self.in_bufs[i], B["G"][i], B["ws"], dW, inv_S)
+                dWs[i] = dW
             if i == 0 and not need_input_grad:
                 break
             dX = B["dX"][i]
@@ -322,6 +351,10 @@ class _ChainEngine:
         return self.out
 
 
+def _release_engine(eng) -> None:
+    eng.busy = False
+
+
 class _ChainFunction(torch.autograd.Function):
     """Differentiable wrapper of a conv chain: forward and backward both run on the sm_100a kernels.
     With n_feats > 0 the intermediate activations feeding convs 1..n_feats are returned too (discriminator)."""
@@ -330,6 +363,9 @@ class _ChainFunction(torch.autograd.Function):
     def forward(ctx, eng: "_ChainEngine", n_inputs: int, n_feats: int, *tensors):
         inputs = tensors[:n_inputs]
         ctx.eng, ctx.n_inputs, ctx.n_feats = eng, n_inputs, n_feats
+        # a grad-enabled forward that is never back-propagated (eval without no_grad, an exception, a dropped loss term)
+        # must not pin the engine: release it when autograd frees this node
+        weakref.finalize(ctx, _release_engine, eng)
         ctx.in_channels = [t.shape[1] for t in inputs]
         ctx.need_in = any(t.requires_grad for t in inputs)
         out = eng.run([t.detach().float() for t in inputs]).clone()
@@ -341,7 +377,8 @@ class _ChainFunction(torch.autograd.Function):
     def backward(ctx, *grads):
         eng = ctx.eng
         extra = {j + 1: g for j, g in enumerate(grads[:-1])}
-        gin, dWs, dbs = eng.backward(grads[-1], ctx.need_in, sum(ctx.in_channels), extra)
+        need_w = any(ctx.needs_input_grad[3 + ctx.n_inputs:])
+        gin, dWs, dbs = eng.backward(grads[-1], ctx.need_in, sum(ctx.in_channels), extra, need_weight_grad=need_w)
         eng.busy = False
         grads_in = [None] * ctx.n_inputs
         if gin is not None:
@@ -351,9 +388,9 @@ class _ChainFunction(torch.autograd.Function):
                 off += c
         grads_p = []
         for i, Lr in enumerate(eng.chain):
-            grads_p.append(dWs[i])
+            grads_p.append(dWs[i] if need_w else None)
             # a bias in front of an affine-free InstanceNorm has exactly zero gradient
-            grads_p.append(dbs[i] if dbs[i] is not None else torch.zeros_like(Lr["params"].bias))
+            grads_p.append((dbs[i] if dbs[i] is not None else torch.zeros_like(Lr["params"].bias)) if need_w else None)
         return (None, None, None) + tuple(grads_in) + tuple(grads_p)
 
 

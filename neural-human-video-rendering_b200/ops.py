@@ -330,25 +330,23 @@ def composite(fgm: torch.Tensor, bg: torch.Tensor, out: Optional[torch.Tensor] =
 class _TextureSampleFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, uvp, atlas, use_mask_texture):
-        if not use_mask_texture:
-            raise capi.NhvrError("texture lookup backward is built for --use_mask_texture (the reference's setting) only")
         u = uvp.detach().contiguous().float()
         acl = atlas_to_channels_last(atlas)
-        tex, _, _ = texture_sample(u, acl, atlas.shape[1], True, want_indices=False)
-        ctx.saved = (u, acl, atlas.shape)
+        tex, _, _ = texture_sample(u, acl, atlas.shape[1], bool(use_mask_texture), want_indices=False)
+        ctx.saved = (u, acl, atlas.shape, bool(use_mask_texture))
         return tex
 
     @staticmethod
     def backward(ctx, gtex):
-        u, acl, ashape = ctx.saved
+        u, acl, ashape, use_mask = ctx.saved
         N, _, H, W = u.shape
         P, Ct, S, _ = ashape
         gtex = gtex.contiguous().float()
         guvp = torch.empty_like(u)
         gacl = torch.zeros_like(acl)
         with _prof("sampler_bwd", float(N) * H * W * (73 * 2 + Ct) * 4.0):
-            check(load().nhvr_texture_sample_bwd(u.data_ptr(), acl.data_ptr(), gtex.data_ptr(), N, H, W, S, Ct, guvp.data_ptr(),
-                                                 gacl.data_ptr(), stream_ptr()), "nhvr_texture_sample_bwd")
+            check(load().nhvr_texture_sample_bwd(u.data_ptr(), acl.data_ptr(), gtex.data_ptr(), N, H, W, S, Ct, int(use_mask),
+                                                 guvp.data_ptr(), gacl.data_ptr(), stream_ptr()), "nhvr_texture_sample_bwd")
         gatlas = gacl[..., :Ct].permute(0, 3, 1, 2).contiguous()
         return guvp, gatlas, None
 

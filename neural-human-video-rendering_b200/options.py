@@ -95,6 +95,8 @@ class BaseOptions:
         p.add_argument("--n_clusters", type=int, default=10)
         # B200 additions (not reference flags)
         p.add_argument("--clips_in_flight", type=int, default=1, help="independent clips advanced in lock-step per GPU")
+        p.add_argument("--precision", type=str, default="strict", choices=["strict", "balanced", "fast"],
+                       help="inference operand precision preset (pipeline.RenderPipeline)")
         self.initialized = True
 
     def parse(self, args=None, save=False):
@@ -111,8 +113,10 @@ class BaseOptions:
         self.opt.gpu_ids = [i for i in ids if i >= 0]
         if not self.opt.gpu_ids:
             raise SystemExit("--gpu_ids -1: this build has no CPU path (sm_100a kernels only)")
-        # pose channels actually fed to the networks (SPEC D1 / D12)
-        self.opt.pose_nc = self.opt.input_nc + (3 if (self.opt.use_laplace and self.opt.pose_plus_laplace) else 0)
+        # pose channels actually fed to the networks (SPEC D1 / D12): --use_laplace alone adds the 3 LaplaceProj channels.
+        # train_start/pretrain_start.sh passes --use_laplace without --pose_plus_laplace, test_start/start.sh passes both:
+        # deriving the count from --use_laplace keeps a checkpoint written by train.py loadable by test.py
+        self.opt.pose_nc = self.opt.input_nc + (3 if self.opt.use_laplace else 0)
         if save:
             expr_dir = os.path.join(self.opt.checkpoints_dir, self.opt.name)
             os.makedirs(expr_dir, exist_ok=True)

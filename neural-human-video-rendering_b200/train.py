@@ -107,37 +107,40 @@ class RenderTrainer:
         self.bucket_D = FlatGradBucket(self.netD.parameters()) if distributed else None
 
     def step(self, batch: dict) -> dict:
+        """pix2pixHD's optimize_parameters order: every discriminator pass of the step (fake detached, real, fake for the
+        generator) sees the SAME discriminator weights; the generator side is updated first, then the discriminator."""
         pipe, D, lam = self.pipe, self.netD, self.lam
         pose0, pose1, real1 = batch["pose_prev"], batch["pose"], batch["image"]
         with torch.no_grad():
             r0 = pipe.forward_train(pose0, torch.zeros_like(real1))
         r1 = pipe.forward_train(pose1, r0["out"])
         fake = r1["out"]
-        # ---- discriminator
-        self.opt_D.zero_grad(set_to_none=True)
+        # ---- discriminator passes (no weight update in between)
         pred_fake_d = D(pose1, fake.detach())
         pred_real = D(pose1, real1)
         loss_D = losses.lsgan_diff(pred_fake_d, False, 0.5) + losses.lsgan_diff(pred_real, True, 0.5)
-        loss_D.backward()
-        if self.bucket_D is not None:
-            self.bucket_D.all_reduce_mean()
-        self.opt_D.step()
-        # ---- generator side
-        self.opt_G.zero_grad(set_to_none=True)
         for p in D.parameters():
             p.requires_grad_(False)
         pred_fake = D(pose1, fake)
+        for p in D.parameters():
+            p.requires_grad_(True)
         loss_G = (losses.lsgan_diff(pred_fake, True)
                   + losses.feature_matching_diff(pred_fake, [[t.detach() for t in s] for s in pred_real], self.n_layers_D, self.num_D, lam["feat"])
                   + losses.mse_diff(fake, real1, lam["l2"])
                   + losses.uv_prob_objective(r1["uvp"], batch["dp_i"], batch["dp_uv"], lam["uv"], lam["prob"])
                   + losses.temporal_diff(fake, r0["out"], batch["flow_inv"], lam["temp"]))
+        # ---- generator side
+        self.opt_G.zero_grad(set_to_none=True)
         loss_G.backward()
-        for p in D.parameters():
-            p.requires_grad_(True)
         if self.bucket_G is not None:
             self.bucket_G.all_reduce_mean()
         self.opt_G.step()
+        # ---- discriminator
+        self.opt_D.zero_grad(set_to_none=True)
+        loss_D.backward()
+        if self.bucket_D is not None:
+            self.bucket_D.all_reduce_mean()
+        self.opt_D.step()
         return {"loss_D": loss_D.detach(), "loss_G": loss_G.detach()}
 
 

@@ -218,3 +218,26 @@ def test_flat_grad_bucket_allreduce_world_size_2_gloo():
     assert g0 == [[1.5] * 4] * 3                               # mean of 1 and 2
     assert g1 == [0.0, 1.5, 3.0, 4.5, 6.0]
     assert g2 == [[0.0, 0.0], [0.0, 0.0]]
+
+
+def test_train_and_test_scripts_build_checkpoint_compatible_pipelines():
+    """train_start/pretrain_start.sh (--use_laplace, no --pose_plus_laplace, no --use_mask_texture) and
+    test_start/start.sh (--use_laplace --pose_plus_laplace --use_mask_texture) must describe the same networks: a
+    checkpoint written by train.py loads in test.py (state_dict keys and shapes identical)."""
+    import json
+    from nhvr_b200.options import TestOptions, TrainOptions, pipeline_kwargs
+    from nhvr_b200.pipeline import RenderPipeline
+    flags = json.load(open(os.path.join(GOLD, "ref_flags.json")))
+    train_argv = next(c["argv"] for f, cmds in flags.items() for c in cmds if c["entry"] == "train.py")
+    test_argv = next(c["argv"] for f, cmds in flags.items() for c in cmds if c["entry"] == "test.py")
+    ot = TrainOptions().parse([a.replace("$DANCE", "d").replace("${DANCE}", "d") for a in train_argv])
+    oe = TestOptions().parse([a.replace("$DANCE", "d").replace("${DANCE}", "d") for a in test_argv])
+    assert ot.pose_nc == oe.pose_nc == 6
+    assert not ot.use_mask_texture and oe.use_mask_texture
+    kw_t, kw_e = pipeline_kwargs(ot), pipeline_kwargs(oe)
+    small = dict(size=64, atlas_size=16, ngf_global=8, ngf_translate=8, ngf_bg=8, n_blocks_global=1, n_blocks_translate=1)
+    kw_t.update(small); kw_e.update(small)
+    if torch.cuda.is_available():
+        pytest.skip("CPU-side construction check")
+    pt, pe = RenderPipeline(**kw_t), RenderPipeline(**kw_e)
+    pe.load_state_dict(pt.state_dict(), strict=True)

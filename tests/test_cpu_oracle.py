@@ -163,3 +163,27 @@ def test_reference_scripts_parse_verbatim():
         TestOptions().parse(["--gpu_ids", "-1"])
     with pytest.raises(SystemExit):
         TestOptions().parse(["--no_such_flag"])
+
+
+def test_independent_numpy_restatement_agrees_with_the_torch_oracle(gold):
+    """oracle/numpy_ref.py restates ReflectionPad2d / Conv2d / ConvTranspose2d / InstanceNorm2d / the ResnetBlock / the
+    odd-size PatchGAN arithmetic (4x4 stride 2 padding 2: 24 -> 13 -> 7 -> 8 -> 9; AvgPool(3,2,1) without padded counts)
+    from the operator definitions in plain numpy.  It must reproduce the golden vectors the torch.nn oracle produced
+    (tests/golden/oracle_small.npz): the two restatements pin each other."""
+    from oracle import numpy_ref as R
+    sd = {k: gold[k] for k in gold.files}
+    y = R.global_generator(gold["x"], sd, n_down=1, n_blocks=1, final="tanh_sigmoid_last", prefix="g.")
+    assert y.shape == gold["y"].shape
+    assert np.abs(y - gold["y"]).max() <= 2e-5
+    feats = R.multiscale_discriminator(gold["xd"], sd, num_D=2, n_layers=2, prefix="d.")
+    assert feats[0][0].shape == gold["yd_feat00"].shape == (1, 8, 13, 13)
+    assert feats[0][-1].shape == (1, 1, 9, 9) and feats[1][-1].shape == (1, 1, 6, 6)
+    assert np.abs(feats[0][0] - gold["yd_feat00"]).max() <= 2e-5
+    assert np.abs(feats[0][-1] - gold["yd_last0"]).max() <= 5e-5
+    assert np.abs(feats[1][-1] - gold["yd_last1"]).max() <= 5e-5
+    # single operators on odd sizes against their definitions' corner cases
+    x = np.arange(2 * 1 * 5 * 7, dtype=np.float64).reshape(2, 1, 5, 7)
+    p = R.reflect_pad(x, 2)
+    assert p.shape == (2, 1, 9, 11) and p[0, 0, 0, 0] == x[0, 0, 2, 2] and p[0, 0, 8, 10] == x[0, 0, 2, 4]
+    a = R.avgpool3s2(x)
+    assert a.shape == (2, 1, 3, 4) and a[0, 0, 0, 0] == x[0, 0, :2, :2].mean() and a[0, 0, 2, 3] == x[0, 0, 3:5, 5:7].mean()

@@ -553,10 +553,13 @@ def test_sampler_and_composite_backward_exact(cuda_dev):
     atlas = smooth_atlas(3, 16, cuda_dev).requires_grad_(True)
     u2, a2 = uvp.detach().clone().requires_grad_(True), atlas.detach().clone().requires_grad_(True)
     w = torch.randn(2, 3, 20, 24, device=cuda_dev)
-    (ops.texture_sample_diff(uvp, atlas, True) * w).sum().backward()
-    (texture_sample(u2, a2, True)[0] * w).sum().backward()
-    assert (uvp.grad - u2.grad).abs().max().item() <= 1e-3 * u2.grad.abs().max().item()
-    assert (atlas.grad - a2.grad).abs().max().item() <= 1e-3 * a2.grad.abs().max().item()
+    for use_mask in (True, False):        # --use_mask_texture (start.sh) and the renormalised blend pretrain_start.sh trains with
+        for t in (uvp, atlas, u2, a2):
+            t.grad = None
+        (ops.texture_sample_diff(uvp, atlas, use_mask) * w).sum().backward()
+        (texture_sample(u2, a2, use_mask)[0] * w).sum().backward()
+        assert (uvp.grad - u2.grad).abs().max().item() <= 1e-3 * u2.grad.abs().max().item(), use_mask
+        assert (atlas.grad - a2.grad).abs().max().item() <= 1e-3 * a2.grad.abs().max().item(), use_mask
     fgm = torch.rand(3, 4, 10, 12, device=cuda_dev).requires_grad_(True)
     bg = torch.rand(3, 10, 12, device=cuda_dev).requires_grad_(True)
     f2, b2 = fgm.detach().clone().requires_grad_(True), bg.detach().clone().requires_grad_(True)
@@ -599,6 +602,18 @@ def test_discriminator_backward_parity(cuda_dev):
         assert cos >= 0.99, (name, cos)
 
 
+def test_forward_without_backward_does_not_pin_engines(cuda_dev):
+    """Grad-enabled forwards that are never back-propagated release their training engine when autograd frees the node."""
+    net, _ = _pair_G(cuda_dev, 3, 3, 16, "global", 1, 1, seed=43)
+    x = torch.rand(1, 3, 32, 32, device=cuda_dev) * 2 - 1
+    for _ in range(12):                      # more than the 8-engine pool
+        y = net(x)
+        assert y.requires_grad
+        del y
+    pool = next(v for k, v in net._engines.items() if k[-1] == "train")
+    assert len(pool) <= 2
+
+
 def test_full_training_step_runs_and_matches_oracle_losses(cuda_dev):
     """configs[2] in miniature: one RenderTrainer step (D step + G step) — its loss values against the oracle's
     formulas on the same weights/batch, and a few steps of Adam change every parameter group."""
@@ -624,10 +639,15 @@ def test_full_training_step_runs_and_matches_oracle_losses(cuda_dev):
         uvp1, out1 = frame(batch["pose"], out0)
         pf, pr = refD(torch.cat([batch["pose"], out1], 1)), refD(torch.cat([batch["pose"], batch["image"]], 1))
         lD = 0.5 * (O.gan_loss(pf, False) + O.gan_loss(pr, True))
+        # generator objective with the SAME discriminator weights (pix2pixHD computes both sides before either update)
+        lG = (O.gan_loss(pf, True) + O.feature_matching_loss(pf, pr, 3, 2, 10.0) + 500.0 * O.l2_loss(out1, batch["image"])
+              + 1000.0 * O.uv_loss(uvp1, batch["dp_i"], batch["dp_uv"]) + 10.0 * O.prob_loss(uvp1, batch["dp_i"])
+              + 500.0 * O.temporal_loss(out1, out0, batch["flow_inv"]))
     trainer = RenderTrainer(pipe, netD)
     before = {k: v.detach().clone() for k, v in list(pipe.named_parameters()) + list(netD.named_parameters())}
     out = trainer.step(batch)
     assert abs(out["loss_D"].item() - lD.item()) <= 2e-2 * abs(lD.item()), (out["loss_D"].item(), lD.item())
+    assert abs(out["loss_G"].item() - lG.item()) <= 2e-2 * abs(lG.item()), (out["loss_G"].item(), lG.item())
     for _ in range(2):
         out = trainer.step(batch)
     assert torch.isfinite(out["loss_G"]) and torch.isfinite(out["loss_D"])

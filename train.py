@@ -42,7 +42,14 @@ def main(argv=None):
     if opt.load_pretrain_TransG:
         p = net_path(opt.load_pretrain_TransG, opt.which_epoch_TransG, "TransG")
         if os.path.isfile(p):
-            pipe.netTransG.load_state_dict(torch.load(p, map_location="cpu"))
+            sd = torch.load(p, map_location="cpu")
+            # pretrainTrans.sh trains the UV generator on the 3-channel pose map (--input_nc 3, no --use_laplace) while
+            # pretrain_start.sh feeds pose + LaplaceProj (--use_laplace): widen the stem with zero weights for the extra
+            # input channels - the same function on the first channels
+            w = sd.get("model.1.weight")
+            if w is not None and w.shape[1] < opt.pose_nc:
+                sd["model.1.weight"] = torch.cat([w, torch.zeros(w.shape[0], opt.pose_nc - w.shape[1], *w.shape[2:])], 1)
+            pipe.netTransG.load_state_dict(sd)
             print("[train.py] loaded", p)
         else:
             print("[train.py] --load_pretrain_TransG: %s not found, UV generator starts from random init" % p)
