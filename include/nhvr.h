@@ -163,6 +163,13 @@ int nhvr_in_apply(const void* raw, const nhvr_act_desc* raw_desc, const double* 
                   const void* residual, const nhvr_act_desc* res_desc,
                   void* dst, const nhvr_act_desc* dst_desc, void* stream);
 
+/* ---- keypoints -> pose maps (the step before the path: --pose_path ./keypoints of OpenPose BODY_25 JSONs, start.sh:9,24-25) ----
+ * kps: device float [T][25][3] (x, y, confidence) in a src_size^2 frame; out: device float [T][pose_nc][size][size]: the
+ * 3-channel stick figure of nhvr_b200/pose.py in [-1, 1] (bit-identical to the host rasteriser), further channels zero
+ * (LaplaceProj input of --use_laplace: no data in the fixtures).  limb_colors_host: HOST uint8 [24][3]. */
+int nhvr_pose_rasterize(const float* kps, int32_t T, int32_t size, float src_size, float thickness, float conf_thresh,
+                        int32_t pose_nc, const uint8_t* limb_colors_host, float* out, void* stream);
+
 /* ---- texture lookup ("--TexG part --use_mask_texture", start.sh:14,18; README.md:64) ----
  * uvp: float [N][73][H][W] = 25 part logits, 24 U, 24 V (raw UV-generator output).
  * atlas: float [24][S][S][Ct4] (channels-last, Ct4 = Ctex rounded up to 4).
@@ -174,6 +181,16 @@ int nhvr_in_apply(const void* raw, const nhvr_act_desc* raw_desc, const double* 
 int nhvr_texture_sample(const float* uvp, const float* atlas, int32_t N, int32_t H, int32_t W,
                         int32_t S, int32_t Ctex, int32_t use_mask_texture,
                         float* tex_out, uint8_t* part_out, int16_t* texel_out, void* stream);
+
+/* ---- unfold_texture (README.md:64: the initial texture.jpg built from the frames and their DensePose IUV) ----
+ * The adjoint of the bilinear lookup: every pixel with part dp_i in 1..24 splats img into the four texels around
+ * (u, v) * (S-1) of its part with the lookup's weights.  img float [N][C][H][W]; dp_i int32 [N][H][W]; dp_uv float [N][2][H][W]
+ * in [0,1]; acc float [24][S][S][Q], Q = 4*ceil((C+1)/4) (C colour sums then the weight sum), zeroed by the caller and
+ * accumulated over as many calls as there are frame batches; _finish divides: atlas float [24][C][S][S], 0 where the
+ * weight is <= min_weight. */
+int nhvr_texture_unfold(const float* img, const int32_t* dp_i, const float* dp_uv, int32_t N, int32_t H, int32_t W, int32_t S,
+                        int32_t C, float* acc, void* stream);
+int nhvr_texture_unfold_finish(const float* acc, int32_t S, int32_t C, float min_weight, float* atlas, void* stream);
 
 /* ---- mask / background composite (README.md:15,52,60; --bg_path start.sh:12) ----
  * out = m*fg + (1-m)*bg.  fgm: float [N][4][H][W] (RGB in [-1,1], mask in [0,1]);

@@ -70,8 +70,11 @@ SYMBOLS = {
     "nhvr_conv_forward": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(ActDesc), _P, _P]),
     "nhvr_in_apply": (C.c_int, [_P, C.POINTER(ActDesc), _P, C.c_float, C.c_int32, _P, C.POINTER(ActDesc), _P,
                                 C.POINTER(ActDesc), _P]),
+    "nhvr_pose_rasterize": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32, _P, _P, _P]),
     "nhvr_texture_sample": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P,
                                       _P, _P]),
+    "nhvr_texture_unfold": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "nhvr_texture_unfold_finish": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_float, _P, _P]),
     "nhvr_composite": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "nhvr_texture_sample_bwd": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     "nhvr_composite_bwd": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),

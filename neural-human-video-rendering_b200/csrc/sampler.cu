@@ -364,3 +364,91 @@ extern "C" int nhvr_composite_bwd(const float* fgm, const float* bg, int32_t bg_
   if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
   return NHVR_OK;
 }
+
+
+// =================================================================================================
+// unfold_texture (README.md:64: the initial texture.jpg from the frames and their DensePose IUV) - the ADJOINT of the
+// bilinear lookup: every foreground pixel splats its colour into the four texels around (u, v) of its part with the
+// lookup's own weights; the atlas is the weighted mean.
+// =================================================================================================
+namespace nhvr {
+
+// acc: float [24][S][S][Q] with Q = 4 * ceil((C + 1) / 4): C colour sums, then the weight sum
+__global__ void __launch_bounds__(256) texture_unfold_kernel(const float* __restrict__ img, const int32_t* __restrict__ dp_i,
+                                                             const float* __restrict__ dp_uv, int N, int H, int W, int S, int C, int Q,
+                                                             float* __restrict__ acc) {
+  const int64_t HW = (int64_t)H * W, total = (int64_t)N * HW;
+  const float sm1 = (float)(S - 1);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int part = dp_i[idx];
+    if (part < 1 || part > kParts) continue;
+    const int n = (int)(idx / HW);
+    const int64_t pix = idx - (int64_t)n * HW;
+    const float u = fminf(fmaxf(dp_uv[((int64_t)n * 2) * HW + pix], 0.f), 1.f);
+    const float v = fminf(fmaxf(dp_uv[((int64_t)n * 2 + 1) * HW + pix], 0.f), 1.f);
+    const float fx = __fmul_rn(u, sm1), fy = __fmul_rn(v, sm1);
+    const float x0f = floorf(fx), y0f = floorf(fy);
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const int x1 = min(x0 + 1, S - 1), y1 = min(y0 + 1, S - 1);
+    const float wx = fx - x0f, wy = fy - y0f;
+    const float wts[4] = {(1.f - wy) * (1.f - wx), (1.f - wy) * wx, wy * (1.f - wx), wy * wx};
+    const int64_t tb = (int64_t)(part - 1) * S * S;
+    const int64_t at[4] = {tb + (int64_t)y0 * S + x0, tb + (int64_t)y0 * S + x1, tb + (int64_t)y1 * S + x0, tb + (int64_t)y1 * S + x1};
+    for (int q = 0; q < Q; q += 4) {
+      float val[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = q + e;
+        val[e] = c < C ? img[((int64_t)n * C + c) * HW + pix] : (c == C ? 1.f : 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float* dst = acc + at[k] * Q + q;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(wts[k] * val[0]), "f"(wts[k] * val[1]),
+                     "f"(wts[k] * val[2]), "f"(wts[k] * val[3]) : "memory");
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) texture_unfold_finish_kernel(const float* __restrict__ acc, int S, int C, int Q, float min_weight,
+                                                                    float* __restrict__ atlas) {
+  const int64_t total = (int64_t)kParts * S * S;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(t / ((int64_t)S * S));
+    const int64_t yx = t - (int64_t)k * S * S;
+    const float w = acc[t * Q + C];
+    for (int c = 0; c < C; ++c)
+      atlas[((int64_t)k * C + c) * S * S + yx] = w > min_weight ? acc[t * Q + c] / w : 0.f;
+  }
+}
+
+}  // namespace nhvr
+
+extern "C" int nhvr_texture_unfold(const float* img, const int32_t* dp_i, const float* dp_uv, int32_t N, int32_t H, int32_t W, int32_t S,
+                                   int32_t C, float* acc, void* stream) {
+  if (!img || !dp_i || !dp_uv || !acc) return NHVR_ERR_NULL;
+  if (N <= 0 || H <= 0 || W <= 0 || S < 2 || C <= 0 || C > 19) return NHVR_ERR_SHAPE;
+  if (((uintptr_t)acc & 15) != 0) return NHVR_ERR_ALIGN;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  const int Q = (C + 1 + 3) / 4 * 4;
+  const int64_t total = (int64_t)N * H * W;
+  texture_unfold_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(img, dp_i, dp_uv, N, H, W, S, C, Q, acc);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
+  return NHVR_OK;
+}
+
+extern "C" int nhvr_texture_unfold_finish(const float* acc, int32_t S, int32_t C, float min_weight, float* atlas, void* stream) {
+  if (!acc || !atlas) return NHVR_ERR_NULL;
+  if (S < 2 || C <= 0 || C > 19) return NHVR_ERR_SHAPE;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  const int Q = (C + 1 + 3) / 4 * 4;
+  const int64_t total = (int64_t)kParts * S * S;
+  texture_unfold_finish_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(acc, S, C, Q, min_weight, atlas);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
+  return NHVR_OK;
+}

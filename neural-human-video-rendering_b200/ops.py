@@ -379,3 +379,43 @@ class _CompositeFn(torch.autograd.Function):
 
 def composite_diff(fgm: torch.Tensor, bg: torch.Tensor) -> torch.Tensor:
     return _CompositeFn.apply(fgm, bg)
+
+
+def pose_rasterize(kps: torch.Tensor, size: int, pose_nc: int = 3, src_size: float = 1024.0, thickness: float = 4.0,
+                   conf_thresh: float = 0.05, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nhvr_pose_rasterize: device keypoints [T,25,3] fp32 -> pose maps [T,pose_nc,size,size] fp32 (stick figure in [-1,1],
+    bit-identical to nhvr_b200.pose.rasterize; Laplace channels zero)."""
+    from .pose import LIMB_COLORS
+    assert kps.is_cuda and kps.dtype == torch.float32 and kps.shape[1:] == (25, 3)
+    kps = kps.contiguous()
+    T = kps.shape[0]
+    if out is None:
+        out = torch.empty(T, pose_nc, size, size, dtype=torch.float32, device=kps.device)
+    cols = (C.c_uint8 * 72)(*[int(v) for v in LIMB_COLORS.reshape(-1)])
+    check(load().nhvr_pose_rasterize(kps.data_ptr(), T, size, float(src_size), float(thickness), float(conf_thresh), pose_nc,
+                                     C.cast(cols, C.c_void_p), out.data_ptr(), stream_ptr()), "nhvr_pose_rasterize")
+    return out
+
+
+class TextureUnfolder:
+    """unfold_texture on the GPU (README.md:64): accumulate frames + DensePose IUV into the 24 x S x S part atlas
+    (nhvr_texture_unfold, the lookup's adjoint), then divide by the accumulated weights."""
+
+    def __init__(self, S: int = 200, C_: int = 3, device=None):
+        self.S, self.C = S, C_
+        self.Q = (C_ + 1 + 3) // 4 * 4
+        self.acc = torch.zeros(24, S, S, self.Q, dtype=torch.float32, device=device or torch.device("cuda"))
+
+    def add(self, img: torch.Tensor, dp_i: torch.Tensor, dp_uv: torch.Tensor) -> None:
+        img, dp_uv = img.contiguous().float(), dp_uv.contiguous().float()
+        dp_i = dp_i.contiguous().to(torch.int32)
+        N, Cc, H, W = img.shape
+        assert Cc == self.C and dp_i.shape == (N, H, W) and dp_uv.shape == (N, 2, H, W)
+        check(load().nhvr_texture_unfold(img.data_ptr(), dp_i.data_ptr(), dp_uv.data_ptr(), N, H, W, self.S, self.C, self.acc.data_ptr(),
+                                         stream_ptr()), "nhvr_texture_unfold")
+
+    def atlas(self, min_weight: float = 0.0) -> torch.Tensor:
+        out = torch.empty(24, self.C, self.S, self.S, dtype=torch.float32, device=self.acc.device)
+        check(load().nhvr_texture_unfold_finish(self.acc.data_ptr(), self.S, self.C, float(min_weight), out.data_ptr(), stream_ptr()),
+              "nhvr_texture_unfold_finish")
+        return out

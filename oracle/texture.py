@@ -121,3 +121,28 @@ def composite(fgm: torch.Tensor, bg: torch.Tensor) -> torch.Tensor:
     if bg.dim() == 3:
         bg = bg.unsqueeze(0)
     return m * fg + (1 - m) * bg
+
+
+def unfold_texture(img: torch.Tensor, dp_i: torch.Tensor, dp_uv: torch.Tensor, S: int, min_weight: float = 0.0) -> torch.Tensor:
+    """unfold_texture [REF README.md:64]: the initial part atlas from frames + DensePose IUV, as the weighted mean of the
+    pixels splatted with the bilinear lookup's own corner weights (the adjoint of texture_sample's gather; the reference's
+    script is absent - SPEC: same (u, v) -> texel rule as the lookup, align_corners).  img [N,C,H,W]; dp_i [N,H,W] in 0..24;
+    dp_uv [N,2,H,W] in [0,1] -> atlas [24,C,S,S] (0 where no pixel landed)."""
+    N, C, H, W = img.shape
+    acc = torch.zeros(N_PARTS * S * S, C + 1, dtype=torch.float64)
+    fg = (dp_i >= 1) & (dp_i <= N_PARTS)
+    u = dp_uv[:, 0].float().clamp(0, 1)
+    v = dp_uv[:, 1].float().clamp(0, 1)
+    fx, fy = u * float(S - 1), v * float(S - 1)
+    x0f, y0f = torch.floor(fx), torch.floor(fy)
+    x0, y0 = x0f.long(), y0f.long()
+    x1, y1 = torch.clamp(x0 + 1, max=S - 1), torch.clamp(y0 + 1, max=S - 1)
+    wx, wy = (fx - x0f), (fy - y0f)
+    vals = torch.cat([img.double().permute(0, 2, 3, 1), torch.ones(N, H, W, 1, dtype=torch.float64)], -1)   # [N,H,W,C+1]
+    base = (dp_i.long() - 1).clamp(min=0) * S * S
+    for yy, xx, w in ((y0, x0, (1 - wy) * (1 - wx)), (y0, x1, (1 - wy) * wx), (y1, x0, wy * (1 - wx)), (y1, x1, wy * wx)):
+        at = (base + yy * S + xx)[fg]
+        acc.index_add_(0, at, vals[fg] * w.double()[fg].unsqueeze(-1))
+    wsum = acc[:, C:]
+    atlas = torch.where(wsum > min_weight, acc[:, :C] / wsum.clamp(min=1e-30), torch.zeros_like(acc[:, :C]))
+    return atlas.reshape(N_PARTS, S, S, C).permute(0, 3, 1, 2).float().contiguous()

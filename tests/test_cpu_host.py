@@ -241,3 +241,60 @@ def test_train_and_test_scripts_build_checkpoint_compatible_pipelines():
         pytest.skip("CPU-side construction check")
     pt, pe = RenderPipeline(**kw_t), RenderPipeline(**kw_e)
     pe.load_state_dict(pt.state_dict(), strict=True)
+
+
+def test_graph_posenorm_cli_recovers_a_known_scale_and_translation(tmp_path):
+    """data/data_prep/graph_posenorm.py with run_alignPose.sh's flags: a source sequence that is the target one scaled by
+    0.8 about a point and shifted is aligned back onto it (ankles and body height within 2 px)."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("graph_posenorm", os.path.join(ROOT, "data", "data_prep", "graph_posenorm.py"))
+    gp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gp)
+    kps = np.load(os.path.join(GOLD, "keypoints_body25.npy"))[:30]
+    tdir, sdir, odir = tmp_path / "tgt", tmp_path / "src", tmp_path / "out"
+    tdir.mkdir(); sdir.mkdir()
+    base = json.load(open(os.path.join(GOLD, "keypoints_frame0.json")))
+    src = kps.copy()
+    src[:, :, 0] = (kps[:, :, 0] - 500.0) * 0.8 + 430.0
+    src[:, :, 1] = (kps[:, :, 1] - 800.0) * 0.8 + 700.0
+    for d, arr in ((tdir, kps), (sdir, src)):
+        for i, k in enumerate(arr):
+            j = json.loads(json.dumps(base))
+            j["people"][0]["pose_keypoints_2d"] = [float(v) for v in k.reshape(-1)]
+            json.dump(j, open(d / ("frame%05d_keypoints.json" % i), "w"))
+    flags = json.load(open(os.path.join(GOLD, "ref_flags.json")))["data/data_prep/run_alignPose.sh"][0]["argv"]
+    argv = list(flags)
+    for name, val in (("--target_keypoints", str(tdir)), ("--source_keypoints", str(sdir)), ("--results", str(odir)), ("--source_frames", str(sdir))):
+        argv[argv.index(name) + 1] = val
+    argv[argv.index("--target_spread") + 1:argv.index("--target_spread") + 3] = ["700", "900"]
+    argv[argv.index("--source_spread") + 1:argv.index("--source_spread") + 3] = ["600", "800"]
+    out = gp.main(argv)
+    assert out.shape == kps.shape and len(os.listdir(odir)) == 30
+    ank_o, ank_t = 0.5 * (out[:, 11, 1] + out[:, 14, 1]), 0.5 * (kps[:, 11, 1] + kps[:, 14, 1])
+    assert np.abs(np.median(ank_o) - np.median(ank_t)) <= 6.0
+    h_o, h_t = ank_o - out[:, 0, 1], ank_t - kps[:, 0, 1]
+    assert abs(np.median(h_o) / np.median(h_t) - 1.0) <= 0.02
+    back = json.load(open(odir / "frame00000_keypoints.json"))
+    assert len(back["people"][0]["pose_keypoints_2d"]) == 75
+
+
+def test_texture_grid_layout_round_trip_and_tex_flags_parse():
+    """unfold_texture.py's texture.jpg layout (4 x 6 parts) round-trips; pre_train_tex.sh's flags parse verbatim."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("unfold_texture", os.path.join(ROOT, "unfold_texture.py"))
+    ut = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ut)
+    atlas = (torch.randint(0, 256, (24, 3, 8, 8)).float() / 127.5 - 1.0)
+    grid = ut.atlas_to_grid(atlas)
+    assert grid.shape == (32, 48, 3)
+    assert torch.allclose(ut.grid_to_atlas(grid, 8), atlas, atol=1e-6)
+    assert (grid[8:16, 16:24] == ((atlas[8].permute(1, 2, 0) + 1) * 127.5).round().numpy().astype(np.uint8)).all()   # part 8 -> row 1, col 2
+    from nhvr_b200.options import TrainOptions
+    argv = json.load(open(os.path.join(GOLD, "ref_flags.json")))["pre_train_tex.sh"][0]["argv"]
+    to = TrainOptions()
+    to.initialize()
+    to.parser.add_argument("--synthetic_steps", type=int, default=0)
+    opt = to.parse(argv)
+    assert opt.input_nc == 81 and opt.loadSize == 200 and opt.n_blocks_global == 5 and opt.ngf_global == 64 and opt.use_mask_texture

@@ -656,3 +656,47 @@ def test_full_training_step_runs_and_matches_oracle_losses(cuda_dev):
     assert any(k.startswith("netTransG") for k in changed) and any(k.startswith("netG") for k in changed)
     assert any(k.startswith("netBG") for k in changed) and "atlas" in changed and "bg" in changed
     assert any(k.startswith("scale0") for k in changed) and any(k.startswith("scale1") for k in changed)
+
+
+def test_pose_rasteriser_bit_exact_on_bundled_keypoints(cuda_dev):
+    """GPU keypoint -> pose-map rasteriser against the host module on all 100 bundled OpenPose frames (configs[0] input),
+    512^2 with the 6 pose channels of start.sh and 256^2 with 3: bit-identical maps."""
+    import numpy as np
+    from nhvr_b200 import ops, pose as posemod
+    kps = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "keypoints_body25.npy"))
+    for size, nc, sl in ((512, 6, slice(0, 100, 7)), (256, 3, slice(0, 100, 9)), (1024, 6, slice(3, 5))):
+        host = torch.from_numpy(posemod.pose_maps(kps[sl], size, nc))
+        dev = ops.pose_rasterize(torch.from_numpy(kps[sl]).to(cuda_dev), size, nc)
+        assert torch.equal(dev.cpu(), host), (size, (dev.cpu() != host).sum().item())
+    # a missing joint (confidence 0) drops its limbs on both sides
+    k2 = kps[:2].copy(); k2[:, 4, 2] = 0.0; k2[:, 0] = 0.0
+    assert torch.equal(ops.pose_rasterize(torch.from_numpy(k2).to(cuda_dev), 512, 3).cpu(), torch.from_numpy(posemod.pose_maps(k2, 512, 3)))
+
+
+def test_unfold_texture_matches_oracle_and_inverts_the_lookup(cuda_dev):
+    """unfold_texture (README.md:64) as the lookup's adjoint: GPU scatter against the fp64 oracle; and a round trip -
+    frames rendered by looking a known atlas up are unfolded back to it wherever the UVs cover a texel."""
+    from nhvr_b200 import ops
+    from oracle.texture import unfold_texture
+    torch.manual_seed(17)
+    N, H, W, S = 3, 96, 80, 24
+    img = torch.rand(N, 3, H, W) * 2 - 1
+    dp_i = torch.randint(0, 25, (N, H, W))
+    dp_uv = torch.rand(N, 2, H, W)
+    unf = ops.TextureUnfolder(S, 3, cuda_dev)
+    unf.add(img[:2].to(cuda_dev), dp_i[:2].to(cuda_dev), dp_uv[:2].to(cuda_dev))
+    unf.add(img[2:].to(cuda_dev), dp_i[2:].to(cuda_dev), dp_uv[2:].to(cuda_dev))          # accumulates over batches
+    got = unf.atlas().cpu()
+    ref = unfold_texture(img, dp_i, dp_uv, S)
+    assert got.shape == ref.shape == (24, 3, S, S)
+    assert (got - ref).abs().max().item() <= 1e-4
+    # round trip with texel-centred UVs: the weighted mean returns the atlas exactly where covered
+    atlas = torch.rand(24, 3, S, S) * 2 - 1
+    ys, xs = torch.meshgrid(torch.arange(S), torch.arange(S), indexing="ij")
+    uv = torch.stack([xs.float() / (S - 1), ys.float() / (S - 1)], 0)                        # [2,S,S]
+    parts = torch.arange(1, 25).view(24, 1, 1).expand(24, S, S)
+    frames = atlas.clone()                                                                   # frame k shows part k's texture
+    unf2 = ops.TextureUnfolder(S, 3, cuda_dev)
+    unf2.add(frames.to(cuda_dev), parts.contiguous().to(cuda_dev), uv.unsqueeze(0).expand(24, 2, S, S).contiguous().to(cuda_dev))
+    back = unf2.atlas().cpu()
+    assert (back - atlas).abs().max().item() <= 1e-4
