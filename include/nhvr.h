@@ -275,6 +275,10 @@ int nhvr_loss_temporal(const float* cur, const float* prev, const float* flow, i
 /* gradient of coef * mean|cur - warp(prev, flow)| w.r.t. cur (prev = detached previous frame) */
 int nhvr_loss_temporal_bwd(const float* cur, const float* prev, const float* flow, int32_t N, int32_t C, int32_t H,
                            int32_t W, float coef, const float* grad_scale, float* grad_cur, void* stream);
+/* Adam over a flat fp32 bucket (pix2pixHD's torch.optim.Adam(lr 2e-4, betas (0.5, 0.999)); no weight decay, no amsgrad): one launch.
+ * g is multiplied by grad_scale first (1 / world_size after a summing all-reduce); n % 4 == 0; step counts from 1. */
+int nhvr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                   float grad_scale, int32_t step, void* stream);
 /* AvgPool2d(3, stride 2, padding 1, count_include_pad=False) between discriminator scales (pix2pixHD
  * MultiscaleDiscriminator.downsample): in float [N][C][H][W] -> out float [N][C][(H+1)/2][(W+1)/2]. */
 int nhvr_avgpool3s2(const float* in, int32_t N, int32_t C, int32_t H, int32_t W, float* out, void* stream);

@@ -95,6 +95,7 @@ SYMBOLS = {
     "nhvr_loss_uv_prob_bwd": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_float, C.c_float, _P, _P, _P]),
     "nhvr_loss_temporal": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "nhvr_loss_temporal_bwd": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P]),
+    "nhvr_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _P]),
     "nhvr_avgpool3s2": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
 }
 

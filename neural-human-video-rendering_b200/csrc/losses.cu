@@ -7,6 +7,7 @@
 // train_start/pretrain_start.sh:31-37 --lambda_L2/--lambda_UV/--lambda_Prob/--lambda_Temp,
 // pix2pixHD GANLoss / feature matching).
 #include "common.cuh"
+#include <cmath>
 #include "p8.cuh"
 #include <algorithm>
 
@@ -337,5 +338,44 @@ extern "C" int nhvr_avgpool3s2(const float* in, int32_t N, int32_t C, int32_t H,
   if (!arch_ok_cached()) return NHVR_ERR_ARCH;
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   avgpool3s2_kernel<<<blocks_for((int64_t)N * C * Ho * Wo), 256, 0, (cudaStream_t)stream>>>(in, (int64_t)N * C, H, W, Ho, Wo, out);
+  NHVR_POST_LAUNCH();
+}
+
+
+// =================================================================================================
+// Adam over a flat fp32 parameter bucket (pix2pixHD: torch.optim.Adam(lr 2e-4, betas (0.5, 0.999)), no weight decay):
+// one launch per bucket instead of four foreach launches per step of the stock optimiser.
+//   m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps),   g = grad * grad_scale
+// =================================================================================================
+namespace nhvr {
+__global__ void __launch_bounds__(256) adam_step_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                                                        float4* __restrict__ v, int64_t n4, float b1, float b2, float eps, float step_size,
+                                                        float inv_sqrt_bc2, float grad_scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 P = p[i], G = g[i], M = m[i], V = v[i];
+    float* pp = reinterpret_cast<float*>(&P); float* gg = reinterpret_cast<float*>(&G);
+    float* mm = reinterpret_cast<float*>(&M); float* vv = reinterpret_cast<float*>(&V);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gr = gg[e] * grad_scale;
+      mm[e] = b1 * mm[e] + (1.f - b1) * gr;
+      vv[e] = b2 * vv[e] + (1.f - b2) * gr * gr;
+      pp[e] -= step_size * mm[e] / (sqrtf(vv[e]) * inv_sqrt_bc2 + eps);
+    }
+    p[i] = P; m[i] = M; v[i] = V;
+  }
+}
+}  // namespace nhvr
+
+extern "C" int nhvr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                              float grad_scale, int32_t step, void* stream) {
+  if (!p || !g || !m || !v) return NHVR_ERR_NULL;
+  if (n <= 0 || (n & 3) || step < 1) return NHVR_ERR_SHAPE;
+  if ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) != 0) return NHVR_ERR_ALIGN;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  const double bc1 = 1.0 - std::pow((double)beta1, (double)step), bc2 = 1.0 - std::pow((double)beta2, (double)step);
+  adam_step_kernel<<<blocks_for(n / 4), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g),
+                                                                        reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), n / 4, beta1, beta2,
+                                                                        eps, (float)((double)lr / bc1), (float)(1.0 / std::sqrt(bc2)), grad_scale);
   NHVR_POST_LAUNCH();
 }

@@ -99,6 +99,8 @@ class _ChainEngine:
             plan = ops.ConvPlan(capi.CONV_TRANSPOSE if p.transposed else capi.CONV, p.cin, p.cout, p.k, p.stride, p.pad,
                                 N, h, w, L["halo"], epi, act, allow_tap_pairing=not train, split3=split3,
                                 centred_stats=(i == 0 and self._centres_stem(chain)))
+            plan.label = ("head" if last else "stem" if i == 0 else "res" if L.get("res") else "up" if p.transposed
+                          else "down" if p.stride == 2 else "conv") + "%dx%d_%d-%d" % (p.k, p.k, p.cin, p.cout)
             self.plans.append(plan)
             h, w = plan.Ho, plan.Wo
         self.out = torch.empty(N, out_channels, h, w, dtype=torch.float32, device=device)
@@ -158,7 +160,8 @@ class _ChainEngine:
             plan.pack_weights(L["params"].weight)
 
     def maybe_repack(self) -> None:
-        ver = tuple(L["params"].weight._version for L in self.chain) + tuple(L["params"].weight.data_ptr() for L in self.chain)
+        ver = (tuple(L["params"].weight._version for L in self.chain) + tuple(L["params"].weight.data_ptr() for L in self.chain)
+               + tuple(getattr(L["params"], "ext_version", 0) for L in self.chain))
         if ver != self.weight_versions:
             self.pack_weights()
             self.weight_versions = ver
@@ -206,6 +209,7 @@ class _ChainEngine:
                 dp = ops.ConvPlan(capi.CONV_DGRAD_S1, p.cin, p.cout, p.k, 1, p.pad, self.N, d.H, d.W, capi.HALO_ZERO, capi.EPI_RAW_P8)
                 fold = (p.pad, p.pad, Lr["halo"] == capi.HALO_REFLECT)
             ops.conv_set_input_desc(dp, wp.g_desc)
+            dp.label = "dgrad_" + plan.label
             B["dplans"][i] = dp
             B["fold"][i] = fold
             xd = ops.make_desc(self.N, dp.Cout8, dp.Ho, dp.Wo)
@@ -259,7 +263,7 @@ class _ChainEngine:
             self._build_backward()
         B = self._bwd
         extra_grads = {k: v for k, v in (extra_grads or {}).items() if v is not None}
-        ver = tuple(Lr["params"].weight._version for Lr in self.chain)
+        ver = tuple((Lr["params"].weight._version, getattr(Lr["params"], "ext_version", 0)) for Lr in self.chain)
         if ver != self._bwd_versions:                       # dgrad convs read the same weights, differently packed
             for Lr, dp in zip(self.chain, B["dplans"]):
                 dp.pack_weights(Lr["params"].weight)
@@ -273,7 +277,8 @@ class _ChainEngine:
         self._last_S = S
         g_pre = ops.head_bwd(self.out, grad_out, self.final_act, S)
         dbs: List[Optional[torch.Tensor]] = [None] * L
-        dbs[L - 1] = ops.bias_grad(g_pre, inv_S)
+        if need_weight_grad:
+            dbs[L - 1] = ops.bias_grad(g_pre, inv_S)
         ops.pack_nchw([g_pre], B["G"][L - 1])
         dWs: List[Optional[torch.Tensor]] = [None] * L
         dy_total: Dict[int, ops.P8Buffer] = {}
@@ -281,9 +286,15 @@ class _ChainEngine:
         for i in range(L - 1, -1, -1):
             Lr, plan = self.chain[i], self.plans[i]
             if need_weight_grad:                             # frozen discriminator under the generator loss: input grads only
-                dW = torch.empty_like(Lr["params"].weight, dtype=torch.float32)
-                B["wplans"][i].run(self.in_bufs[i], B["G"][i], B["ws"], dW, inv_S)
-                dWs[i] = dW
+                wgt = Lr["params"].weight
+                if getattr(wgt, "_nhvr_direct_grad", False) and wgt.grad is not None:
+                    # train.ParamBucket: .grad is a view of the flat gradient bucket - accumulate straight into it, autograd
+                    # gets None for this parameter (no allocation, no AccumulateGrad kernel, no gather / scatter copies)
+                    B["wplans"][i].run(self.in_bufs[i], B["G"][i], B["ws"], wgt.grad, inv_S, accumulate=True)
+                else:
+                    dW = torch.empty_like(wgt, dtype=torch.float32)
+                    B["wplans"][i].run(self.in_bufs[i], B["G"][i], B["ws"], dW, inv_S)
+                    dWs[i] = dW
             if i == 0 and not need_input_grad:
                 break
             dX = B["dX"][i]
@@ -318,7 +329,8 @@ class _ChainEngine:
             else:                                            # conv + bias + activation without norm
                 dbias = torch.zeros(self.plans[i - 1].Cout8 * 8, dtype=torch.float32, device=self.device)
                 ops.act_bwd(dX, pt, pl_, refl, self.in_bufs[i], prev["act"], B["G"][i - 1], dbias, skip=skip)
-                dbs[i - 1] = dbias[:prev["params"].cout] * inv_S
+                if need_weight_grad:
+                    dbs[i - 1] = dbias[:prev["params"].cout] * inv_S
         return input_grad, dWs, dbs
 
     def feature(self, i: int) -> torch.Tensor:
@@ -389,8 +401,18 @@ class _ChainFunction(torch.autograd.Function):
         grads_p = []
         for i, Lr in enumerate(eng.chain):
             grads_p.append(dWs[i] if need_w else None)
-            # a bias in front of an affine-free InstanceNorm has exactly zero gradient
-            grads_p.append((dbs[i] if dbs[i] is not None else torch.zeros_like(Lr["params"].bias)) if need_w else None)
+            b = Lr["params"].bias
+            if not need_w:
+                grads_p.append(None)
+            elif getattr(b, "_nhvr_direct_grad", False) and b.grad is not None:
+                if dbs[i] is not None:                       # biases in front of an affine-free InstanceNorm: exactly zero, skipped
+                    b.grad.add_(dbs[i])
+                grads_p.append(None)
+            else:
+                grads_p.append(dbs[i] if dbs[i] is not None else torch.zeros_like(b))
+        hook = getattr(eng, "after_backward", None)
+        if hook is not None and need_w:
+            hook()                                           # e.g. fire this network's gradient all-reduce (train.ParamBucket)
         return (None, None, None) + tuple(grads_in) + tuple(grads_p)
 
 
@@ -462,6 +484,7 @@ class GlobalGeneratorB200(nn.Module):
                 eng = _ChainEngine(self._chain(), N, H, W, dev, self._final_act(), self.output_nc, train=True)
                 pool.append(eng)
             eng.busy = True
+            eng.after_backward = getattr(self, "_after_backward", None)
             eng.maybe_repack()
             return eng
         key = (N, H, W, dev.index, train, self.precision)
@@ -576,6 +599,7 @@ class MultiscaleDiscriminatorB200(nn.Module):
                 pool.append(engs)
             for e in engs:
                 e.busy = True
+                e.after_backward = getattr(self, "_after_backward", None)
             return engs
         key = (N, H, W, dev.index)
         if key not in self._engines:

@@ -134,6 +134,7 @@ class ConvPlan:
         self.Ho, self.Wo, self.Cout8 = ho.value, wo.value, c8.value
         self.Cout, self.Cin, self.N = Cout, Cin, N
         self.epilogue = epilogue
+        self.label = "conv"                 # layer class for bench.py's per-class roofline (set by the engines)
         self.weight_bytes = load().nhvr_conv_weight_bytes(h)
         self.flops = load().nhvr_conv_flops(h)
         self.packed: Optional[torch.Tensor] = None
@@ -169,7 +170,7 @@ class ConvPlan:
     def forward(self, x: P8Buffer, out_ptr: int, bias: Optional[torch.Tensor] = None,
                 out_desc: Optional[ActDesc] = None, stats: Optional[torch.Tensor] = None) -> None:
         assert self.packed is not None, "pack_weights() first"
-        with _prof("conv3" if self.split3 else "conv", self.flops):
+        with _prof(("conv3:" if self.split3 else "conv:") + self.label, self.flops):
             check(load().nhvr_conv_forward(self.handle, x.ptr, self.packed.data_ptr(), ptr(bias), out_ptr,
                                            C.byref(out_desc) if out_desc is not None else None, ptr(stats), stream_ptr()),
                   "nhvr_conv_forward")

@@ -66,7 +66,7 @@ class RenderPipeline(nn.Module):
 
     # ------------------------------------------------------------------ pieces
     def atlas_channels_last(self) -> torch.Tensor:
-        ver = (self.atlas._version, self.atlas.data_ptr())
+        ver = (self.atlas._version, self.atlas.data_ptr(), getattr(self, "ext_version", 0))
         if self._atlas_cl is None or ver != self._atlas_ver:
             self._atlas_cl = ops.atlas_to_channels_last(self.atlas)
             self._atlas_ver = ver
@@ -88,7 +88,22 @@ class RenderPipeline(nn.Module):
 
     def forward_train(self, pose: torch.Tensor, prev: torch.Tensor) -> Dict[str, torch.Tensor]:
         """Differentiable frame: every stage runs forward AND backward on the sm_100a kernels (autograd only
-        routes the gradients).  `prev` is the (detached) previous composited frame."""
+        routes the gradients).  `prev` is the (detached) previous composited frame.  Under torch.no_grad() (frame t-1 of a
+        training step) the networks run their fp16 inference engines - the precision the training engines use - not the
+        split-precision rendering preset."""
+        if not torch.is_grad_enabled():
+            nets = (self.netTransG, self.netG, self.netBG)
+            saved = [n.precision for n in nets]
+            try:
+                for n in nets:
+                    n.precision = "f16"
+                return self._forward_train(pose, prev)
+            finally:
+                for n, p in zip(nets, saved):
+                    n.precision = p
+        return self._forward_train(pose, prev)
+
+    def _forward_train(self, pose: torch.Tensor, prev: torch.Tensor) -> Dict[str, torch.Tensor]:
         uvp = self.netTransG(pose)
         tex = ops.texture_sample_diff(uvp, self.atlas, self.use_mask_texture)
         fgm = self.netG(tex, pose, prev.detach())
@@ -150,7 +165,8 @@ class RenderPipeline(nn.Module):
 
     def state_version(self) -> tuple:
         """Changes whenever a parameter is modified in place or re-assigned (optimizer step, load_state_dict, .to())."""
-        return tuple((p._version, p.data_ptr()) for p in self.parameters())
+        ext = sum(getattr(m, "ext_version", 0) for m in self.modules())      # native optimiser updates (train.ParamBucket)
+        return tuple((p._version + ext, p.data_ptr()) for p in self.parameters())
 
 
 class _StepGraph:
@@ -277,6 +293,7 @@ class _StepGraph:
         """Copy step t's frames out (device staging slot t & 1, then the d2h stream) under the next step's kernels."""
         s = t & 1
         B = self.out.shape[0]
+        t_out = t % out.shape[1]              # `out` shorter than the clip acts as a ring (a consumer drains it as it fills)
         cur, d2h = torch.cuda.current_stream(), st["d2h"]
         if used[s]:
             cur.wait_event(st["out_free"][s])
@@ -285,10 +302,10 @@ class _StepGraph:
         with torch.cuda.stream(d2h):
             d2h.wait_event(st["out_ready"][s])
             if out.is_cuda:
-                out[:, t].copy_(st["out"][s], non_blocking=True)
+                out[:, t_out].copy_(st["out"][s], non_blocking=True)
             else:
                 for b in range(B):
-                    out[b, t].copy_(st["out"][s][b], non_blocking=True)
+                    out[b, t_out].copy_(st["out"][s][b], non_blocking=True)
             st["out_free"][s].record(d2h)
 
     def stream_keypoints(self, kps: torch.Tensor, out: torch.Tensor, src_size: float = 1024.0) -> None:

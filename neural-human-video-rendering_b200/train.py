@@ -52,6 +52,74 @@ class FlatGradBucket:
         self.scatter()
 
 
+class ParamBucket:
+    """Parameters, gradients and Adam state of one network as flat fp32 buffers.
+
+    * every parameter's storage is re-pointed into ``flat_p`` and its ``.grad`` into ``flat_g`` (views): the weight-gradient
+      kernels accumulate straight into the bucket (networks._ChainEngine.backward), nothing is gathered or scattered;
+    * ``all_reduce_async`` launches ONE NCCL all-reduce of ``flat_g`` as soon as the network's backward has finished
+      (networks: ``after_backward`` hook) so that it runs under the remaining backward of the other networks;
+    * ``adam_step`` is one native launch (nhvr_adam_step) on CUDA; the 1 / world_size of the mean is folded into it.
+    On CPU (the gloo tests of the host logic) the same class falls back to torch arithmetic for the update."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 2e-4, beta1: float = 0.5, beta2: float = 0.999, eps: float = 1e-8,
+                 owners: Iterable[torch.nn.Module] = ()):
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.n = (n + 3) // 4 * 4
+        self.flat_p = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat_p[off:off + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat_p[off:off + k].view_as(p)
+            p.grad = self.flat_g[off:off + k].view_as(p)
+            p._nhvr_direct_grad = True
+            off += k
+        self.lr, self.b1, self.b2, self.eps = lr, beta1, beta2, eps
+        self.steps = 0
+        self.work = None
+        self.world = 1
+        self.owners = [m for o in owners for m in o.modules()]
+
+    def zero_grad(self) -> None:
+        self.flat_g.zero_()
+
+    def all_reduce_async(self, group=None) -> None:
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        self.world = dist.get_world_size(group)
+        self.work = dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+    def wait(self) -> None:
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+
+    def adam_step(self) -> None:
+        self.wait()
+        self.steps += 1
+        gs = 1.0 / self.world
+        if self.flat_p.is_cuda:
+            from . import capi
+            capi.check(capi.load().nhvr_adam_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.n,
+                                                  self.lr, self.b1, self.b2, self.eps, gs, self.steps, capi.stream_ptr()), "nhvr_adam_step")
+        else:                                                   # host-logic tests only
+            g = self.flat_g * gs
+            self.m.mul_(self.b1).add_(g, alpha=1 - self.b1)
+            self.v.mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
+            bc1, bc2 = 1 - self.b1 ** self.steps, 1 - self.b2 ** self.steps
+            self.flat_p.addcdiv_(self.m, self.v.sqrt() / bc2 ** 0.5 + self.eps, value=-self.lr / bc1)
+        self.world = 1
+        for mod in self.owners:                                 # the kernel wrote the storage behind the parameters' backs:
+            mod.ext_version = getattr(mod, "ext_version", 0) + 1    # packed-weight caches key on this counter too
+
+
 class UVPretrainer:
     """configs[1]: UV generator pre-train step (forward, objective, backward, optional DDP all-reduce, Adam)."""
 
@@ -59,17 +127,17 @@ class UVPretrainer:
                  distributed: bool = False):
         self.net = netTransG
         self.lambda_uv, self.lambda_prob = lambda_uv, lambda_prob
-        self.opt = torch.optim.Adam(self.net.parameters(), lr=lr, betas=(beta1, 0.999))
-        self.bucket: Optional[FlatGradBucket] = FlatGradBucket(self.net.parameters()) if distributed else None
+        self.bucket = ParamBucket(self.net.parameters(), lr, beta1, owners=[self.net])
+        self.distributed = distributed
+        if distributed:
+            self.net._after_backward = self.bucket.all_reduce_async
 
     def step(self, pose: torch.Tensor, dp_i: torch.Tensor, dp_uv: torch.Tensor) -> torch.Tensor:
-        self.opt.zero_grad(set_to_none=True)
+        self.bucket.zero_grad()
         uvp = self.net(pose)
         loss = losses.uv_prob_objective(uvp, dp_i, dp_uv, self.lambda_uv, self.lambda_prob)
         loss.backward()
-        if self.bucket is not None:
-            self.bucket.all_reduce_mean()
-        self.opt.step()
+        self.bucket.adam_step()
         return loss.detach()
 
 
@@ -101,10 +169,25 @@ class RenderTrainer:
         self.pipe, self.netD = pipe, netD
         self.lam = dict(feat=lambda_feat, l2=lambda_l2, uv=lambda_uv, prob=lambda_prob, temp=lambda_temp)
         self.n_layers_D, self.num_D = n_layers_D, num_D
-        self.opt_G = torch.optim.Adam(self.pipe.parameters(), lr=lr, betas=(beta1, 0.999))
-        self.opt_D = torch.optim.Adam(self.netD.parameters(), lr=lr, betas=(beta1, 0.999))
-        self.bucket_G = FlatGradBucket(self.pipe.parameters()) if distributed else None
-        self.bucket_D = FlatGradBucket(self.netD.parameters()) if distributed else None
+        # one flat bucket per network: its all-reduce starts when that network's backward ends and overlaps the rest
+        self.buckets_G = {"netG": ParamBucket(pipe.netG.parameters(), lr, beta1, owners=[pipe.netG]),
+                          "netBG": ParamBucket(pipe.netBG.parameters(), lr, beta1, owners=[pipe.netBG]),
+                          "netTransG": ParamBucket(pipe.netTransG.parameters(), lr, beta1, owners=[pipe.netTransG]),
+                          "tex": ParamBucket([pipe.atlas, pipe.bg], lr, beta1)}
+        self.bucket_D = ParamBucket(netD.parameters(), lr, beta1, owners=[netD])
+        self.distributed = distributed
+        self._d_backwards = 0
+        if distributed:
+            for name in ("netG", "netBG", "netTransG"):
+                getattr(pipe, name)._after_backward = self.buckets_G[name].all_reduce_async
+            netD._after_backward = self._d_backward_done
+
+    def _d_backward_done(self) -> None:
+        """The discriminator runs twice per scale under its own loss (fake detached, real): its bucket is complete after
+        2 * num_D weight-gradient backwards."""
+        self._d_backwards += 1
+        if self._d_backwards == 2 * self.num_D:
+            self.bucket_D.all_reduce_async()
 
     def step(self, batch: dict) -> dict:
         """pix2pixHD's optimize_parameters order: every discriminator pass of the step (fake detached, real, fake for the
@@ -129,18 +212,20 @@ class RenderTrainer:
                   + losses.mse_diff(fake, real1, lam["l2"])
                   + losses.uv_prob_objective(r1["uvp"], batch["dp_i"], batch["dp_uv"], lam["uv"], lam["prob"])
                   + losses.temporal_diff(fake, r0["out"], batch["flow_inv"], lam["temp"]))
-        # ---- generator side
-        self.opt_G.zero_grad(set_to_none=True)
+        # ---- generator side (the discriminator's weights are frozen under loss_G: its backward yields input grads only)
+        for b in self.buckets_G.values():
+            b.zero_grad()
+        self.bucket_D.zero_grad()
+        self._d_backwards = 0
         loss_G.backward()
-        if self.bucket_G is not None:
-            self.bucket_G.all_reduce_mean()
-        self.opt_G.step()
-        # ---- discriminator
-        self.opt_D.zero_grad(set_to_none=True)
+        if self.distributed:
+            self.buckets_G["tex"].all_reduce_async()
+        # ---- discriminator (its all-reduce and the generator side's run under each other's backward / update)
         loss_D.backward()
-        if self.bucket_D is not None:
-            self.bucket_D.all_reduce_mean()
-        self.opt_D.step()
+        for b in self.buckets_G.values():
+            b.adam_step()
+        self.bucket_D.adam_step()
+        pipe.ext_version = getattr(pipe, "ext_version", 0) + 1
         return {"loss_D": loss_D.detach(), "loss_G": loss_G.detach()}
 
 

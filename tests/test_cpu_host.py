@@ -298,3 +298,27 @@ def test_texture_grid_layout_round_trip_and_tex_flags_parse():
     to.parser.add_argument("--synthetic_steps", type=int, default=0)
     opt = to.parse(argv)
     assert opt.input_nc == 81 and opt.loadSize == 200 and opt.n_blocks_global == 5 and opt.ngf_global == 64 and opt.use_mask_texture
+
+
+def test_param_bucket_matches_torch_adam_and_keeps_views():
+    """train.ParamBucket (host arithmetic path): parameters and gradients live in flat buffers as views; three Adam steps
+    equal torch.optim.Adam(lr 2e-4, betas (0.5, 0.999)); the 1 / world_size of a summed all-reduce is folded in."""
+    from nhvr_b200.train import ParamBucket
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))
+    ref = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))
+    ref.load_state_dict(net.state_dict())
+    opt = torch.optim.Adam(ref.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    bucket = ParamBucket(net.parameters(), 2e-4, 0.5)
+    assert all(p.data_ptr() >= bucket.flat_p.data_ptr() for p in net.parameters()) and bucket.n % 4 == 0
+    x = torch.randn(11, 7)
+    for _ in range(3):
+        bucket.zero_grad()
+        net(x).square().mean().backward()                       # autograd accumulates INTO the flat views
+        assert all(p.grad.data_ptr() >= bucket.flat_g.data_ptr() for p in net.parameters())
+        bucket.adam_step()
+        opt.zero_grad()
+        ref(x).square().mean().backward()
+        opt.step()
+    for p, q in zip(net.parameters(), ref.parameters()):
+        assert torch.allclose(p, q, atol=1e-7, rtol=1e-5)

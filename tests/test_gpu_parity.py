@@ -700,3 +700,30 @@ def test_unfold_texture_matches_oracle_and_inverts_the_lookup(cuda_dev):
     unf2.add(frames.to(cuda_dev), parts.contiguous().to(cuda_dev), uv.unsqueeze(0).expand(24, 2, S, S).contiguous().to(cuda_dev))
     back = unf2.atlas().cpu()
     assert (back - atlas).abs().max().item() <= 1e-4
+
+
+def test_native_adam_matches_torch(cuda_dev):
+    """nhvr_adam_step over a flat bucket against torch.optim.Adam on the same gradients, 4 steps; and the engines see the
+    update (packed weights are re-packed through the bucket's ext_version)."""
+    from nhvr_b200.train import ParamBucket
+    net, ref = _pair_G(cuda_dev, 3, 3, 16, "global", 1, 1, seed=71)
+    ref.train()
+    opt = torch.optim.Adam(ref.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    bucket = ParamBucket(net.parameters(), 2e-4, 0.5, owners=[net])
+    x = torch.rand(2, 3, 32, 32, device=cuda_dev) * 2 - 1
+    with torch.no_grad():
+        y0 = net(x)
+    for _ in range(4):
+        opt.zero_grad()
+        ref(x).square().mean().backward()
+        bucket.zero_grad()
+        for p, q in zip(net.parameters(), ref.parameters()):
+            p.grad.copy_(q.grad)                                  # identical gradients: isolates the optimiser
+        opt.step()
+        bucket.adam_step()
+    for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+        assert torch.allclose(p, q, atol=2e-7, rtol=1e-5), k
+    with torch.no_grad():
+        y1, y1_ref = net(x), ref(x)
+    assert (y1 - y0).abs().max().item() > 1e-5                     # the inference engine picked the new weights up
+    assert (y1 - y1_ref).abs().max().item() <= 2e-2

@@ -32,8 +32,8 @@ for i in range(n):
     ms = sum(recs[i + r * n][2].elapsed_time(recs[i + r * n][3]) for r in range(REP)) / REP
     unit = "TFLOP/s" if kind.startswith("conv") else "GB/s"
     rate = work / ms / (1e9 if kind.startswith("conv") else 1e6)
-    tot[kind] = tot.get(kind, 0.0) + ms
-    print(f"{i:3d} {kind:10s} work={work:.3e} {ms*1e3:8.1f} us  {rate:8.1f} {unit}")
+    tot[kind.split(":")[0]] = tot.get(kind.split(":")[0], 0.0) + ms
+    print(f"{i:3d} {kind:28s} work={work:.3e} {ms*1e3:8.1f} us  {rate:8.1f} {unit}")
 print({k: round(v, 3) for k, v in tot.items()}, "sum ms", round(sum(tot.values()), 3))
 
 # whole step under a CUDA graph
