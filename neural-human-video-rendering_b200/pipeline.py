@@ -131,10 +131,8 @@ class RenderPipeline(nn.Module):
         if out is None:
             out = torch.empty(B, T, 3, H, W, dtype=torch.float32, device=dev)
         if poses.is_cuda and out.is_cuda:
-            for t in range(T):
-                step.pose.copy_(poses[:, t], non_blocking=True)
-                step.run()
-                out[:, t].copy_(step.out, non_blocking=True)
+            step.drive(T, lambda t, dst: dst.copy_(poses[:, t], non_blocking=True),
+                       lambda t: out[:, t].copy_(step.out, non_blocking=True))
             return out
         step.stream_clips(poses, out)
         return out
@@ -154,11 +152,16 @@ class RenderPipeline(nn.Module):
         step.stream_keypoints(kps, out, src_size)
         return out
 
-    def step_graph(self, B: int, H: int, W: int, use_graph: bool = True) -> "_StepGraph":
-        key = (B, H, W, use_graph, self.netTransG.precision, self.netG.precision, self.netBG.precision, self.use_mask_texture)
+    def step_graph(self, B: int, H: int, W: int, use_graph: bool = True, pipelined: Optional[bool] = None) -> "_StepGraph":
+        """pipelined (default: automatically for B <= 2 under a CUDA graph): the UV generator of frame t+1 runs on a second
+        stream next to the temporal generator of frame t (_PipelinedStepGraph) - with one or two clips a conv launch has
+        fewer tiles than the GPU has CTA slots, and only the temporal generator depends on the previous frame."""
+        if pipelined is None:
+            pipelined = use_graph and B * ((H + 127) // 128) * ((W + 127) // 128) <= 32
+        key = (B, H, W, use_graph, pipelined, self.netTransG.precision, self.netG.precision, self.netBG.precision, self.use_mask_texture)
         g = self._graphs.get(key)
         if g is None:
-            g = _StepGraph(self, B, H, W, use_graph)
+            g = _PipelinedStepGraph(self, B, H, W) if pipelined else _StepGraph(self, B, H, W, use_graph)
             self._graphs[key] = g
         g.refresh()           # weights / atlas / background may have changed since the graph was captured
         return g
@@ -221,6 +224,29 @@ class _StepGraph:
     def reset(self) -> None:
         self.prev.zero_()
 
+    # ---- frame protocol shared with _PipelinedStepGraph
+    lookahead = False                      # True: frame t+1's pose must be in its slot BEFORE advance(t)
+
+    def pose_slot(self, t: int) -> torch.Tensor:
+        """Buffer frame t's pose maps [B, pose_nc, H, W] must be written to."""
+        return self.pose
+
+    def advance(self, t: int) -> None:
+        """Render frame t (its pose is in pose_slot(t)); afterwards self.out holds the frames."""
+        self.run()
+
+    def drive(self, T: int, write_pose, emit) -> None:
+        """write_pose(t, dst) enqueues frame t's pose maps into dst; emit(t) consumes self.out (frame t)."""
+        self.reset()
+        write_pose(0, self.pose_slot(0))
+        for t in range(T):
+            if self.lookahead and t + 1 < T:
+                write_pose(t + 1, self.pose_slot(t + 1))
+            self.advance(t)
+            emit(t)
+            if not self.lookahead and t + 1 < T:
+                write_pose(t + 1, self.pose_slot(t + 1))
+
     def refresh(self) -> None:
         """Re-pack weights, re-evaluate the background net and re-copy the atlas if any parameter changed since the
         last call (training step, load_state_dict): everything is updated in the buffers the captured graph reads."""
@@ -259,12 +285,12 @@ class _StepGraph:
         h2d, d2h = st["h2d"], st["d2h"]
         h2d.wait_stream(cur)
         d2h.wait_stream(cur)
-        used = [False, False]
+        used, pused = [False, False], [False, False]
 
         def fetch(t: int) -> None:
             s = t & 1
             with torch.cuda.stream(h2d):
-                if used[s]:
+                if pused[s]:
                     h2d.wait_event(st["pose_free"][s])
                 if poses.is_cuda:
                     st["pose"][s].copy_(poses[:, t], non_blocking=True)
@@ -273,17 +299,24 @@ class _StepGraph:
                         st["pose"][s][b].copy_(poses[b, t], non_blocking=True)
                 st["pose_ready"][s].record(h2d)
 
-        fetch(0)
-        for t in range(T):
+        fetched = set()
+
+        def write_pose(t: int, dst: torch.Tensor) -> None:
             s = t & 1
-            if t + 1 < T:
-                fetch(t + 1)
+            if t not in fetched:
+                fetch(t); fetched.add(t)
             cur.wait_event(st["pose_ready"][s])
-            self.pose.copy_(st["pose"][s], non_blocking=True)
+            dst.copy_(st["pose"][s], non_blocking=True)
             st["pose_free"][s].record(cur)
-            self.run()
+            pused[s] = True
+            if t + 1 < T and (t + 1) not in fetched:           # prefetch the next frame's poses under this frame's kernels
+                fetch(t + 1); fetched.add(t + 1)
+
+        def emit(t: int) -> None:
             self._emit_frame(t, out, st, used)
-            used[s] = True
+            used[t & 1] = True
+
+        self.drive(T, write_pose, emit)
         cur.wait_stream(d2h)
         cur.wait_stream(h2d)
         if not out.is_cuda:
@@ -319,11 +352,13 @@ class _StepGraph:
         st["d2h"].wait_stream(cur)
         used = [False, False]
         kps = kps.to(self.pose.device, torch.float32)
-        for t in range(T):
-            ops.pose_rasterize(kps[:, t].contiguous(), H, self.pose.shape[1], src_size, out=self.pose)
-            self.run()
+        nc = self.pose.shape[1]
+
+        def emit(t: int) -> None:
             self._emit_frame(t, out, st, used)
             used[t & 1] = True
+
+        self.drive(T, lambda t, dst: ops.pose_rasterize(kps[:, t].contiguous(), H, nc, src_size, out=dst), emit)
         cur.wait_stream(st["d2h"])
         if not out.is_cuda:
             st["d2h"].synchronize()
@@ -340,6 +375,90 @@ class _StepGraph:
             self.graph.replay()
         else:
             self._body()
+
+
+class _PipelinedStepGraph(_StepGraph):
+    """Frame step for ONE or TWO clips: a two-stage software pipeline across frames inside one CUDA graph.
+
+    Only the temporal generator depends on the previous frame; the UV generator and the texture lookup of frame t+1 need
+    nothing but its pose.  With a single clip every conv launch has fewer tiles (130 at 128^2) than the GPU has CTA slots
+    (296), so the graph of step t forks into two streams: netG(tex_t, pose_t, prev) -> composite, and next to it
+    netTransG(pose_{t+1}) -> lookup -> tex_{t+1}; the two nets' CTAs share the SMs.  Two graphs alternate (buffer parity)."""
+
+    lookahead = True
+
+    def __init__(self, pipe: "RenderPipeline", B: int, H: int, W: int):
+        capi.require_device()
+        self.pipe = pipe
+        dev = pipe.bg.device
+        self.poses = [torch.zeros(B, pipe.pose_nc, H, W, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.texs = [torch.zeros(B, pipe.tex_nc, H, W, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.pose = self.poses[0]              # shape / device carrier for the staging helpers
+        self.prev = torch.zeros(B, 3, H, W, dtype=torch.float32, device=dev)
+        self.out = self.prev
+        self.bg_refined = pipe.refine_bg()
+        self.atlas_cl = pipe.atlas_channels_last().clone()
+        self.engT = pipe.netTransG.engine(B, H, W)
+        self.engG = pipe.netG.engine(B, H, W)
+        self._version = pipe.state_version()
+        self._stage = None
+        self.use_graph = True
+        self.side = torch.cuda.Stream(device=dev)
+        self.graph = None
+        self.graphs: List[torch.cuda.CUDAGraph] = []
+        self.launches_per_step = 0
+        self._capture()
+
+    def _uv_stage(self, p: int) -> None:
+        """UV generator + lookup for the pose in slot p -> texs[p]."""
+        pipe = self.pipe
+        uvp = self.engT.run([self.poses[p]])
+        ops.texture_sample(uvp, self.atlas_cl, pipe.tex_nc, pipe.use_mask_texture, tex_out=self.texs[p], want_indices=False)
+
+    def _g_stage(self, p: int) -> None:
+        fgm = self.engG.run([self.texs[p], self.poses[p], self.prev])
+        ops.composite(fgm, self.bg_refined, out=self.prev)
+
+    def _frame(self, p: int) -> None:
+        """Frame in slot p is rendered while the frame in slot 1-p gets its texture (fork / join on the side stream)."""
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            self._uv_stage(1 - p)
+        self._g_stage(p)
+        cur.wait_stream(self.side)
+
+    def _capture(self) -> None:
+        dev = self.prev.device
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):                              # warm-up: attribute set-up, weight packing
+            self._uv_stage(0)
+            for p in (0, 1):
+                self._frame(p)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graphs = []
+        for p in (0, 1):
+            g = torch.cuda.CUDAGraph()
+            n0 = capi.launch_count()
+            with torch.cuda.graph(g):
+                self._frame(p)
+            self.launches_per_step = capi.launch_count() - n0
+            self.graphs.append(g)
+        self.graph = self.graphs[0]
+        self.reset()
+
+    def pose_slot(self, t: int) -> torch.Tensor:
+        return self.poses[t & 1]
+
+    def advance(self, t: int) -> None:
+        if t == 0:
+            self._uv_stage(0)                                   # pipeline prologue: frame 0's texture
+        self.graphs[t & 1].replay()
+
+    def run(self) -> None:
+        raise capi.NhvrError("the pipelined step is driven through advance(t) / drive()")
 
 
 # ------------------------------------------------------------------ clip sharding (no collective)

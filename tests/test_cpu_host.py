@@ -322,3 +322,54 @@ def test_param_bucket_matches_torch_adam_and_keeps_views():
         opt.step()
     for p, q in zip(net.parameters(), ref.parameters()):
         assert torch.allclose(p, q, atol=1e-7, rtol=1e-5)
+
+
+def _gloo_bucket_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from nhvr_b200.train import ParamBucket
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    torch.manual_seed(0)                                         # identical initial weights on every rank
+    net = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.Linear(4, 2))
+    bucket = ParamBucket(net.parameters(), 2e-4, 0.5)
+    g = torch.Generator().manual_seed(100 + rank)                # a different data shard per rank
+    x = torch.randn(8, 6, generator=g)
+    for _ in range(2):
+        bucket.zero_grad()
+        net(x).square().mean().backward()
+        bucket.all_reduce_async()                                # what the networks' after_backward hook fires
+        bucket.adam_step()                                       # waits, folds 1 / world into the update
+    if rank == 0:
+        q.put((bucket.flat_p.tolist(), x.tolist()))
+    else:
+        q.put(("other", bucket.flat_p.tolist(), x.tolist()))
+    dist.destroy_process_group()
+
+
+def test_param_bucket_data_parallel_world_size_2_gloo():
+    """Two ranks with different batches: asynchronous all-reduce of the flat gradient bucket + Adam gives every rank the
+    parameters of ONE process trained on the mean gradient of both shards."""
+    import torch.multiprocessing as mp
+    from nhvr_b200.train import ParamBucket
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120), q.get(timeout=120)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    r0 = next(g for g in got if g[0] != "other")
+    r1 = next(g for g in got if g[0] == "other")
+    assert r0[0] == r1[1]                                        # both ranks hold identical parameters
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.Linear(4, 2))
+    bucket = ParamBucket(net.parameters(), 2e-4, 0.5)
+    xs = [torch.tensor(r0[1]), torch.tensor(r1[2])]
+    for _ in range(2):
+        bucket.zero_grad()
+        (0.5 * (net(xs[0]).square().mean() + net(xs[1]).square().mean())).backward()
+        bucket.adam_step()
+    assert torch.allclose(bucket.flat_p, torch.tensor(r0[0]), atol=1e-7)
