@@ -315,7 +315,8 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     def barrier():
         if dist is not None:
@@ -424,8 +425,9 @@ def main():
                              "synthetic DensePose targets%s" % (TS, TS, TB, ", NCCL gradient all-reduce" if world > 1 else ""),
                  "steps_per_s": 1000.0 / tms, "ms_per_step": tms, "samples_per_s": world * TB * 1000.0 / tms,
                  "conv_tflops_fwd_dgrad_wgrad": 3.0 * eng.flops / (tms * 1e-3) / 1e12, "final_loss": float(last)}
+        rl = train_roofline(lambda: trainer.step(pose, dp_i, dp_uv), pk)       # a training step holds collectives: every rank runs it
         if rank == 0:
-            train["roofline"] = train_roofline(lambda: trainer.step(pose, dp_i, dp_uv), pk)
+            train["roofline"] = rl
         del trainer, netT, eng
         torch.cuda.empty_cache()
         if args.train_e2e_batch > 0:
@@ -449,8 +451,9 @@ def main():
                 ems = rank_max(t0.elapsed_time(t1)) / steps
                 res = {"steps_per_s": 1000.0 / ems, "ms_per_step": ems, "samples_per_s": world * batch * 1000.0 / ems,
                        "loss_G": float(o["loss_G"]), "loss_D": float(o["loss_D"])}
+                rl = train_roofline(lambda: tr.step(bt), pk)                     # every rank (collectives inside)
                 if rank == 0:
-                    res["roofline"] = train_roofline(lambda: tr.step(bt), pk)
+                    res["roofline"] = rl
                 capi.check_overflow(dev, "training leg")
                 return res
             EB = args.train_e2e_batch
