@@ -148,11 +148,12 @@ int nhvr_conv_pack_weights(const nhvr_conv_plan* p, const float* w, void* packed
 int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const void* packed_w, const float* bias,
                       void* out, const nhvr_act_desc* out_desc, double* stats, void* stream);
 
-/* Centring shift of a FIRST layer's statistics: writes s[n][co] = sum_ci (sum_taps w[co][ci][tap]) * mean(src[n][ci]) (sampled
- * mean) into slot 2 of the zeroed statistics record, i.e. the conv output wherever the input is flat.  Stick-figure pose maps
+/* Centring shift of a FIRST layer's statistics: writes s[n][co] = sum_ci wsum[co][ci] * mean(src[n][ci]) (mean over 256 sampled
+ * pixels; wsum = the filter summed over its taps) into slot 2 of the zeroed statistics record, i.e. the conv output wherever
+ * the input is flat.  Stick-figure pose maps
  * (keypoints/*.json rasterised, start.sh:9,24) are ~98 % background: the stem output is c + small with mean^2/var up to 250,
- * and un-centred sums lose 2-3 digits of the variance.  w: fp32 [Cout][Cin][taps]; src as in nhvr_pack_nchw (Cin <= 32). */
-int nhvr_stem_stat_shift(const float* w, int32_t Cout, int32_t Cin, int32_t taps, const float* const* src, const int32_t* src_c,
+ * and un-centred sums lose 2-3 digits of the variance.  wsum: fp32 [Cout][Cin]; src as in nhvr_pack_nchw (Cin <= 32, H*W >= 256). */
+int nhvr_stem_stat_shift(const float* wsum, int32_t Cout, int32_t Cin, const float* const* src, const int32_t* src_c,
                          int32_t nsrc, int32_t N, int32_t H, int32_t W, double* stats, void* stream);
 
 /* ---- InstanceNorm2d(affine=False) apply + activation (+ residual) + halo write ----

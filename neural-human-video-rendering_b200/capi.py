@@ -50,7 +50,7 @@ SYMBOLS = {
     "nhvr_set_overflow_flag": (C.c_int, [_P]),
     "nhvr_act_bytes": (C.c_size_t, [C.POINTER(ActDesc)]),
     "nhvr_pack_nchw": (C.c_int, [C.POINTER(_P), C.POINTER(C.c_int32), C.c_int32, _P, C.POINTER(ActDesc), _P]),
-    "nhvr_stem_stat_shift": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+    "nhvr_stem_stat_shift": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int32), C.c_int32, C.c_int32,
                                        C.c_int32, C.c_int32, _P, _P]),
     "nhvr_unpack_nchw": (C.c_int, [_P, C.POINTER(ActDesc), _P, C.c_int32, _P]),
     "nhvr_conv_plan_create": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(_P)]),

@@ -226,8 +226,9 @@ __global__ void __launch_bounds__(256, 4) in_apply_kernel(const __grid_constant_
 // row (mirror / zero halo rows), per unit only the column mirror remains.
 // HILO: split-precision activations (nhvr_act_desc.hilo): raw, residual and destination all carry hi + lo planes; the
 // value is rebuilt in fp32, normalised, and split again (the residual stream of a ResnetBlock keeps ~22 bits).
-template <bool HAS_RES, bool HILO>
-__global__ void __launch_bounds__(256, HILO ? 2 : 4) in_apply_rows_kernel(const __grid_constant__ ApplyParams P) {
+// HILO: 0 = plain 16-bit activations; 1, 2, 3 = split precision with 3, 5, 2 columns per lane in flight
+template <bool HAS_RES, int HILO>
+__global__ void __launch_bounds__(256, HILO == 0 ? 4 : HILO == 3 ? 3 : 2) in_apply_rows_kernel(const __grid_constant__ ApplyParams P) {
   const ActGeom& g = P.dg;
   const int np = blockIdx.y;                                  // n * (logical planes) + logical plane
   const int CL = HILO ? g.C8 >> 1 : g.C8;
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(256, HILO ? 2 : 4) in_apply_rows_kernel(const 
   for (int e = 0; e < 8; ++e) { scale[e] = s_norm[e]; shift[e] = s_norm[8 + e]; }
   const bool reflect = g.halo != NHVR_HALO_ZERO;
   const uint64_t once = l2_policy_evict_first();      // the raw tensor is dead after this pass
-  constexpr int COLS = HILO ? 3 : 5;   // 160 columns per pass: the 130-wide (128^2) rows take one pass, 258 two, 518 four
+  constexpr int COLS = HILO == 0 ? 5 : HILO == 1 ? 3 : HILO == 2 ? 5 : 2;   // 160 columns per pass: the 130-wide (128^2) rows take one pass, 258 two, 518 four
   const int Hq = g.Hp >> 1, Wq = g.Wp >> 1;
   // Range guard (nhvr_set_overflow_flag): a 16-bit overflow of the conv output needs |x| > 65504, hence a plane whose
   // sum of squares (taken from the un-rounded fp32 accumulators) reaches 65504^2.  Only such planes are scanned for
@@ -332,55 +333,51 @@ __global__ void __launch_bounds__(256, HILO ? 2 : 4) in_apply_rows_kernel(const 
   }
 }
 
-// Centring shift of a stem's InstanceNorm statistics: s[n][co] = sum_ci (sum_taps w[co][ci][tap]) * m[n][ci] with m the
-// (sampled) per-channel mean of the input image - the value the conv output takes wherever the input is flat.  Stick-
+// Centring shift of a stem's InstanceNorm statistics: s[n][co] = sum_ci wsum[co][ci] * m[n][ci] with wsum the filter summed
+// over its taps and m the (sampled, 256 pixels) per-channel mean of the input image - the value the conv output takes wherever the input is flat.  Stick-
 // figure pose maps are ~98 % background, so the stem output is c + small with mean^2 / var up to ~250; centred sums
 // keep E[(x-s)^2] - E[x-s]^2 free of that cancellation.  Any s is mathematically valid (it only re-centres the sums).
 struct StemShiftParams {
   const float* src[4];
   int32_t src_c[4];
-  int32_t nsrc, Cin, Cout, taps, C8out8;
+  int32_t nsrc, Cin, Cout, C8out8;
   int64_t HW;
-  const float* w;      // [Cout][Cin][taps]
+  const float* wsum;   // [Cout][Cin]: the filter summed over its taps
   double* stats;       // [N][C8out8][4]: slot 2 receives s
 };
+// one block per image: 256 samples per input channel (all loads in flight before the reductions), then a Cout x Cin GEMV
 __global__ void __launch_bounds__(256) stem_stat_shift_kernel(const __grid_constant__ StemShiftParams P) {
   __shared__ float m[32];
-  __shared__ float red[8];
+  __shared__ float red[32][8];
   const int n = blockIdx.x;
-  const int64_t step = P.HW > 4096 ? P.HW / 4096 : 1;
-  int cbase = 0;
-  for (int s = 0; s < P.nsrc; ++s) {
-    for (int c = 0; c < P.src_c[s]; ++c) {
-      const float* p = P.src[s] + ((int64_t)n * P.src_c[s] + c) * P.HW;
-      float acc = 0.f;
-      int cnt = 0;
-      for (int64_t i = (int64_t)threadIdx.x * step; i < P.HW; i += 256 * step) { acc += __ldg(p + i); ++cnt; }
-      float tot = acc, num = (float)cnt;
+  const int64_t stride = P.HW >= 256 ? P.HW / 256 : 1;
+  const int64_t at = min((int64_t)threadIdx.x * stride + (stride >> 1), P.HW - 1);
+  float v[32];
+  int c = 0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { tot += __shfl_xor_sync(0xffffffffu, tot, o); num += __shfl_xor_sync(0xffffffffu, num, o); }
-      __syncthreads();
-      if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = tot; }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int k = 0; k < 8; ++k) t += red[k];
-        const int64_t nsamp = (P.HW + step - 1) / step;
-        if (cbase + c < 32) m[cbase + c] = t / (float)nsamp;
-      }
-      (void)num;
+  for (int s = 0; s < 4; ++s) {
+    if (s < P.nsrc) {
+      for (int k = 0; k < P.src_c[s] && c < 32; ++k, ++c) v[c] = __ldg(P.src[s] + ((int64_t)n * P.src_c[s] + k) * P.HW + at);
     }
-    cbase += P.src_c[s];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < P.Cin && k < 32; ++k) {
+    float t = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) red[k][warp] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < P.Cin && threadIdx.x < 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    m[threadIdx.x] = t * (1.f / 256.f);
   }
   __syncthreads();
   for (int co = threadIdx.x; co < P.Cout; co += 256) {
     float sft = 0.f;
-    for (int ci = 0; ci < P.Cin; ++ci) {
-      const float* wp = P.w + ((int64_t)co * P.Cin + ci) * P.taps;
-      float ws = 0.f;
-      for (int t = 0; t < P.taps; ++t) ws += wp[t];
-      sft += ws * m[ci];
-    }
+    for (int ci = 0; ci < P.Cin; ++ci) sft += __ldg(P.wsum + (int64_t)co * P.Cin + ci) * m[ci];
     P.stats[((int64_t)n * P.C8out8 + co) * 4 + 2] = (double)sft;
   }
 }
@@ -429,10 +426,10 @@ extern "C" int nhvr_pack_nchw(const float* const* src, const int32_t* src_c, int
   return NHVR_OK;
 }
 
-extern "C" int nhvr_stem_stat_shift(const float* w, int32_t Cout, int32_t Cin, int32_t taps, const float* const* src, const int32_t* src_c,
+extern "C" int nhvr_stem_stat_shift(const float* wsum, int32_t Cout, int32_t Cin, const float* const* src, const int32_t* src_c,
                                     int32_t nsrc, int32_t N, int32_t H, int32_t W, double* stats, void* stream) {
-  if (!w || !src || !src_c || !stats) return NHVR_ERR_NULL;
-  if (nsrc < 1 || nsrc > 4 || Cin < 1 || Cin > 32 || Cout < 1 || taps < 1 || N < 1 || H < 1 || W < 1) return NHVR_ERR_SHAPE;
+  if (!wsum || !src || !src_c || !stats) return NHVR_ERR_NULL;
+  if (nsrc < 1 || nsrc > 4 || Cin < 1 || Cin > 32 || Cout < 1 || N < 1 || H < 1 || W < 1 || (int64_t)H * W < 256) return NHVR_ERR_SHAPE;
   if (!arch_ok_cached()) return NHVR_ERR_ARCH;
   StemShiftParams P;
   int csum = 0;
@@ -442,10 +439,10 @@ extern "C" int nhvr_stem_stat_shift(const float* w, int32_t Cout, int32_t Cin, i
     if (i < nsrc) { if (!src[i] || src_c[i] <= 0) return NHVR_ERR_NULL; csum += src_c[i]; }
   }
   if (csum != Cin) return NHVR_ERR_SHAPE;
-  P.nsrc = nsrc; P.Cin = Cin; P.Cout = Cout; P.taps = taps;
+  P.nsrc = nsrc; P.Cin = Cin; P.Cout = Cout;
   P.C8out8 = ((Cout + 7) / 8 + 1) / 2 * 2 * 8;      // channel count of the statistics record: Cout8 (even) * 8
   P.HW = (int64_t)H * W;
-  P.w = w; P.stats = stats;
+  P.wsum = wsum; P.stats = stats;
   stem_stat_shift_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(P);
   count_launch();
   cudaError_t e = cudaGetLastError();
@@ -509,10 +506,14 @@ extern "C" int nhvr_in_apply(const void* raw, const nhvr_act_desc* raw_desc, con
     { static const char* e = std::getenv("NHVR_APPLY_GY"); if (e && std::atoi(e) > 0) gy = std::min(std::atoi(e), gy); }
     dim3 grid_r(gy, planes);
     if (hilo) {
-      if (P.res) in_apply_rows_kernel<true, true><<<grid_r, 256, 0, (cudaStream_t)stream>>>(P);
-      else in_apply_rows_kernel<false, true><<<grid_r, 256, 0, (cudaStream_t)stream>>>(P);
-    } else if (P.res) in_apply_rows_kernel<true, false><<<grid_r, 256, 0, (cudaStream_t)stream>>>(P);
-    else in_apply_rows_kernel<false, false><<<grid_r, 256, 0, (cudaStream_t)stream>>>(P);
+      int variant = 3;      // measured (tools/apply_bench.py): 2 columns in flight at 3 blocks / SM: 4.1-5.4 TB/s vs 3.4-4.9 for 3 columns at 2 blocks
+      if (const char* e = std::getenv("NHVR_APPLY_HILO_VARIANT")) variant = std::atoi(e);      // experiments
+      cudaStream_t st_ = (cudaStream_t)stream;
+      if (variant == 2) { if (P.res) in_apply_rows_kernel<true, 2><<<grid_r, 256, 0, st_>>>(P); else in_apply_rows_kernel<false, 2><<<grid_r, 256, 0, st_>>>(P); }
+      else if (variant != 1) { if (P.res) in_apply_rows_kernel<true, 3><<<grid_r, 256, 0, st_>>>(P); else in_apply_rows_kernel<false, 3><<<grid_r, 256, 0, st_>>>(P); }
+      else { if (P.res) in_apply_rows_kernel<true, 1><<<grid_r, 256, 0, st_>>>(P); else in_apply_rows_kernel<false, 1><<<grid_r, 256, 0, st_>>>(P); }
+    } else if (P.res) in_apply_rows_kernel<true, 0><<<grid_r, 256, 0, (cudaStream_t)stream>>>(P);
+    else in_apply_rows_kernel<false, 0><<<grid_r, 256, 0, (cudaStream_t)stream>>>(P);
   } else if (hilo) {
     return NHVR_ERR_UNSUPPORTED;
   } else if (P.res) in_apply_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(P);

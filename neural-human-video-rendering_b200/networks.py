@@ -158,6 +158,12 @@ class _ChainEngine:
     def pack_weights(self) -> None:
         for L, plan in zip(self.chain, self.plans):
             plan.pack_weights(L["params"].weight)
+        if self._centres_stem(self.chain):                       # the stem's filter summed over its taps (ops.stem_stat_shift)
+            w0 = self.chain[0]["params"].weight.detach().float().sum((2, 3)).contiguous()
+            if getattr(self, "_wsum", None) is None:
+                self._wsum = w0
+            else:
+                self._wsum.copy_(w0)                             # in place: a captured graph keeps reading this buffer
 
     def maybe_repack(self) -> None:
         ver = (tuple(L["params"].weight._version for L in self.chain) + tuple(L["params"].weight.data_ptr() for L in self.chain)
@@ -170,7 +176,7 @@ class _ChainEngine:
         self.stats_all.zero_()
         if self._centres_stem(self.chain):
             # centre the stem's InstanceNorm sums on its response to the flat part of the input (stick-figure pose maps)
-            ops.stem_stat_shift(self.chain[0]["params"].weight, inputs, self.stats[0])
+            ops.stem_stat_shift(self._wsum, inputs, self.stats[0])
         ops.pack_nchw(inputs, self.in_bufs[0])
         return self.run_packed(zero_stats=False)
 

@@ -83,8 +83,9 @@ def pack_nchw(srcs: Sequence[torch.Tensor], dst: P8Buffer) -> None:
         check(load().nhvr_pack_nchw(arr, cs, n, dst.ptr, C.byref(dst.desc), stream_ptr()), "nhvr_pack_nchw")
 
 
-def stem_stat_shift(weight: torch.Tensor, srcs: Sequence[torch.Tensor], stats: torch.Tensor) -> None:
-    """nhvr_stem_stat_shift: centre the (zeroed) statistics record of a first layer on the conv output of the flat input."""
+def stem_stat_shift(wsum: torch.Tensor, srcs: Sequence[torch.Tensor], stats: torch.Tensor) -> None:
+    """nhvr_stem_stat_shift: centre the (zeroed) statistics record of a first layer on the conv output of the flat input.
+    wsum [Cout, Cin] = the stem's filter summed over its taps."""
     n = len(srcs)
     arr = (C.c_void_p * n)()
     cs = (C.c_int32 * n)()
@@ -93,10 +94,9 @@ def stem_stat_shift(weight: torch.Tensor, srcs: Sequence[torch.Tensor], stats: t
         assert t.dtype == torch.float32 and t.is_cuda
         arr[i] = t.data_ptr()
         cs[i] = t.shape[1]
-    w = weight.detach()
-    assert w.is_contiguous() and w.dtype == torch.float32
+    assert wsum.is_contiguous() and wsum.dtype == torch.float32 and wsum.dim() == 2
     N, _, H, W = keep[0].shape
-    check(load().nhvr_stem_stat_shift(w.data_ptr(), w.shape[0], w.shape[1], w.shape[2] * w.shape[3], arr, cs, n, N, H, W,
+    check(load().nhvr_stem_stat_shift(wsum.data_ptr(), wsum.shape[0], wsum.shape[1], arr, cs, n, N, H, W,
                                       stats.data_ptr(), stream_ptr()), "nhvr_stem_stat_shift")
 
 

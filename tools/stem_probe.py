@@ -24,7 +24,7 @@ for shift in (0.0,):
     raw = ops.P8Buffer(plan.raw_desc(), dev)
     stats = torch.zeros(plan.Cout8 * 8 * 4, dtype=torch.float64, device=dev)
     if len(sys.argv) > 1:
-        ops.stem_stat_shift(w, [x], stats)
+        ops.stem_stat_shift(w.sum((2, 3)).contiguous(), [x], stats)
     plan.forward(xin, raw.ptr, stats=stats)
     r = ops.unpack_nchw(raw, 64).double()
     ref = F.conv2d(F.pad(x.double(), (3,) * 4, mode="reflect"), w.double())
