@@ -47,7 +47,8 @@ enum { NHVR_CONV = 0, NHVR_CONV_TRANSPOSE = 1 /* stride 2: k3 p1 output_padding 
 enum { NHVR_EPI_RAW_STATS = 0,   /* bf16 P8 un-padded conv output + per-(n,c) sum / sum-of-squares */
        NHVR_EPI_BIAS_ACT_F32 = 1,/* bias + activation, fp32 NCHW output                            */
        NHVR_EPI_BIAS_ACT_P8 = 2, /* bias + activation, bf16 P8 output in a consumer's format       */
-       NHVR_EPI_RAW_P8 = 3       /* P8 un-padded output, no statistics (gradient convs)            */ };
+       NHVR_EPI_RAW_P8 = 3,      /* P8 un-padded output, no statistics (gradient convs)            */
+       NHVR_EPI_IN_FUSED = 4     /* internal: set by nhvr_conv_forward_in_fused on a RAW_STATS plan  */ };
 
 /* P8 activation descriptor (see header comment). */
 typedef struct nhvr_act_desc {
@@ -163,6 +164,24 @@ int nhvr_stem_stat_shift(const float* wsum, int32_t Cout, int32_t Cin, const flo
 int nhvr_in_apply(const void* raw, const nhvr_act_desc* raw_desc, const double* stats, float eps, int32_t act,
                   const void* residual, const nhvr_act_desc* res_desc,
                   void* dst, const nhvr_act_desc* dst_desc, void* stream);
+
+/* ---- conv + InstanceNorm2d + activation (+ residual) + halo write in ONE kernel (north_star: "InstanceNorm, ReLU and
+ * reflection padding are fused into conv prologues and epilogues") ----
+ * Same result as nhvr_conv_forward (RAW_STATS plan) followed by nhvr_in_apply, without the raw tensor's HBM round trip: the
+ * accumulators of a tile stay in TMEM while the CTAs of its image meet at a per-image arrival counter (after their sum /
+ * sum-of-squares atomics); then each CTA normalises its own tile from the fp32 accumulators and writes it into dst, mirrored
+ * halo copies included (a zero halo is left untouched: the buffer must have been zeroed once).
+ * Needs every CTA of an image resident at once: nhvr_conv_in_fused_supported() returns 1 when tiles-per-image x N-splits fits
+ * half the GPU's resident CTA slots (so that two such kernels on concurrent streams cannot starve each other), the plan has one
+ * M block / one accumulator per CTA and its statistics are not centred.  128 x 128 ResnetBlock layers: 130 tiles per image.
+ * stats: zeroed by the caller; on return its four slots per channel hold two replicas of {sum, sum of squares} (even / odd
+ * tiles; no centring shift on this path).  sync: device uint32 [N] arrival counters, zeroed by the caller before every launch
+ * (the engines keep them behind the statistics so that one fill re-arms both).
+ * A wait that exceeds ~2 s traps (sticky CUDA error) instead of hanging the GPU. */
+int nhvr_conv_in_fused_supported(const nhvr_conv_plan* p);
+int nhvr_conv_forward_in_fused(const nhvr_conv_plan* p, const void* in, const void* packed_w, double* stats, float eps, int32_t act,
+                               const void* residual, const nhvr_act_desc* res_desc, void* dst, const nhvr_act_desc* dst_desc,
+                               uint32_t* sync, void* stream);
 
 /* ---- keypoints -> pose maps (the step before the path: --pose_path ./keypoints of OpenPose BODY_25 JSONs, start.sh:9,24-25) ----
  * kps: device float [T][25][3] (x, y, confidence) in a src_size^2 frame; out: device float [T][pose_nc][size][size]: the

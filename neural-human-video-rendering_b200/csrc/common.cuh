@@ -192,6 +192,16 @@ NHVR_DEVINL uint4 ld_hint(const uint4* addr, uint64_t pol) {
   return w;
 }
 
+// ------------------------------------------------------------------ inter-CTA arrival counter (fused InstanceNorm epilogue)
+NHVR_DEVINL void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+NHVR_DEVINL uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 NHVR_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets lane (base_lane + i).
@@ -247,6 +257,13 @@ NHVR_DEVINL float unpack_lo(uint32_t v, int f16) {
 NHVR_DEVINL float unpack_hi(uint32_t v, int f16) {
   if (f16) { __half2 h = *reinterpret_cast<__half2*>(&v); return __high2float(h); }
   return __uint_as_float(v & 0xFFFF0000u);
+}
+
+// eight 16-bit values of one P8 unit -> fp32
+NHVR_DEVINL void unpack8f(const uint4& u, float (&v)[8], int f16) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = (e & 1) ? unpack_hi(w[e >> 1], f16) : unpack_lo(w[e >> 1], f16);
 }
 
 // a 16-byte unit of eight 16-bit values holds an inf / NaN (exponent field all ones)?

@@ -59,6 +59,16 @@ struct ConvKParams {
   int32_t stat_centred;    // RAW_STATS sums are centred on stats[n][c][2] (conv desc flag bit 4)
   int32_t out_hilo;        // RAW outputs are written as a split-precision (hilo) activation
   int32_t pair;            // 1: launched as clusters of two CTAs running cta_group::2 MMAs (weights packed per CTA half)
+  // NHVR_EPI_IN_FUSED (nhvr_conv_forward_in_fused): the InstanceNorm is finished inside this kernel.  The accumulators stay
+  // in TMEM while the CTAs of an image meet at a per-image arrival counter; then every CTA normalises its own tile and
+  // writes it (activation, + residual, mirrored halo) straight into the consumer's P8 buffer `out` with geometry `og`.
+  const uint4* res;        // residual (skip) activation, nullable; geometry sg
+  uint32_t* sync;          // [N + 1] zero-initialised: per-image arrivals, CTAs past their wait (the last one re-zeroes)
+  ActGeom sg;
+  float eps, inv_hw;
+  int32_t res_bulk;        // residual tile staged in shared memory by bulk copies (skip activation linearises like the input)
+  int32_t res_off;         // units from (plane base + q0) to the tile's first residual unit
+  int32_t res_sp;          // epilogue steps (pairs of 16-channel groups) per staging phase
   ConvRun runs[kMaxRuns];
   ConvMma mma[kMaxMma + 1];   // +1: the issue loop prefetches one entry ahead
 };

@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(kThreads, V ? 2 : 1) conv_shiftgemm_kernel(con
   uint64_t* a_peer = acc_full + 1;           // PAIR, leader only: the peer's slab / weight stage is full
   uint64_t* b_peer = a_peer + P.SA;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_peer + P.SB);
-  float* s_stats = reinterpret_cast<float*>(tmem_ptr + 2);   // [Npad][2]
+  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_ptr + 2);   // fused InstanceNorm epilogue: residual tile landed in shared memory
+  float* s_stats = reinterpret_cast<float*>(res_bar + 1);    // [Npad][2]
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < P.SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(kThreads, V ? 2 : 1) conv_shiftgemm_kernel(con
     mbar_init(acc_full, 1);
     for (int i = 0; i < P.SA; ++i) mbar_init(&a_peer[i], 1);
     for (int i = 0; i < P.SB; ++i) mbar_init(&b_peer[i], 1);
+    mbar_init(res_bar, 1);
     fence_mbar_init();
   }
   if (warp == 3) {
@@ -416,6 +418,35 @@ __global__ void __launch_bounds__(kThreads, V ? 2 : 1) conv_shiftgemm_kernel(con
       if (trace && lane == 0) { trace[0] = t_mma0 - t_entry; trace[1] = wa; trace[2] = wb; trace[3] = clock64() - t_entry; }
     }
     __syncwarp();
+  } else if (warp == 3 && V && P.epilogue == NHVR_EPI_IN_FUSED && P.res_bulk) {
+    // ------------------------------------------------------------------ fused InstanceNorm epilogue: residual tile stager
+    // The residual tile is 128 consecutive units per plane (the skip activation linearises like this conv's input): bulk
+    // async copies bring it into the shared memory the operand rings no longer need (every MMA has retired), in phases of
+    // res_sp epilogue steps = 2 * res_sp channel groups, one plane per lane, while the statistics are reduced and the
+    // image's CTAs meet.  Later phases start when the 256 epilogue threads have released the previous one (barrier 3).
+    const ActGeom& sg = P.sg;
+    const int hilo = sg.hilo, npl = hilo ? 4 : 2;
+    const int ngroups = P.Npad >> 4, cout_off = split * P.Npad;
+    mbar_wait_warp(acc_full, 0);
+    const uint4* rbase = P.res + (int64_t)n * sg.C8 * sg.plane_units + q0 + P.res_off;
+    for (int phase = 0; 2 * phase * P.res_sp < ngroups; ++phase) {
+      if (phase) asm volatile("bar.sync 3, 288;" ::: "memory");
+      const int g0 = 2 * phase * P.res_sp, g1 = min(ngroups, g0 + 2 * P.res_sp);
+      int planes = 0;
+      for (int g = g0; g < g1; ++g) {
+        const int pb = hilo ? ((cout_off + g * 16) >> 4) << 2 : (cout_off + g * 16) >> 3;
+        if (pb + npl <= sg.C8) planes += npl;
+      }
+      if (lane == 0) mbar_arrive_expect_tx(res_bar, (uint32_t)planes * 2048u);
+      __syncwarp();
+      for (int i = lane; i < (g1 - g0) * npl; i += 32) {
+        const int g = g0 + i / npl, j = i - (i / npl) * npl;
+        const int pb = hilo ? ((cout_off + g * 16) >> 4) << 2 : (cout_off + g * 16) >> 3;
+        if (pb + npl <= sg.C8)
+          bulk_g2s(a_smem + (size_t)i * 2048, rbase + (int64_t)(pb + j) * sg.plane_units, 2048u, res_bar);
+      }
+      __syncwarp();
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
     const int we = warp & 3;                  // TMEM lane quarter == warp % 4
@@ -581,6 +612,169 @@ __global__ void __launch_bounds__(kThreads, V ? 2 : 1) conv_shiftgemm_kernel(con
             asm volatile("bar.sync 2, 128;" ::: "memory");
           }
           emit16<V>(P, acc, cg * 16, valid, n, y, x, cg, lane, s_stats, s_bias + cg * 16);
+        }
+      }
+    } else if (V && P.epilogue == NHVR_EPI_IN_FUSED) {
+      // ---- conv + InstanceNorm + activation (+ residual) + halo in one kernel (one M block, one accumulator per CTA).
+      const ActGeom& og = P.og;
+      const ActGeom& sg = P.sg;
+      const int hilo = og.hilo;
+      const int npl = hilo ? 4 : 2;                                   // physical planes per 16-channel group
+      // The residual tile is 128 consecutive units per plane (the skip activation has this conv's own input geometry):
+      // bulk async copies bring it into the shared memory the operand rings no longer need (every MMA has retired), in
+      // phases of `res_sp` steps = 2 * res_sp groups, while the statistics are reduced and the image's CTAs meet.
+      // Pass 1: per-channel sum / sum of squares of this tile straight from TMEM (nothing is stored).
+      for (int g = half; g < ngroups; g += 2) {
+        uint32_t vr[16];
+        tmem_ld16(t_lane + (uint32_t)(g * 16), vr);
+        tmem_ld_wait();
+        float s[16], ss[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { s[i] = valid_m ? __uint_as_float(vr[i]) * accs : 0.f; ss[i] = s[i] * s[i]; }
+        const float cs = warp_colsum16(s, lane);
+        const float css = warp_colsum16(ss, lane);
+        atomicAdd(&s_stats[(g * 16 + (lane >> 1)) * 2 + (lane & 1)], (lane & 1) ? css : cs);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (trace && threadIdx.x == 128) trace[1] = clock64() - t_entry;          // (fused) pass 1 done
+      const int nch = min(P.Npad, P.Cout8 * 8 - cout_off);         // channels of this CTA that exist in the record
+      // the record's four slots hold TWO replicas of {sum, sum of squares} here (no centring shift on this path): even /
+      // odd tiles add to different addresses, halving the same-address contention of an image's 130 CTAs
+      double* gs = P.stats + ((int64_t)n * P.Cout8 * 8 + cout_off) * 4 + 2 * (blockIdx.x & 1);
+      for (int i = threadIdx.x - 128; i < nch * 2; i += 256) atomicAdd(gs + (i >> 1) * 4 + (i & 1), (double)s_stats[i]);
+      __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // The image's CTAs meet: CTAs are dispatched in block-index order and an image's CTAs fit the GPU at once (checked by
+      // the host), so everything this wait depends on is already running.  A protocol bug traps instead of hanging.
+      if (threadIdx.x == 128) {
+        if (trace) trace[2] = clock64() - t_entry;                               // (fused) statistics merged, arriving
+        red_release_gpu_add(P.sync + n, 1u);
+        const uint32_t total = gridDim.x * gridDim.z;
+        const long long t0 = clock64();
+        while (ld_acquire_gpu(P.sync + n) < total) {
+          __nanosleep(128);
+          if (clock64() - t0 > (1ll << 32)) __trap();
+        }
+        if (trace) trace[7] = clock64() - t_entry;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // per-channel (rstd, -mean * rstd): fp64 mean / variance exactly as nhvr_in_apply forms them
+      for (int i = threadIdx.x - 128; i < P.Npad; i += 256) {
+        float sc = 0.f, sh = 0.f;
+        if (i < nch) {
+          const double2* rec = reinterpret_cast<const double2*>(P.stats + ((int64_t)n * P.Cout8 * 8 + cout_off + i) * 4);
+          const double2 q = __ldcg(rec), r = __ldcg(rec + 1);
+          const double m0 = (q.x + r.x) * (double)P.inv_hw;
+          const double var = fmax((q.y + r.y) * (double)P.inv_hw - m0 * m0, 0.0);
+          sc = rsqrtf((float)var + P.eps);
+          sh = -(float)m0 * sc;
+        }
+        reinterpret_cast<float2*>(s_stats)[i] = make_float2(sc, sh);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (trace && threadIdx.x == 128) trace[6] = clock64() - t_entry;          // (fused) scale / shift ready
+      // Pass 2: normalise from the fp32 accumulators, activation, + residual, and write the consumer's format: the pixel
+      // itself plus its mirror images in the halo (ReflectionPad2d: up to 3 rows x 3 columns for tiny images, 1 x 1 inside).
+      int tyv[3], txv[3], nty = 0, ntx = 0;
+      if (valid_m) {
+        tyv[nty++] = y + og.pad_t;
+        txv[ntx++] = x + og.pad_l;
+        if (og.halo != NHVR_HALO_ZERO) {
+          if (y >= 1 && y <= og.pad_t) tyv[nty++] = og.pad_t - y;
+          if (y <= og.H - 2 && og.pad_t + 2 * (og.H - 1) - y < og.Hp) tyv[nty++] = og.pad_t + 2 * (og.H - 1) - y;
+          if (x >= 1 && x <= og.pad_l) txv[ntx++] = og.pad_l - x;
+          if (x <= og.W - 2 && og.pad_l + 2 * (og.W - 1) - x < og.Wp) txv[ntx++] = og.pad_l + 2 * (og.W - 1) - x;
+        }
+      }
+      const int64_t u_main = valid_m ? plane_unit(og, y + og.pad_t, x + og.pad_l) : 0;
+      const bool mirrors = nty * ntx > 1;
+      const int64_t res_u = (P.res && valid_m && !P.res_bulk) ? plane_unit(sg, y + sg.pad_t, x + sg.pad_l) : 0;
+      uint4* o = reinterpret_cast<uint4*>(P.out);
+      int step = 0, phase = 0;
+      for (int g = half; g < ngroups; g += 2, ++step) {
+        const int c0 = cout_off + g * 16;
+        const int pb = hilo ? (c0 >> 4) << 2 : c0 >> 3;               // first physical plane of this 16-channel group
+        const bool have = pb + npl <= og.C8;                          // Cout8 is even: both logical planes exist or neither
+        uint4 rr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rr[j] = make_uint4(0, 0, 0, 0);
+        if (P.res_bulk) {
+          if (step == (phase + 1) * P.res_sp) {                       // next phase: everyone is done with the previous tile part
+            ++phase;
+            asm volatile("bar.sync 3, 288;" ::: "memory");             // releases warp 3, which stages the next part
+          }
+          if (step == phase * P.res_sp) mbar_wait_warp(res_bar, (uint32_t)(phase & 1));
+          if (have) {
+            const uint4* rs = reinterpret_cast<const uint4*>(a_smem + (size_t)(g - 2 * phase * P.res_sp) * npl * 2048) + m;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < npl) rr[j] = rs[j * 128];
+          }
+        } else if (P.res && valid_m && have) {
+          const uint4* rp = P.res + ((int64_t)n * sg.C8 + pb) * sg.plane_units + res_u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < npl) rr[j] = __ldg(rp + (int64_t)j * sg.plane_units);
+        }
+        uint32_t vr[16];
+        tmem_ld16(t_lane + (uint32_t)(g * 16), vr);
+        tmem_ld_wait();
+        if (!(valid_m && have)) continue;
+        float t[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 nrm = reinterpret_cast<const float2*>(s_stats)[g * 16 + i];
+          t[i] = fmaf(__uint_as_float(vr[i]) * accs, nrm.x, nrm.y);
+        }
+        if (P.act == NHVR_ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) t[i] = fmaxf(t[i], 0.f);
+        } else if (P.act == NHVR_ACT_LRELU02) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) t[i] = t[i] > 0.f ? t[i] : 0.2f * t[i];
+        }
+        if (P.res) {
+          float a[8], b[8];
+          unpack8f(rr[0], a, P.f16); unpack8f(rr[1], b, P.f16);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { t[i] += a[i]; t[8 + i] += b[i]; }
+          if (hilo) {
+            unpack8f(rr[2], a, P.f16); unpack8f(rr[3], b, P.f16);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { t[i] += a[i]; t[8 + i] += b[i]; }
+          }
+        }
+        uint4 u[4];
+        if (hilo) {
+          split_hilo(t[0], t[1], P.f16, u[0].x, u[2].x);   split_hilo(t[2], t[3], P.f16, u[0].y, u[2].y);
+          split_hilo(t[4], t[5], P.f16, u[0].z, u[2].z);   split_hilo(t[6], t[7], P.f16, u[0].w, u[2].w);
+          split_hilo(t[8], t[9], P.f16, u[1].x, u[3].x);   split_hilo(t[10], t[11], P.f16, u[1].y, u[3].y);
+          split_hilo(t[12], t[13], P.f16, u[1].z, u[3].z); split_hilo(t[14], t[15], P.f16, u[1].w, u[3].w);
+        } else {
+          u[0].x = pack2(t[0], t[1], P.f16);  u[0].y = pack2(t[2], t[3], P.f16);
+          u[0].z = pack2(t[4], t[5], P.f16);  u[0].w = pack2(t[6], t[7], P.f16);
+          u[1].x = pack2(t[8], t[9], P.f16);  u[1].y = pack2(t[10], t[11], P.f16);
+          u[1].z = pack2(t[12], t[13], P.f16); u[1].w = pack2(t[14], t[15], P.f16);
+          u[2] = u[3] = make_uint4(0, 0, 0, 0);
+        }
+        uint4* ob = o + ((int64_t)n * og.C8 + pb) * og.plane_units;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < npl) ob[u_main + (int64_t)j * og.plane_units] = u[j];
+        if (mirrors) {                                                // border pixels only
+#pragma unroll
+          for (int iy = 0; iy < 3; ++iy) {
+            if (iy >= nty) break;
+#pragma unroll
+            for (int ix = 0; ix < 3; ++ix) {
+              if (ix >= ntx) break;
+              if (iy + ix == 0) continue;
+              uint4* od = ob + plane_unit(og, tyv[iy], txv[ix]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j < npl) od[(int64_t)j * og.plane_units] = u[j];
+            }
+          }
         }
       }
     } else {
@@ -948,7 +1142,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   // exact dynamic shared memory of a configuration (must equal what the kernel carves up)
   int pair = 0;
   auto smem_need = [&](int kcp_, int sa, int dv, int sb) -> long {
-    return (long)sa * kcp_ * slab * 16 + (long)sb * dv * Npad * (pair ? 16 : 32) + (long)(3 * sa + 3 * sb + 1) * 8 + 8 + (long)Npad * 8 * nacc +
+    return (long)sa * kcp_ * slab * 16 + (long)sb * dv * Npad * (pair ? 16 : 32) + (long)(3 * sa + 3 * sb + 1) * 8 + 16 + (long)Npad * 8 * nacc +
            (long)Npad * 4 + (rowmode ? (K.Cp == 8 ? 2L * 2 * 3 * 7 * 7 * std::min(gemm_n, 8) * 4 : 8704L) : 0) + 128;
   };
   auto try_fit = [&](long limit) -> bool {
@@ -1224,6 +1418,58 @@ extern "C" int nhvr_conv_pack_weights(const nhvr_conv_plan* p, const float* w, v
   return NHVR_OK;
 }
 
+static cudaError_t conv_set_attrs() {
+  static bool attr_set = false;
+  if (attr_set) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(conv_shiftgemm_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_shiftgemm_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_shiftgemm_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_shiftgemm_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) attr_set = true;
+  return e;
+}
+
+static inline dim3 conv_grid(const nhvr_conv_plan* p) {
+  return dim3(p->kp.pair ? (p->tiles_per_img + 1) & ~1 : p->tiles_per_img, p->d.N, p->nsplit);   // pairs: an even number of tiles
+}
+
+// launch with the plan's lowering (CTA pair or not; `special` selects kernel variant 1, see the kernel header)
+static cudaError_t conv_launch(const nhvr_conv_plan* p, const ConvKParams& K, bool special, cudaStream_t stream) {
+  const dim3 grid = conv_grid(p);
+  if (!K.pair) {
+    if (special) conv_shiftgemm_kernel<false, 1><<<grid, kThreads, p->smem_bytes, stream>>>(K);
+    else conv_shiftgemm_kernel<false, 0><<<grid, kThreads, p->smem_bytes, stream>>>(K);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = p->smem_bytes; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  if (special) return cudaLaunchKernelEx(&cfg, conv_shiftgemm_kernel<true, 1>, K);
+  return cudaLaunchKernelEx(&cfg, conv_shiftgemm_kernel<true, 0>, K);
+}
+
+// NHVR_CONV_TRACE diagnostics: per-CTA cycle breakdown printed to stderr (synchronises)
+static void conv_launch_traced(const nhvr_conv_plan* p, ConvKParams& K, bool special, cudaStream_t stream) {
+  const dim3 grid = conv_grid(p);
+  const size_t nct = (size_t)grid.x * grid.y * grid.z;
+  cudaMalloc(&K.trace, nct * 64);
+  cudaMemset(K.trace, 0, nct * 64);
+  conv_launch(p, K, special, stream);
+  cudaDeviceSynchronize();
+  std::vector<long long> h(nct * 8);
+  cudaMemcpy(h.data(), K.trace, nct * 64, cudaMemcpyDeviceToHost);
+  cudaFree(K.trace);
+  double m[8] = {0};
+  for (size_t i = 0; i < nct; ++i) for (int j = 0; j < 8; ++j) m[j] += (double)h[i * 8 + j] / nct;
+  if (K.epilogue == NHVR_EPI_IN_FUSED)
+    std::fprintf(stderr, "[conv trace fused] acc_full@%.0f pass1_done@%.0f stats_merged@%.0f image_met@%.0f norm_ready@%.0f epi_done@%.0f\n", m[4], m[1], m[2], m[7], m[6], m[5]);
+  std::fprintf(stderr, "[conv trace] ctas=%zu pair=%d mrep=%d N=%d  first_wait@%.0f  wait_a=%.0f wait_b=%.0f  mma_issued@%.0f  last_b_req@%.0f  acc_full@%.0f  image_met@%.0f  epi_done@%.0f cycles (mean per CTA)\n",
+               nct, K.pair, K.mrep, K.Npad, m[0], m[1], m[2], m[3], m[6], m[4], m[7], m[5]);
+}
+
 extern "C" int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const void* packed_w, const float* bias,
                                  void* out, const nhvr_act_desc* out_desc, double* stats, void* stream) {
   if (!p || !in || !packed_w || !out) return NHVR_ERR_NULL;
@@ -1243,52 +1489,111 @@ extern "C" int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const 
   K.bias = bias;
   K.out = out;
   K.stats = stats;
+  K.res = nullptr; K.sync = nullptr;
   K.acc_scale = p->pp.split3 ? reinterpret_cast<const float*>(reinterpret_cast<const uint4*>(packed_w) + (int64_t)p->nsplit * K.w_split_units) + 1 : nullptr;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_shiftgemm_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_shiftgemm_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_shiftgemm_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_shiftgemm_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
-    attr_set = true;
-  }
-  dim3 grid(K.pair ? (p->tiles_per_img + 1) & ~1 : p->tiles_per_img, p->d.N, p->nsplit);   // pairs: an even number of tiles
+  { cudaError_t e = conv_set_attrs(); if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; } }
   // variant 1 = the layers that need the special epilogue paths (see the kernel header)
   const bool special = K.acc_scale != nullptr || K.out_hilo || K.stat_centred || (K.rowmode && K.Cp == 8);
-  auto launch = [&]() -> cudaError_t {
-    if (!K.pair) {
-      if (special) conv_shiftgemm_kernel<false, 1><<<grid, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(K);
-      else conv_shiftgemm_kernel<false, 0><<<grid, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(K);
-      return cudaGetLastError();
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = p->smem_bytes; cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    if (special) return cudaLaunchKernelEx(&cfg, conv_shiftgemm_kernel<true, 1>, K);
-    return cudaLaunchKernelEx(&cfg, conv_shiftgemm_kernel<true, 0>, K);
-  };
   K.trace = nullptr;
-  if (std::getenv("NHVR_CONV_TRACE")) {     // diagnostics: per-CTA cycle breakdown printed to stderr (synchronises)
-    const size_t nct = (size_t)grid.x * grid.y * grid.z;
-    cudaMalloc(&K.trace, nct * 64);
-    cudaMemset(K.trace, 0, nct * 64);
-    launch();
-    cudaDeviceSynchronize();
-    std::vector<long long> h(nct * 8);
-    cudaMemcpy(h.data(), K.trace, nct * 64, cudaMemcpyDeviceToHost);
-    cudaFree(K.trace);
-    double m[8] = {0};
-    for (size_t i = 0; i < nct; ++i) for (int j = 0; j < 8; ++j) m[j] += (double)h[i * 8 + j] / nct;
-    std::fprintf(stderr, "[conv trace] ctas=%zu pair=%d mrep=%d N=%d  first_wait@%.0f  wait_a=%.0f wait_b=%.0f  mma_issued@%.0f  last_b_req@%.0f  acc_full@%.0f  epi_done@%.0f cycles (mean per CTA)\n",
-                 nct, K.pair, K.mrep, K.Npad, m[0], m[1], m[2], m[3], m[6], m[4], m[5]);
+  if (std::getenv("NHVR_CONV_TRACE")) {
+    conv_launch_traced(p, K, special, (cudaStream_t)stream);
     count_launch();
     return NHVR_OK;
   }
-  cudaError_t e = launch();
+  cudaError_t e = conv_launch(p, K, special, (cudaStream_t)stream);
+  count_launch();
+  if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
+  return NHVR_OK;
+}
+
+// ---- conv + InstanceNorm + activation (+ residual) + halo in one kernel (include/nhvr.h) -----------------------------
+// structural conditions of the fused epilogue (no device needed)
+static bool in_fused_shape_ok(const nhvr_conv_plan* p) {
+  const ConvKParams& K = p->kp;
+  return K.epilogue == NHVR_EPI_RAW_STATS && K.mrep == 1 && K.nacc == 1 && !K.rowmode && !K.xtiles && !K.stat_centred &&
+         K.oys == 1 && K.oxs == 1 && p->d.kind == NHVR_CONV && !std::getenv("NHVR_NO_IN_FUSED");
+}
+
+extern "C" int nhvr_conv_in_fused_supported(const nhvr_conv_plan* p) {
+  if (!p || !in_fused_shape_ok(p) || !arch_ok_cached()) return 0;
+  if (conv_set_attrs() != cudaSuccess) return 0;
+  int dev = 0, sms = 0, smem_sm = 0, regs_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev) != cudaSuccess)
+    return 0;
+  cudaFuncAttributes fa;
+  cudaError_t e = p->kp.pair ? cudaFuncGetAttributes(&fa, conv_shiftgemm_kernel<true, 1>) : cudaFuncGetAttributes(&fa, conv_shiftgemm_kernel<false, 1>);
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  // Resident CTAs per SM of kernel variant 1 with this plan's shared memory.  Computed from the device limits (1 KB of
+  // shared memory is reserved per CTA; registers are allocated per warp in units of 256; 512 TMEM columns per SM) rather
+  // than cudaOccupancyMaxActiveBlocksPerMultiprocessor, which answers for the DEFAULT shared-memory carve-out (1 CTA)
+  // while launches of this kernel run with the maximum one (ncu: launch__occupancy_limit_shared_mem = 2,
+  // sm__warps_active 22-23 of 24; profiles/r02_ncu_uvres_raw.csv).
+  const long regs_cta = (long)((fa.numRegs * 32 + 255) / 256 * 256) * (kThreads / 32);
+  const long by_smem = smem_sm / (long)(p->smem_bytes + fa.sharedSizeBytes + 1024);
+  const long by_regs = regs_sm / regs_cta;
+  const long by_tmem = 512 / p->kp.tmem_cols;
+  const long per_sm = std::min(by_smem, std::min(by_regs, by_tmem));
+  const long slots = per_sm * sms;
+  const dim3 grid = conv_grid(p);
+  if (std::getenv("NHVR_DEBUG_FUSED"))
+    std::fprintf(stderr, "[in_fused] pair=%d grid=(%u,%u,%u) smem=%zu regs=%d tmem=%d per_sm=%ld (smem %ld regs %ld tmem %ld) slots=%ld\n", p->kp.pair,
+                 grid.x, grid.y, grid.z, p->smem_bytes, fa.numRegs, p->kp.tmem_cols, per_sm, by_smem, by_regs, by_tmem, slots);
+  // an image's CTAs must be resident together, also while a second fused kernel runs on a concurrent stream
+  return (long)grid.x * grid.z <= slots / 2 ? 1 : 0;
+}
+
+extern "C" int nhvr_conv_forward_in_fused(const nhvr_conv_plan* p, const void* in, const void* packed_w, double* stats, float eps,
+                                          int32_t act, const void* residual, const nhvr_act_desc* res_desc, void* dst,
+                                          const nhvr_act_desc* dst_desc, uint32_t* sync, void* stream) {
+  if (!p || !in || !packed_w || !stats || !dst || !dst_desc || !sync) return NHVR_ERR_NULL;
+  if (residual && !res_desc) return NHVR_ERR_NULL;
+  if ((((uintptr_t)in | (uintptr_t)packed_w | (uintptr_t)dst | (uintptr_t)residual) & 15) != 0) return NHVR_ERR_ALIGN;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  if (!in_fused_shape_ok(p)) return NHVR_ERR_UNSUPPORTED;
+  if (act != NHVR_ACT_NONE && act != NHVR_ACT_RELU && act != NHVR_ACT_LRELU02) return NHVR_ERR_UNSUPPORTED;
+  ConvKParams K = p->kp;
+  const int hilo = p->pp.split3 ? 1 : 0;
+  K.og = make_geom(*dst_desc);
+  if (K.og.N != p->d.N || K.og.H != p->Ho || K.og.W != p->Wo || K.og.hilo != hilo || K.og.C8 != p->Cout8 * (hilo ? 2 : 1)) return NHVR_ERR_SHAPE;
+  K.sg = K.og;
+  if (residual) {
+    K.sg = make_geom(*res_desc);
+    if (K.sg.N != K.og.N || K.sg.H != K.og.H || K.sg.W != K.og.W || K.sg.C8 != K.og.C8 || K.sg.hilo != hilo || K.sg.split) return NHVR_ERR_SHAPE;
+  }
+  K.epilogue = NHVR_EPI_IN_FUSED;
+  K.act = act;
+  K.f16 = operand_f16();
+  K.debug = 0;
+  K.in = reinterpret_cast<const uint4*>(in);
+  K.w = reinterpret_cast<const uint4*>(packed_w);
+  K.bias = nullptr;
+  K.out = dst;
+  K.stats = stats;
+  K.res = reinterpret_cast<const uint4*>(residual);
+  // residual tile by bulk copy: the skip activation must linearise like this conv's input (same row pitch, not split), so
+  // that a tile's 128 positions are 128 consecutive units of every residual plane
+  K.res_bulk = 0; K.res_off = 0; K.res_sp = 1;
+  if (residual && !K.sg.split && K.sg.Wp == K.Wrow && !std::getenv("NHVR_NO_RES_BULK")) {
+    const long avail = (long)K.SA * K.kcp * K.slab_units * 16 + (long)K.SB * K.bpb * K.Npad * (K.pair ? 16 : 32);
+    const int sp = (int)(avail / (2L * (hilo ? 4 : 2) * 2048));
+    const int ngroups = K.Npad >> 4;
+    // several phases need both epilogue halves to take the same number of steps (they meet at a barrier between phases)
+    if (sp >= 1 && (2 * sp >= ngroups || (ngroups & 1) == 0)) { K.res_bulk = 1; K.res_sp = sp; K.res_off = K.sg.pad_t * K.sg.Wp + K.sg.pad_l; }
+  }
+  K.sync = sync;
+  K.eps = eps;
+  K.inv_hw = 1.0f / ((float)p->Ho * (float)p->Wo);
+  K.acc_scale = p->pp.split3 ? reinterpret_cast<const float*>(reinterpret_cast<const uint4*>(packed_w) + (int64_t)p->nsplit * K.w_split_units) + 1 : nullptr;
+  { cudaError_t e = conv_set_attrs(); if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; } }
+  K.trace = nullptr;
+  if (std::getenv("NHVR_CONV_TRACE")) {
+    conv_launch_traced(p, K, true, (cudaStream_t)stream);
+    count_launch();
+    return NHVR_OK;
+  }
+  cudaError_t e = conv_launch(p, K, true, (cudaStream_t)stream);
   count_launch();
   if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
   return NHVR_OK;

@@ -137,14 +137,33 @@ class _ChainEngine:
                 self.raw_bufs.append(self._raws[rkey])
             else:
                 self.raw_bufs.append(None)
-        # InstanceNorm statistics: one zero-fill per forward
+        # inference: layers whose InstanceNorm is finished inside the conv kernel (no raw tensor, no nhvr_in_apply launch).
+        # Measured (profiles/r02b_in_fused.md): the image-wide meeting point makes co-resident CTAs run in lock-step, which
+        # exposes the epilogue; split-precision layers (3x longer MMA phase, 2x larger raw tensor) gain 2.5-4 % of the frame
+        # step, plain fp16 layers lose 2-7 % - so the default is split precision only.  NHVR_IN_FUSED=1 / 0 forces it on / off
+        # (NHVR_NO_IN_FUSED=1 disables it inside the library as well).
+        self.fused = [False] * len(self.plans)
+        env = __import__("os").environ.get("NHVR_IN_FUSED")
+        want = split3 if env is None else env not in ("0", "")
+        if not train and want:
+            for i, (L, plan) in enumerate(zip(chain[:-1], self.plans[:-1])):
+                self.fused[i] = bool(L.get("norm", True)) and plan.in_fused_supported()
+        # InstanceNorm statistics: one zero-fill per forward; the arrival counters of the fused layers (N uint32 each) live
+        # behind them in the same buffer so that the same fill re-arms them
         sizes = [N * pl.Cout8 * 8 * 4 if chain[i].get("norm", True) else 0 for i, pl in enumerate(self.plans[:-1])]   # {sum, sum sq, shift, -}
-        self.stats_all = torch.zeros(max(1, sum(sizes)), dtype=torch.float64, device=device)     # fp64 sums (include/nhvr.h)
+        nsync = (sum(self.fused) * N + 1) // 2
+        self.stats_all = torch.zeros(max(1, sum(sizes) + nsync), dtype=torch.float64, device=device)     # fp64 sums (include/nhvr.h)
         self.stats: List[torch.Tensor] = []
         off = 0
         for s in sizes:
             self.stats.append(self.stats_all[off:off + s])
             off += s
+        sync_all = self.stats_all[off:off + nsync].view(torch.int32)
+        self.sync: List[Optional[torch.Tensor]] = []
+        k = 0
+        for f in self.fused:
+            self.sync.append(sync_all[k * N:(k + 1) * N] if f else None)
+            k += 1 if f else 0
         self.flops = sum(pl.flops for pl in self.plans)
         self.weight_versions: Optional[tuple] = None
 
@@ -360,10 +379,14 @@ class _ChainEngine:
                 nxt = self.in_bufs[i + 1]
                 plan.forward(x, nxt.ptr, bias=L["params"].bias, out_desc=nxt.desc)
                 continue
-            raw = self.raw_bufs[i]
-            plan.forward(x, raw.ptr, stats=self.stats[i])
-            ops.in_apply(raw, self.stats[i], L["act"], self.in_bufs[i + 1],
-                         residual=res_src if L.get("res") == "add" else None)
+            if self.fused[i]:
+                plan.forward_in_fused(x, self.stats[i], L["act"], self.in_bufs[i + 1], self.sync[i],
+                                      residual=res_src if L.get("res") == "add" else None)
+            else:
+                raw = self.raw_bufs[i]
+                plan.forward(x, raw.ptr, stats=self.stats[i])
+                ops.in_apply(raw, self.stats[i], L["act"], self.in_bufs[i + 1],
+                             residual=res_src if L.get("res") == "add" else None)
             if L.get("res") == "add":
                 res_src = None
         return self.out

@@ -176,6 +176,24 @@ class ConvPlan:
                   "nhvr_conv_forward")
 
 
+    def in_fused_supported(self) -> bool:
+        """conv + InstanceNorm + activation (+ residual) + halo in one kernel is possible for this plan on this GPU
+        (include/nhvr.h nhvr_conv_in_fused_supported: every CTA of an image resident at once)."""
+        return bool(load().nhvr_conv_in_fused_supported(self.handle))
+
+    def forward_in_fused(self, x: P8Buffer, stats: torch.Tensor, act: int, dst: P8Buffer, sync: torch.Tensor,
+                         residual: Optional[P8Buffer] = None, eps: float = 1e-5) -> None:
+        """RAW_STATS plan: the InstanceNorm apply happens in the conv's epilogue, `dst` (the consumer's input buffer) is
+        written directly.  sync: int32 [N] zeros (this launch's arrival counters, re-zeroed by the caller before the next use)."""
+        assert self.packed is not None, "pack_weights() first"
+        with _prof(("conv3:" if self.split3 else "conv:") + self.label, self.flops):
+            check(load().nhvr_conv_forward_in_fused(self.handle, x.ptr, self.packed.data_ptr(), stats.data_ptr(), eps, act,
+                                                    residual.ptr if residual is not None else None,
+                                                    C.byref(residual.desc) if residual is not None else None,
+                                                    dst.ptr, C.byref(dst.desc), sync.data_ptr(), stream_ptr()),
+                  "nhvr_conv_forward_in_fused")
+
+
 class WgradPlan:
     """Weight-gradient plan of one forward conv (nhvr_wgrad_*): dW from the forward's P8 input and the output
     gradient stored in ``g_desc`` (which the matching dgrad conv also reads)."""
