@@ -44,9 +44,9 @@ enum { NHVR_ACT_NONE = 0, NHVR_ACT_RELU = 1, NHVR_ACT_LRELU02 = 2, NHVR_ACT_TANH
        NHVR_ACT_TANH_SIGMOID_LAST = 4 /* tanh on all channels but the last, sigmoid on the last */ };
 enum { NHVR_CONV = 0, NHVR_CONV_TRANSPOSE = 1 /* stride 2: k3 p1 output_padding 1, or k4 p2 (input-gradient of a 4x4 s2 p2 conv) */,
        NHVR_CONV_DGRAD_S1 = 2 /* input-gradient of a stride-1 conv; the desc describes the FORWARD conv */ };
-enum { NHVR_EPI_RAW_STATS = 0,   /* bf16 P8 un-padded conv output + per-(n,c) sum / sum-of-squares */
+enum { NHVR_EPI_RAW_STATS = 0,   /* 16-bit P8 un-padded conv output + per-(n,c) sum / sum-of-squares */
        NHVR_EPI_BIAS_ACT_F32 = 1,/* bias + activation, fp32 NCHW output                            */
-       NHVR_EPI_BIAS_ACT_P8 = 2, /* bias + activation, bf16 P8 output in a consumer's format       */
+       NHVR_EPI_BIAS_ACT_P8 = 2, /* bias + activation, 16-bit P8 output in a consumer's format     */
        NHVR_EPI_RAW_P8 = 3,      /* P8 un-padded output, no statistics (gradient convs)            */
        NHVR_EPI_IN_FUSED = 4     /* internal: set by nhvr_conv_forward_in_fused on a RAW_STATS plan  */ };
 
@@ -114,13 +114,13 @@ uint64_t nhvr_launch_count(void);
 
 /* ---- P8 activations ---- */
 size_t nhvr_act_bytes(const nhvr_act_desc* d);   /* includes the tail slack tiles may over-read */
-/* NCHW fp32 -> P8 bf16 with halo.  Up to 4 sources are concatenated along C (the reference's
+/* NCHW fp32 -> P8 (16-bit operand type) with halo.  Up to 4 sources are concatenated along C (the reference's
  * torch.cat of texture / pose / Laplace / previous frame in front of the generator; evidence:
  * --input_nc 3, --use_laplace, --pose_plus_laplace, name *_Temporal, start.sh:7,11,19,24).
  * src[i] is [N][src_c[i]][H][W] fp32; channels beyond the sum are zero. */
 int nhvr_pack_nchw(const float* const* src, const int32_t* src_c, int32_t nsrc,
                    void* dst, const nhvr_act_desc* dst_desc, void* stream);
-/* P8 bf16 (interior) -> NCHW fp32, first C channels. */
+/* P8 (interior) -> NCHW fp32, first C channels. */
 int nhvr_unpack_nchw(const void* src, const nhvr_act_desc* src_desc, float* dst, int32_t C, void* stream);
 
 /* ---- convolution (tcgen05 shift-GEMM) ---- */
@@ -201,7 +201,6 @@ int nhvr_pose_rasterize(const float* kps, int32_t T, int32_t size, float src_siz
 int nhvr_texture_sample(const float* uvp, const float* atlas, int32_t N, int32_t H, int32_t W,
                         int32_t S, int32_t Ctex, int32_t use_mask_texture,
                         float* tex_out, uint8_t* part_out, int16_t* texel_out, void* stream);
-
 /* ---- unfold_texture (README.md:64: the initial texture.jpg built from the frames and their DensePose IUV) ----
  * The adjoint of the bilinear lookup: every pixel with part dp_i in 1..24 splats img into the four texels around
  * (u, v) * (S-1) of its part with the lookup's weights.  img float [N][C][H][W]; dp_i int32 [N][H][W]; dp_uv float [N][2][H][W]

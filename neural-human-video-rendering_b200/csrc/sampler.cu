@@ -11,6 +11,8 @@
 #include "common.cuh"
 #include "p8.cuh"
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 namespace nhvr {
 
@@ -22,8 +24,8 @@ constexpr int kParts = 24;
 
 NHVR_DEVINL float uv_act(float t) { return fminf(fmaxf(__fadd_rn(__fmul_rn(t, 0.5f), 0.5f), 0.f), 1.f); }
 
-template <int G>   // G = number of float4 channel groups per texel (Ct4 / 4)
-__global__ void __launch_bounds__(128) texture_sample_kernel(const float* __restrict__ uvp, const float4* __restrict__ atlas,
+template <int G, int MINB>   // G = number of float4 channel groups per texel (Ct4 / 4); MINB = resident blocks per SM asked for
+__global__ void __launch_bounds__(128, MINB) texture_sample_kernel(const float* __restrict__ uvp, const float4* __restrict__ atlas,
                                                              int N, int H, int W, int S, int Ctex, int use_mask,
                                                              float* __restrict__ tex_out, uint8_t* __restrict__ part_out,
                                                              short2* __restrict__ texel_out) {
@@ -98,6 +100,11 @@ __global__ void __launch_bounds__(128) texture_sample_kernel(const float* __rest
   }
 }
 
+// Measured alternatives (profiles/r02b_sampler.md): a "pair" atlas (texel + right neighbour in one 32-byte record, one LDG.E.256
+// per bilinear row) and a "quad" atlas with four lanes per (pixel, part) were built in round 2.  Neither beats this kernel: the
+// gathers are bound by distinct L1 line misses (2 per pixel and part either way) and by issue latency (IPC ~1 of 4), not by
+// sectors or tag lookups.
+
 // out = m*fg + (1-m)*bg, 4 pixels per thread (float4 along x)
 __global__ void __launch_bounds__(256) composite_kernel(const float4* __restrict__ fgm, const float4* __restrict__ bg, int bg_batched,
                                                         int N, int64_t HW4, float4* __restrict__ out) {
@@ -151,14 +158,19 @@ extern "C" int nhvr_texture_sample(const float* uvp, const float* atlas, int32_t
   if (!arch_ok_cached()) return NHVR_ERR_ARCH;
   const int G = (Ctex + 3) / 4;
   const int64_t total = (int64_t)N * H * W;
-  const int blocks = (int)std::min<int64_t>((total + 127) / 128, (int64_t)148 * 16 * 8);
   const float4* a4 = reinterpret_cast<const float4*>(atlas);
   short2* tx = reinterpret_cast<short2*>(texel_out);
   cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = (int)std::min<int64_t>((total + 127) / 128, (int64_t)148 * 16 * 8);
 #define NHVR_LAUNCH_SAMPLER(GG) \
-  texture_sample_kernel<GG><<<blocks, 128, 0, st>>>(uvp, a4, N, H, W, S, Ctex, use_mask_texture, tex_out, part_out, tx)
+  texture_sample_kernel<GG, 1><<<blocks, 128, 0, st>>>(uvp, a4, N, H, W, S, Ctex, use_mask_texture, tex_out, part_out, tx)
+  static int minb = -1;           // experiments: NHVR_SAMPLER_MINB = 8 caps the Ctex <= 4 kernel at 64 registers (32 warps / SM)
+  if (minb < 0) { const char* e = std::getenv("NHVR_SAMPLER_MINB"); minb = e ? std::atoi(e) : 0; }
   switch (G) {
-    case 1: NHVR_LAUNCH_SAMPLER(1); break;
+    case 1:
+      if (minb >= 8) texture_sample_kernel<1, 8><<<blocks, 128, 0, st>>>(uvp, a4, N, H, W, S, Ctex, use_mask_texture, tex_out, part_out, tx);
+      else NHVR_LAUNCH_SAMPLER(1);
+      break;
     case 2: NHVR_LAUNCH_SAMPLER(2); break;
     case 3: NHVR_LAUNCH_SAMPLER(3); break;
     case 4: NHVR_LAUNCH_SAMPLER(4); break;

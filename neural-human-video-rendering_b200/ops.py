@@ -313,7 +313,8 @@ def atlas_to_channels_last(atlas: torch.Tensor) -> torch.Tensor:
 
 def texture_sample(uvp: torch.Tensor, atlas_cl: torch.Tensor, Ctex: int, use_mask_texture: bool = True,
                    tex_out: Optional[torch.Tensor] = None, want_indices: bool = True):
-    """nhvr_texture_sample: returns (tex [N,Ctex,H,W] f32, part [N,H,W] u8, texel [N,H,W,2] i16)."""
+    """nhvr_texture_sample: returns (tex [N,Ctex,H,W] f32, part [N,H,W] u8, texel [N,H,W,2] i16).
+    atlas_cl: channels-last [24, S, S, Ct4] (ops.atlas_to_channels_last)."""
     assert uvp.is_cuda and uvp.dtype == torch.float32 and uvp.is_contiguous() and uvp.shape[1] == 73
     N, _, H, W = uvp.shape
     S = atlas_cl.shape[1]
