@@ -77,6 +77,8 @@ typedef struct nhvr_conv_desc {
   int32_t in_extra_cols; /* extra zero columns right of the input's right halo (same purpose)                 */
   int32_t out_h, out_w;  /* NHVR_CONV_TRANSPOSE only: output size override (0 = 2H x 2W for k3, 2H-2 for k4)  */
   int32_t flags;         /* bit 0: never use the row-mode lowering (wide kernels with few output channels)
+                            bit 5: intended for nhvr_conv_forward_in_fused: the tile step shrinks so that an image has exactly
+                                   one tile per SM (148), i.e. whole images fill the resident CTA slots
                             bit 4: RAW_STATS sums are centred on the shift the caller stored in slot 2 of the statistics record
                                    (nhvr_stem_stat_shift; first layers, where |mean| >> std on stick-figure pose maps)
                             bit 3: split precision ("3 x fp16"): the input is a hilo activation (nhvr_act_desc.hilo), the

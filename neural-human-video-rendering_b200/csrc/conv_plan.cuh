@@ -68,6 +68,7 @@ struct ConvKParams {
   float eps, inv_hw;
   int32_t res_bulk;        // residual tile staged in shared memory by bulk copies (skip activation linearises like the input)
   int32_t res_off;         // units from (plane base + q0) to the tile's first residual unit
+  int32_t start_delay;     // cycles the launch's second image waits before it starts (0: none)
   int32_t res_sp;          // epilogue steps (pairs of 16-channel groups) per staging phase
   ConvRun runs[kMaxRuns];
   ConvMma mma[kMaxMma + 1];   // +1: the issue loop prefetches one entry ahead

@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(kThreads, V ? 2 : 1) conv_shiftgemm_kernel(con
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int n = blockIdx.y, split = blockIdx.z;
   const long long t_entry = P.trace ? clock64() : 0;
-  long long* trace = P.trace ? P.trace + 8 * ((int64_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+  long long* trace = P.trace ? P.trace + 16 * ((int64_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+  if (trace && threadIdx.x == 0) { uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); trace[8] = sm; trace[9] = clock64(); }
   int ty0 = 0, tx0 = 0;                 // stacked tiles: first output row / column of the tile
   int64_t q0;
   if (P.xtiles) {
@@ -247,6 +248,13 @@ __global__ void __launch_bounds__(kThreads, V ? 2 : 1) conv_shiftgemm_kernel(con
       if (P.epilogue == NHVR_EPI_RAW_STATS) s_bias[i] = (V && P.stat_centred && c < P.Cout8 * 8) ? (float)P.stats[((int64_t)n * P.Cout8 * 8 + c) * 4 + 2] : 0.f;
       else s_bias[i] = (P.bias && c < P.Cout) ? __ldg(P.bias + c) : 0.f;
     }
+  }
+  // Fused InstanceNorm epilogue: the image-wide meeting point keeps all CTAs of an image in phase; starting the SECOND image
+  // of the launch late puts the two CTAs of an SM half a period apart for the rest of the launch (every later image starts
+  // when the image two before it leaves), so that one runs its MMA loop while the other is in its epilogue.
+  if (V && P.epilogue == NHVR_EPI_IN_FUSED && P.start_delay > 0 && blockIdx.y == 1 && threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < (long long)P.start_delay) __nanosleep(200);
   }
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();     // PAIR: the peer's barriers must be initialised before remote arrives
@@ -455,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, V ? 2 : 1) conv_shiftgemm_kernel(con
     int y, x;
     if (P.xtiles) { y = ty0; x = tx0 + m; }
     else { const int64_t q = q0 + m; y = (int)(q / P.Wrow); x = (int)(q - (int64_t)y * P.Wrow); }
-    const bool valid_m = (y < P.Hv) && (x < P.Wv);
+    const bool valid_m = (y < P.Hv) && (x < P.Wv) && (P.xtiles || P.rowmode || m < P.tile_step);   // tiles may own fewer than 128 positions
     const uint32_t t_lane = tmem_base + ((uint32_t)(we * 32) << 16);
     const int cout_off = split * P.Npad;
     const int ngroups = P.Npad >> 4;
@@ -624,13 +632,15 @@ __global__ void __launch_bounds__(kThreads, V ? 2 : 1) conv_shiftgemm_kernel(con
       // bulk async copies bring it into the shared memory the operand rings no longer need (every MMA has retired), in
       // phases of `res_sp` steps = 2 * res_sp groups, while the statistics are reduced and the image's CTAs meet.
       // Pass 1: per-channel sum / sum of squares of this tile straight from TMEM (nothing is stored).
+      // (the TMEM load of the next group is in flight while the current one is reduced)
+      uint32_t vr[16];
+      if (half < ngroups) tmem_ld16(t_lane + (uint32_t)(half * 16), vr);
       for (int g = half; g < ngroups; g += 2) {
-        uint32_t vr[16];
-        tmem_ld16(t_lane + (uint32_t)(g * 16), vr);
         tmem_ld_wait();
         float s[16], ss[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { s[i] = valid_m ? __uint_as_float(vr[i]) * accs : 0.f; ss[i] = s[i] * s[i]; }
+        if (g + 2 < ngroups) tmem_ld16(t_lane + (uint32_t)((g + 2) * 16), vr);
         const float cs = warp_colsum16(s, lane);
         const float css = warp_colsum16(ss, lane);
         atomicAdd(&s_stats[(g * 16 + (lane >> 1)) * 2 + (lane & 1)], (lane & 1) ? css : cs);
@@ -691,6 +701,7 @@ __global__ void __launch_bounds__(kThreads, V ? 2 : 1) conv_shiftgemm_kernel(con
       const int64_t res_u = (P.res && valid_m && !P.res_bulk) ? plane_unit(sg, y + sg.pad_t, x + sg.pad_l) : 0;
       uint4* o = reinterpret_cast<uint4*>(P.out);
       int step = 0, phase = 0;
+      if (half < ngroups) tmem_ld16(t_lane + (uint32_t)(half * 16), vr);
       for (int g = half; g < ngroups; g += 2, ++step) {
         const int c0 = cout_off + g * 16;
         const int pb = hilo ? (c0 >> 4) << 2 : c0 >> 3;               // first physical plane of this 16-channel group
@@ -716,16 +727,15 @@ __global__ void __launch_bounds__(kThreads, V ? 2 : 1) conv_shiftgemm_kernel(con
           for (int j = 0; j < 4; ++j)
             if (j < npl) rr[j] = __ldg(rp + (int64_t)j * sg.plane_units);
         }
-        uint32_t vr[16];
-        tmem_ld16(t_lane + (uint32_t)(g * 16), vr);
         tmem_ld_wait();
-        if (!(valid_m && have)) continue;
         float t[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float2 nrm = reinterpret_cast<const float2*>(s_stats)[g * 16 + i];
           t[i] = fmaf(__uint_as_float(vr[i]) * accs, nrm.x, nrm.y);
         }
+        if (g + 2 < ngroups) tmem_ld16(t_lane + (uint32_t)((g + 2) * 16), vr);   // next group's accumulators in flight
+        if (!(valid_m && have)) continue;
         if (P.act == NHVR_ACT_RELU) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) t[i] = fmaxf(t[i], 0.f);
@@ -1259,6 +1269,14 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
       const bool eligible = nacc == 1 && !rowmode && !(d->flags & 1) && Npad >= 96 && (Npad % 16) == 0;
       pair = eligible && (pe ? std::atoi(pe) != 0 : (Npad > 128 && Npad <= 192)) ? 1 : 0;
     }
+    // flag bit 5 (fused InstanceNorm epilogue): shrink the tile step so that an image has exactly one tile per SM (148) -
+    // whole images then fill the resident slots (2 per SM) and no CTA waits a full round for the rest of its image
+    if ((d->flags & 32) && !rowmode && d->kind == NHVR_CONV && d->stride == 1 && !std::getenv("NHVR_NO_TILE_ALIGN")) {
+      const int64_t last_q = (int64_t)(K.Hv - 1) * K.Wrow + K.Wv;
+      const int sms = 148;
+      const int step = (int)((last_q + sms - 1) / sms);
+      if (step <= kTileM && step >= 96) K.tile_step = step;
+    }
     const int b_block = Npad * 32;
     if (const char* tune = split3 ? nullptr : std::getenv("NHVR_CONV_TUNE")) {   // experiments: "kcp,SA,bpb,SB"
       int a, b, c, e;
@@ -1455,19 +1473,26 @@ static cudaError_t conv_launch(const nhvr_conv_plan* p, const ConvKParams& K, bo
 static void conv_launch_traced(const nhvr_conv_plan* p, ConvKParams& K, bool special, cudaStream_t stream) {
   const dim3 grid = conv_grid(p);
   const size_t nct = (size_t)grid.x * grid.y * grid.z;
-  cudaMalloc(&K.trace, nct * 64);
-  cudaMemset(K.trace, 0, nct * 64);
+  cudaMalloc(&K.trace, nct * 128);
+  cudaMemset(K.trace, 0, nct * 128);
   conv_launch(p, K, special, stream);
   cudaDeviceSynchronize();
-  std::vector<long long> h(nct * 8);
-  cudaMemcpy(h.data(), K.trace, nct * 64, cudaMemcpyDeviceToHost);
+  std::vector<long long> h(nct * 16);
+  cudaMemcpy(h.data(), K.trace, nct * 128, cudaMemcpyDeviceToHost);
   cudaFree(K.trace);
-  double m[8] = {0};
-  for (size_t i = 0; i < nct; ++i) for (int j = 0; j < 8; ++j) m[j] += (double)h[i * 8 + j] / nct;
+  double m[16] = {0};
+  for (size_t i = 0; i < nct; ++i) for (int j = 0; j < 16; ++j) m[j] += (double)h[i * 16 + j] / nct;
   if (K.epilogue == NHVR_EPI_IN_FUSED)
     std::fprintf(stderr, "[conv trace fused] acc_full@%.0f pass1_done@%.0f stats_merged@%.0f image_met@%.0f norm_ready@%.0f epi_done@%.0f\n", m[4], m[1], m[2], m[7], m[6], m[5]);
   std::fprintf(stderr, "[conv trace] ctas=%zu pair=%d mrep=%d N=%d  first_wait@%.0f  wait_a=%.0f wait_b=%.0f  mma_issued@%.0f  last_b_req@%.0f  acc_full@%.0f  image_met@%.0f  epi_done@%.0f cycles (mean per CTA)\n",
                nct, K.pair, K.mrep, K.Npad, m[0], m[1], m[2], m[3], m[6], m[4], m[7], m[5]);
+  if (std::getenv("NHVR_CONV_TRACE_MAP")) {      // placement: SM and start / end time (us at ~1.9 GHz, relative to the first CTA) of every CTA
+    long long tmin = h[9];
+    for (size_t i = 0; i < nct; ++i) tmin = std::min(tmin, h[i * 16 + 9]);
+    for (size_t i = 0; i < nct; ++i)
+      std::fprintf(stderr, "[cta] %zu img=%zu sm=%lld start=%.1f acc_full=%.1f end=%.1f\n", i, i / grid.x % grid.y, h[i * 16 + 8], (h[i * 16 + 9] - tmin) / 1900.0,
+                   (h[i * 16 + 9] - tmin + h[i * 16 + 4]) / 1900.0, (h[i * 16 + 9] - tmin + h[i * 16 + 5]) / 1900.0);
+  }
 }
 
 extern "C" int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const void* packed_w, const float* bias,
@@ -1489,7 +1514,7 @@ extern "C" int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const 
   K.bias = bias;
   K.out = out;
   K.stats = stats;
-  K.res = nullptr; K.sync = nullptr;
+  K.res = nullptr; K.sync = nullptr; K.start_delay = 0;
   K.acc_scale = p->pp.split3 ? reinterpret_cast<const float*>(reinterpret_cast<const uint4*>(packed_w) + (int64_t)p->nsplit * K.w_split_units) + 1 : nullptr;
   { cudaError_t e = conv_set_attrs(); if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; } }
   // variant 1 = the layers that need the special epilogue paths (see the kernel header)
@@ -1583,6 +1608,12 @@ extern "C" int nhvr_conv_forward_in_fused(const nhvr_conv_plan* p, const void* i
     if (sp >= 1 && (2 * sp >= ngroups || (ngroups & 1) == 0)) { K.res_bulk = 1; K.res_sp = sp; K.res_off = K.sg.pad_t * K.sg.Wp + K.sg.pad_l; }
   }
   K.sync = sync;
+  // experiment knob (profiles/r02b_in_fused.md): NHVR_FUSED_DELAY = cycles the launch's second image starts late.  Measured: the
+  // delay adds to the launch time one for one - a CTA's MMA loop is latency-bound, two in phase use the tensor pipe better
+  // than one alone - so the default is none
+  { static int delay = -1;
+    if (delay < 0) { const char* e = std::getenv("NHVR_FUSED_DELAY"); delay = e ? std::atoi(e) : 0; }
+    K.start_delay = p->d.N >= 2 ? delay : 0; }
   K.eps = eps;
   K.inv_hw = 1.0f / ((float)p->Ho * (float)p->Wo);
   K.acc_scale = p->pp.split3 ? reinterpret_cast<const float*>(reinterpret_cast<const uint4*>(packed_w) + (int64_t)p->nsplit * K.w_split_units) + 1 : nullptr;

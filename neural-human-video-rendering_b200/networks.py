@@ -86,6 +86,8 @@ class _ChainEngine:
         self.device = device
         self.chain = chain
         self.plans: List[ops.ConvPlan] = []
+        env = __import__("os").environ.get("NHVR_IN_FUSED")
+        want_fused = (not train) and (split3 if env is None else env not in ("0", ""))       # see self.fused below
         h, w = H, W
         for i, L in enumerate(chain):
             last = i == len(chain) - 1
@@ -98,7 +100,8 @@ class _ChainEngine:
                 epi, act = capi.EPI_BIAS_ACT_P8, L["act"]        # conv + bias + activation, no norm (D layer 0)
             plan = ops.ConvPlan(capi.CONV_TRANSPOSE if p.transposed else capi.CONV, p.cin, p.cout, p.k, p.stride, p.pad,
                                 N, h, w, L["halo"], epi, act, allow_tap_pairing=not train, split3=split3,
-                                centred_stats=(i == 0 and self._centres_stem(chain)))
+                                centred_stats=(i == 0 and self._centres_stem(chain)),
+                                align_tiles=want_fused and bool(L.get("res")) and bool(__import__("os").environ.get("NHVR_ALIGN_TILES")))
             plan.label = ("head" if last else "stem" if i == 0 else "res" if L.get("res") else "up" if p.transposed
                           else "down" if p.stride == 2 else "conv") + "%dx%d_%d-%d" % (p.k, p.k, p.cin, p.cout)
             self.plans.append(plan)
@@ -143,9 +146,7 @@ class _ChainEngine:
         # step, plain fp16 layers lose 2-7 % - so the default is split precision only.  NHVR_IN_FUSED=1 / 0 forces it on / off
         # (NHVR_NO_IN_FUSED=1 disables it inside the library as well).
         self.fused = [False] * len(self.plans)
-        env = __import__("os").environ.get("NHVR_IN_FUSED")
-        want = split3 if env is None else env not in ("0", "")
-        if not train and want:
+        if want_fused:
             for i, (L, plan) in enumerate(zip(chain[:-1], self.plans[:-1])):
                 self.fused[i] = bool(L.get("norm", True)) and plan.in_fused_supported()
         # InstanceNorm statistics: one zero-fill per forward; the arrival counters of the fused layers (N uint32 each) live

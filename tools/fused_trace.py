@@ -11,11 +11,13 @@ split3 = (sys.argv[3] if len(sys.argv) > 3 else "f16") == "split3"
 H = W = int(sys.argv[4]) if len(sys.argv) > 4 else 128
 dev = torch.device("cuda", 0)
 capi.set_operand_dtype("f16")
-plan = ops.ConvPlan(capi.CONV, C_, C_, 3, 1, 1, B, H, W, capi.HALO_REFLECT, capi.EPI_RAW_STATS, split3=split3)
+ALIGN = os.environ.get("FT_ALIGN", "0") != "0"          # one tile per SM and image (conv desc flag bit 5)
+plan = ops.ConvPlan(capi.CONV, C_, C_, 3, 1, 1, B, H, W, capi.HALO_REFLECT, capi.EPI_RAW_STATS, split3=split3, align_tiles=ALIGN)
+plan_two = ops.ConvPlan(capi.CONV, C_, C_, 3, 1, 1, B, H, W, capi.HALO_REFLECT, capi.EPI_RAW_STATS, split3=split3)
 x = torch.randn(B, C_, H, W, device=dev)
 w = torch.randn(C_, C_, 3, 3, device=dev) * (1.0 / (C_ * 9) ** 0.5)
 xin = ops.P8Buffer(plan.in_desc.copy(), dev); ops.pack_nchw([x], xin)
-plan.pack_weights(w)
+plan.pack_weights(w); plan_two.pack_weights(w)
 raw = ops.P8Buffer(plan.raw_desc(), dev)
 dst = ops.P8Buffer(plan.in_desc.copy(), dev)
 stats = torch.zeros(B * plan.Cout8 * 8 * 4, dtype=torch.float64, device=dev)
@@ -23,7 +25,7 @@ sync = torch.zeros(B, dtype=torch.int32, device=dev)
 print("plan", plan.info(), "fused_supported", plan.in_fused_supported())
 
 def two():
-    stats.zero_(); plan.forward(xin, raw.ptr, stats=stats); ops.in_apply(raw, stats, capi.ACT_RELU, dst, residual=xin)
+    stats.zero_(); plan_two.forward(xin, raw.ptr, stats=stats); ops.in_apply(raw, stats, capi.ACT_RELU, dst, residual=xin)
 def fused():
     stats.zero_(); sync.zero_(); plan.forward_in_fused(xin, stats, capi.ACT_RELU, dst, sync, residual=xin)
 
@@ -45,4 +47,4 @@ for name, fn in (("conv+apply", two), ("fused", fused)):
     for _ in range(20):
         fn()
     e1.record(); torch.cuda.synchronize()
-    print("%-10s C=%d B=%d %s: %.1f us per layer" % (name, C_, B, "split3" if split3 else "f16", e0.elapsed_time(e1) / 20 * 1e3))
+    print("%-10s C=%d B=%d %s align=%d delay=%s: %.1f us per layer" % (name, C_, B, "split3" if split3 else "f16", ALIGN, os.environ.get("NHVR_FUSED_DELAY", "default"), e0.elapsed_time(e1) / 20 * 1e3))
