@@ -16,6 +16,9 @@ a CUDA graph and replayed, so the host issues one graph launch per frame step.
 """
 from __future__ import annotations
 
+import contextlib
+import gc
+
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -27,6 +30,21 @@ from .networks import define_G
 N_PARTS = 24
 UV_CHANNELS = 25 + 2 * N_PARTS
 PRECISION_PRESETS = {"strict": ("split3", "split3"), "balanced": ("split3", "f16"), "fast": ("f16", "f16")}
+
+
+@contextlib.contextmanager
+def _no_gc():
+    """Stream capture must not be interrupted by the cyclic garbage collector: collecting an OLD step graph (pipeline <->
+    graph reference cycles are only freed by the collector) destroys its CUDA graph, which is not permitted while another
+    stream is capturing and invalidates the capture.  torch.cuda.graph() collects once on entry; this keeps the automatic
+    collector off for the duration of the capture."""
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
 
 
 class RenderPipeline(nn.Module):
@@ -210,7 +228,7 @@ class _StepGraph:
             self.reset()
             g = torch.cuda.CUDAGraph()
             n0 = capi.launch_count()
-            with torch.cuda.graph(g):
+            with _no_gc(), torch.cuda.graph(g):
                 self._body()
             self.launches_per_step = capi.launch_count() - n0
             self.graph = g
@@ -442,7 +460,7 @@ class _PipelinedStepGraph(_StepGraph):
         for p in (0, 1):
             g = torch.cuda.CUDAGraph()
             n0 = capi.launch_count()
-            with torch.cuda.graph(g):
+            with _no_gc(), torch.cuda.graph(g):
                 self._frame(p)
             self.launches_per_step = capi.launch_count() - n0
             self.graphs.append(g)
