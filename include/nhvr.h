@@ -249,7 +249,8 @@ int nhvr_composite_bwd(const float* fgm, const float* bg, int32_t bg_batched, co
  * back (ReflectionPad2d), 0 drops them (zero padding).  skip (nullable): extra gradient of the un-padded
  * output (ResnetBlock skip path), P8 [N][C8][H][W].  raw / stats: the forward RAW_STATS outputs.
  * Writes g (gradient w.r.t. raw) in g_desc's format, halo zeroed; dy_out (nullable) receives the folded
- * total gradient of the un-padded output; sums is a float [N][C8*8][2] scratch. */
+ * total gradient of the un-padded output; sums is a 4-byte scratch of N*C8*17 elements (float [N][C8*8][2] sums + N*C8
+ * arrival counters of the single-launch kernel, whose second pass re-reads its rows from L2). */
 int nhvr_in_bwd(const void* dx, int32_t dx_H, int32_t dx_W, int32_t pad_t, int32_t pad_l, int32_t reflect,
                 const void* skip, const void* raw, const nhvr_act_desc* raw_desc, const double* stats, float eps,
                 int32_t act, float* sums, void* g, const nhvr_act_desc* g_desc, void* dy_out, void* stream);

@@ -557,6 +557,7 @@ struct InBwdParams {
   float eps, inv_hw;
   int32_t act, f16;
   int32_t* ovf;            // nullable overflow flag (nhvr_set_overflow_flag)
+  uint32_t* sync;          // single-launch variant: per-plane arrival counters [N*C8], behind `sums`, zeroed with them
 };
 
 // folded gradient of interior pixel (y, x) of plane np
@@ -671,24 +672,13 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const __grid_constant
 // Row formulation of both passes (PASS 0: the two reductions, PASS 1: apply): one warp per interior row y, the padded
 // rows that fold onto it are resolved once per row, lanes stride over x with kBwdCols columns in flight (primary dX tap,
 // raw and skip loads are issued before anything is consumed; the mirrored extra taps only exist on the border).
-constexpr int kBwdCols = 4;
 
-template <int PASS>
-__global__ void __launch_bounds__(256, 2) in_bwd_rows_kernel(const __grid_constant__ InBwdParams P) {
-  const int64_t np = blockIdx.y;
-  const int n = (int)(np / P.C8), p = (int)(np - (int64_t)n * P.C8);
+// One pass over the rows this block owns.  PASS 0 accumulates (s1, s2), PASS 1 applies with (m1, m2).
+template <int PASS, int kBwdCols>
+NHVR_DEVINL void in_bwd_rows_pass(const InBwdParams& P, int64_t np, int n, int p, const float (&scale)[8], const float (&shift)[8],
+                                  const float (&m1)[8], const float (&m2)[8], float (&s1)[8], float (&s2)[8], bool& bad, int row_blocks) {
   const FoldGeom& f = P.f;
   const ActGeom& g = P.gg;
-  float scale[8], shift[8], m1[8], m2[8];
-  fwd_norm_params(P, np, scale, shift);
-  if (PASS == 1) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { m1[e] = P.sums[np * 16 + 2 * e] * P.inv_hw; m2[e] = P.sums[np * 16 + 2 * e + 1] * P.inv_hw; }
-  }
-  float s1[8], s2[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
-  bool bad = false;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint4* dxp = P.dx + np * (int64_t)f.Hp * f.Wp;
   const uint4* rawp = P.raw + np * (int64_t)f.H * f.W;
@@ -698,7 +688,7 @@ __global__ void __launch_bounds__(256, 2) in_bwd_rows_kernel(const __grid_consta
   const int Hq = g.Hp >> 1, Wq = g.Wp >> 1;
   // PASS 0 walks the interior rows, PASS 1 every row of the gradient format (halo rows are written as zeros)
   const int nrows = PASS == 1 ? g.Hp : f.H;
-  for (int rr = blockIdx.x * 8 + warp; rr < nrows; rr += gridDim.x * 8) {
+  for (int rr = blockIdx.x * 8 + warp; rr < nrows; rr += row_blocks * 8) {
     const int y = PASS == 1 ? rr - g.pad_t : rr;
     const bool row_in = (y >= 0) & (y < f.H);
     // padded rows of dX that fold onto interior row y
@@ -783,8 +773,31 @@ __global__ void __launch_bounds__(256, 2) in_bwd_rows_kernel(const __grid_consta
       }
     }
   }
-  if (PASS == 1 && bad && P.ovf) atomicOr(P.ovf, 1);
-  if (PASS == 0) {
+}
+
+// PASS 0 / 1: the two launches of the two-kernel path.  PASS 2: BOTH passes in one launch - the blocks of a plane reduce
+// their rows, meet at a per-plane arrival counter (blocks are dispatched in index order and a plane's blocks fit the GPU at
+// once, checked by the host), and apply to the same rows, which are then served by L2 instead of HBM: 3 tensor passes of DRAM
+// traffic instead of 5.  A wait that exceeds ~2 s traps.
+template <int PASS, int COLS, int MINB>
+__global__ void __launch_bounds__(256, MINB) in_bwd_rows_kernel(const __grid_constant__ InBwdParams P) {
+  const int64_t np = blockIdx.y;
+  const int n = (int)(np / P.C8), p = (int)(np - (int64_t)n * P.C8);
+  float scale[8], shift[8], m1[8], m2[8];
+  fwd_norm_params(P, np, scale, shift);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { m1[e] = 0.f; m2[e] = 0.f; }
+  if (PASS == 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { m1[e] = P.sums[np * 16 + 2 * e] * P.inv_hw; m2[e] = P.sums[np * 16 + 2 * e + 1] * P.inv_hw; }
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
+  bool bad = false;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (PASS == 0 || PASS == 2) {
+    in_bwd_rows_pass<0, COLS>(P, np, n, p, scale, shift, m1, m2, s1, s2, bad, gridDim.x);
     __shared__ float sh[16][8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -799,6 +812,29 @@ __global__ void __launch_bounds__(256, 2) in_bwd_rows_kernel(const __grid_consta
       for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
       atomicAdd(P.sums + np * 16 + threadIdx.x, t);
     }
+  }
+  if (PASS == 2) {
+    __shared__ float s_m[16];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t* cnt = P.sync + np;
+      red_release_gpu_add(cnt, 1u);
+      const long long t0 = clock64();
+      while (ld_acquire_gpu(cnt) < gridDim.x) {
+        __nanosleep(100);
+        if (clock64() - t0 > (1ll << 32)) __trap();
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) s_m[threadIdx.x] = __ldcg(P.sums + np * 16 + threadIdx.x) * P.inv_hw;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { m1[e] = s_m[2 * e]; m2[e] = s_m[2 * e + 1]; }
+  }
+  if (PASS == 1 || PASS == 2) {
+    in_bwd_rows_pass<1, COLS>(P, np, n, p, scale, shift, m1, m2, s1, s2, bad, gridDim.x);
+    if (bad && P.ovf) atomicOr(P.ovf, 1);
   }
 }
 
@@ -949,14 +985,37 @@ extern "C" int nhvr_in_bwd(const void* dx, int32_t dx_H, int32_t dx_W, int32_t p
   P.dy_out = reinterpret_cast<uint4*>(dy_out);
   cudaStream_t s = (cudaStream_t)stream;
   const int planes = P.N * P.C8;
-  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)planes * 16 * sizeof(float), s);
+  P.sync = reinterpret_cast<uint32_t*>(sums + (size_t)planes * 16);
+  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)planes * 17 * sizeof(float), s);      // sums + arrival counters
   if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
   static const char* rows_env = std::getenv("NHVR_BWD_ROWS");
+  static const char* one_env = std::getenv("NHVR_BWD_ONE_LAUNCH");
+  // measured (profiles/r02b_in_fused.md): the single launch LOSES - 9.7 vs 8.2 ms per end-to-end training step, 2.5 vs 2.0 ms per UV
+  // pre-train step: blocks idle at the meeting point cost more than the L2-served second pass saves - so it is opt-in
+  if (!(rows_env && std::atoi(rows_env) == 0) && (one_env && std::atoi(one_env) != 0)) {
+    // Both passes in ONE launch: one row per warp and pass, so that few planes are in flight at a time (296 resident blocks /
+    // 65 blocks per 512-row plane = 4.5 planes x 12.6 MB of dX + raw + g: L2-resident); a plane's blocks (<= 148: half of
+    // the resident blocks of this kernel) meet at an arrival counter between the passes and the second pass re-reads its
+    // rows from L2.
+    int sms = 148;
+    { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int gx = std::max(1, std::min((P.gg.Hp + 7) / 8, sms));
+    in_bwd_rows_kernel<2, 4, 2><<<dim3(gx, planes), 256, 0, s>>>(P);
+    NHVR_POST();
+    return NHVR_OK;
+  }
   if (!(rows_env && std::atoi(rows_env) == 0)) {
     // reduce: ~4 rows per warp (fewer atomics per plane), apply: one row per warp
-    in_bwd_rows_kernel<0><<<dim3(std::max(1, (P.f.H + 31) / 32), planes), 256, 0, s>>>(P);
-    NHVR_POST();
-    in_bwd_rows_kernel<1><<<dim3(std::max(1, (P.gg.Hp + 7) / 8), planes), 256, 0, s>>>(P);
+    // NHVR_BWD_VARIANT = 0 (4 columns in flight per lane, 2 blocks / SM: 122-124 registers) | 1 (2 columns, 3 blocks) | 2 (2, 4) |
+    // 3 (1 column, 4 blocks: 64 registers).  Measured per end-to-end training step / UV pre-train step (ms of in_bwd):
+    // 8.14 / 1.98, 7.24 / 1.71, 7.77 / 1.72, 7.26 / 1.60 -> occupancy beats loads in flight per thread; default 3
+    static int variant = -1;
+    if (variant < 0) { const char* ev = std::getenv("NHVR_BWD_VARIANT"); variant = ev ? std::atoi(ev) : 3; }
+    const dim3 g0(std::max(1, (P.f.H + 31) / 32), planes), g1(std::max(1, (P.gg.Hp + 7) / 8), planes);
+    if (variant == 1) { in_bwd_rows_kernel<0, 2, 3><<<g0, 256, 0, s>>>(P); NHVR_POST(); in_bwd_rows_kernel<1, 2, 3><<<g1, 256, 0, s>>>(P); }
+    else if (variant == 2) { in_bwd_rows_kernel<0, 2, 4><<<g0, 256, 0, s>>>(P); NHVR_POST(); in_bwd_rows_kernel<1, 2, 4><<<g1, 256, 0, s>>>(P); }
+    else if (variant == 3) { in_bwd_rows_kernel<0, 1, 4><<<g0, 256, 0, s>>>(P); NHVR_POST(); in_bwd_rows_kernel<1, 1, 4><<<g1, 256, 0, s>>>(P); }
+    else { in_bwd_rows_kernel<0, 4, 2><<<g0, 256, 0, s>>>(P); NHVR_POST(); in_bwd_rows_kernel<1, 4, 2><<<g1, 256, 0, s>>>(P); }
     NHVR_POST();
     return NHVR_OK;
   }

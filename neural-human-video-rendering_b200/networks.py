@@ -245,7 +245,7 @@ class _ChainEngine:
             B["dX"][i] = xpool[k]
         B["ws"] = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         maxc8 = max(pl.Cout8 for pl in self.plans)
-        B["sums"] = torch.zeros(self.N * maxc8 * 16, dtype=torch.float32, device=dev)
+        B["sums"] = torch.zeros(self.N * maxc8 * 17, dtype=torch.float32, device=dev)      # sums + per-plane arrival counters
         B["dy"] = {}
         self._bwd = B
         self._bwd_versions = None

@@ -17,9 +17,11 @@ if mode == "uv":
     step = lambda: tr.step(*data)
 else:
     pipe = RenderPipeline(**PIPE_KW).to(dev)
-    netD = define_D(6, 64, 3, "instance", False, 2, True)
+    netD = define_D(PIPE_KW["pose_nc"] + 3, 64, 3, "instance", False, 2, True)
     tr = RenderTrainer(pipe, netD)
     batch = synthetic_train_batch(8, 512, dev)
+    z = torch.zeros(8, PIPE_KW["pose_nc"] - 3, 512, 512, device=dev)            # the zero LaplaceProj channels of --use_laplace
+    batch["pose"], batch["pose_prev"] = torch.cat([batch["pose"], z], 1), torch.cat([batch["pose_prev"], z], 1)
     step = lambda: tr.step(batch)
 for _ in range(2):
     step()
