@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import contextlib
 import gc
+import os
 
 from typing import Dict, List, Optional, Tuple
 
@@ -176,6 +177,9 @@ class RenderPipeline(nn.Module):
         fewer tiles than the GPU has CTA slots, and only the temporal generator depends on the previous frame."""
         if pipelined is None:
             pipelined = use_graph and B * ((H + 127) // 128) * ((W + 127) // 128) <= 32
+            env = os.environ.get("NHVR_PIPELINED")             # experiments: force the two-stage frame pipeline on (1) / off (0)
+            if env is not None and use_graph:
+                pipelined = env not in ("0", "")
         key = (B, H, W, use_graph, pipelined, self.netTransG.precision, self.netG.precision, self.netBG.precision, self.use_mask_texture)
         g = self._graphs.get(key)
         if g is None:

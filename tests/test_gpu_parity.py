@@ -12,8 +12,9 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-# parity bars: fp16 operands (default) meet BASELINE's 2e-2 / 45 dB; bf16 operands (NHVR_OPERAND=bf16) are
-# measured ~4x outside it at full depth and are checked against a documented looser bound
+# parity bars: fp16 operands (the default and the only operand type a parity claim is made for) meet BASELINE's 2e-2 / 45 dB.
+# bf16 operands (NHVR_OPERAND=bf16, kept because north_star names bf16) are measured ~4x outside the bar at full depth
+# (profiles/r01_precision.log); their entry is a regression guard for that alternative path, NOT a north_star bar
 BARS = {"f16": (2e-2, 45.0), "bf16": (1.5e-1, 38.0)}
 
 
