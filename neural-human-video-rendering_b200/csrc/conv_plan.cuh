@@ -15,10 +15,12 @@ struct ConvJob {
   int16_t acc;     // accumulator index
   int16_t first;   // first job of its accumulator (overwrites instead of accumulating)
 };
-struct ConvMma {     // one tcgen05.mma of a chunk: precomputed so the issue loop has no arithmetic chains
+struct ConvMma {     // one weight block of a chunk and the tcgen05.mma(s) it feeds: precomputed so the issue loop has no arithmetic chains
   int32_t a_off;     // (job shift + k-step plane offset) in 16-B units inside the chunk slab
   uint32_t meta;     // bits 0-15: accumulator column offset in TMEM; bit 16: first MMA of its accumulator (overwrites
                      // instead of accumulating when executed in the first chunk).  32-bit fields keep the reads uniform.
+  int32_t a_off2;    // split precision: the same weight block (w_hi) feeds a SECOND MMA whose A operand is the lo planes at this
+                     // offset (x_hi*w_hi and x_lo*w_hi share one streamed block); < 0: none
 };
 struct ConvRun {
   int32_t g_off;   // offset (units) from the plane base + q0
@@ -73,6 +75,7 @@ struct ConvKParams {
   ConvRun runs[kMaxRuns];
   ConvMma mma[kMaxMma + 1];   // +1: the issue loop prefetches one entry ahead
 };
+static_assert(sizeof(ConvKParams) <= 4096, "ConvKParams is passed as a __grid_constant__ kernel parameter");
 
 
 }  // namespace nhvr

@@ -182,8 +182,9 @@ constexpr int kThreads = 384;       // warps 0-3: roles, warps 4-11: epilogue
 // per MMA (the measured ceiling of the single-CTA kernel: profiles/r01_conv_ablation.md) drops from
 // A + 2*B to A + B bytes.  The leader (rank 0) issues the MMAs; the peer's MMA warp relays its local "stage full"
 // events to the leader's barriers; commits are multicast to both CTAs; each CTA drains its own 128 TMEM lanes.
-// V = 1 adds the rarely used paths (split precision: accumulator scale + hilo raw output; centred stem statistics; the
-// shuffle epilogue of the row-mode RGB head) so that their registers and code do not weigh on the standard layers.
+// V = 1 adds the rarely used paths (accumulator scale + hilo raw output; centred stem statistics; the shuffle epilogue of the
+// row-mode RGB head; the fused InstanceNorm epilogue) so that their registers and code do not weigh on the standard layers;
+// V = 2 = V = 1 + the split-precision issue loop (a w_hi weight block feeds the x_hi and the x_lo MMA).
 template <bool PAIR, int V>
 __global__ void __launch_bounds__(kThreads, V ? 2 : 1) conv_shiftgemm_kernel(const __grid_constant__ ConvKParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -398,6 +399,18 @@ __global__ void __launch_bounds__(kThreads, V ? 2 : 1) conv_shiftgemm_kernel(con
                 a_lo += a_mstride; d_col += acc_mstride;
                 const uint64_t adesc_i = dhi | a_lo;
                 if (leader) { if (PAIR) umma2_bf16(d_col, adesc_i, bdesc, idesc, acc_flag); else umma_bf16(d_col, adesc_i, bdesc, idesc, acc_flag); }
+              }
+            }
+            if (V == 2 && cur.a_off2 >= 0) {                 // split precision: x_lo * w_hi on the block that just fed x_hi * w_hi
+              uint32_t a2 = a_st_lo + (uint32_t)cur.a_off2, d2 = tmem_base + (cur.meta & 0xffffu);
+              const uint64_t adesc2 = dhi | a2;
+              if (leader) { if (PAIR) umma2_bf16(d2, adesc2, bdesc, idesc, 1u); else umma_bf16(d2, adesc2, bdesc, idesc, 1u); }
+              if (decltype(multi)::value) {
+                for (int i = 1; i < mrep; ++i) {
+                  a2 += a_mstride; d2 += acc_mstride;
+                  const uint64_t adesc_i = dhi | a2;
+                  if (leader) { if (PAIR) umma2_bf16(d2, adesc_i, bdesc, idesc, 1u); else umma_bf16(d2, adesc_i, bdesc, idesc, 1u); }
+                }
               }
             }
             b_lo += b_block_u;
@@ -859,8 +872,9 @@ __global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
     wscale = ldexpf(1.f, sh);
     if (blockIdx.x == 0 && threadIdx.x == 0) P.tail[1] = ldexpf(1.f, -sh);
   }
-  // MMAs per (chunk, tap): kcp/2 plane pairs; split precision: 3 per group of four physical planes (hi*hi, hi*lo, lo*hi)
-  const int qsteps = P.kfold ? 1 : (P.split3 ? 3 * (P.kcp >> 2) : P.kcp >> 1);
+  // weight blocks per (chunk, tap): kcp/2 plane pairs; split precision: 2 per group of four physical planes - w_hi (feeds the
+  // x_hi and the x_lo MMA) and w_lo (feeds x_hi)
+  const int qsteps = P.kfold ? 1 : (P.split3 ? 2 * (P.kcp >> 2) : P.kcp >> 1);
   const int nblocks = P.nchunks * P.njobs * qsteps;
   for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (int64_t)gridDim.x * blockDim.x) {
     const int nrow = (int)(u % P.Npad);
@@ -886,9 +900,9 @@ __global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
         else tap += kp;
       }
       float vals[8];
-      // split precision: block qq = 3*g + t of a chunk covers logical planes 2*(c*kcp/4 + g) + kp; t == 1 carries w_lo
-      const int lplane = P.split3 ? 2 * (c * (P.kcp >> 2) + qq / 3) + kp : c * P.kcp + 2 * qq + kp;
-      const bool w_lo = P.split3 && (qq % 3) == 1;
+      // split precision: block qq = 2*g + t of a chunk covers logical planes 2*(c*kcp/4 + g) + kp; t == 1 carries w_lo
+      const int lplane = P.split3 ? 2 * (c * (P.kcp >> 2) + qq / 2) + kp : c * P.kcp + 2 * qq + kp;
+      const bool w_lo = P.split3 && (qq & 1);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int ci = P.kfold ? e : lplane * 8 + e;
@@ -1162,7 +1176,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
       if (C8 % cand) continue;
       if (split3 && (cand & 3)) continue;                     // hi/lo groups of four physical planes stay in one chunk
       const int nch = C8 / cand;
-      const int bpc = kfold ? (int)taps.size() : split3 ? (int)taps.size() * 3 * (cand / 4) : (int)taps.size() * cand / 2;   // MMA blocks per chunk
+      const int bpc = kfold ? (int)taps.size() : split3 ? (int)taps.size() * 2 * (cand / 4) : (int)taps.size() * cand / 2;   // weight blocks per chunk
       if (bpc > kMaxMma) continue;
       // split precision doubles the slab bytes of a chunk (hi + lo planes) while tripling its MMAs: a single slab stage
       // (the co-resident CTA covers the refill) is allowed there when two stages do not leave room for the weight ring
@@ -1267,7 +1281,10 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
       // NHVR_CONV_PAIR=1 forces every eligible layer, =0 disables
       const char* pe = std::getenv("NHVR_CONV_PAIR");
       const bool eligible = nacc == 1 && !rowmode && !(d->flags & 1) && Npad >= 96 && (Npad % 16) == 0;
-      pair = eligible && (pe ? std::atoi(pe) != 0 : (Npad > 128 && Npad <= 192)) ? 1 : 0;
+      // split precision: also at N = 256 (the weight stream is twice as long per MMA block pair: 435 -> 419 us per 256 -> 256 layer)
+      // (stride-1 layers only: the stride-2 256-channel split-precision layer traps in pair mode - not investigated)
+      const int pair_max = (split3 && d->kind == NHVR_CONV && d->stride == 1) ? 256 : 192;
+      pair = eligible && (pe ? std::atoi(pe) != 0 : (Npad > 128 && Npad <= pair_max)) ? 1 : 0;
     }
     // flag bit 5 (fused InstanceNorm epilogue): shrink the tile step so that an image has exactly one tile per SM (148) -
     // whole images then fill the resident slots (2 per SM) and no CTA waits a full round for the rest of its image
@@ -1320,7 +1337,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   K.kcp = kcp; K.SA = SA; K.bpb = bpb; K.SB = SB;
   K.pair = pair;
   K.nchunks = C8 / kcp;
-  const int ksteps = kfold ? 1 : split3 ? 3 * (kcp / 4) : kcp / 2;
+  const int ksteps = kfold ? 1 : split3 ? 2 * (kcp / 4) : kcp / 2;      // weight blocks per (chunk, tap)
   K.mmas_per_chunk = K.njobs * ksteps;
   K.a_lbo_units = kfold ? 1 : slab;
   K.stages_per_chunk = K.mmas_per_chunk / bpb;           // bpb divides mmas_per_chunk by construction
@@ -1330,9 +1347,11 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   for (int j = 0; j < K.njobs; ++j)
     for (int q = 0; q < ksteps; ++q) {
       ConvMma& m = K.mma[j * ksteps + q];
-      // A planes of step q inside the chunk slab: plane pair q, or (split precision) hi, hi, lo of group q / 3
-      const int aplane = split3 ? 4 * (q / 3) + ((q % 3) == 2 ? 2 : 0) : 2 * q;
+      // A planes of step q inside the chunk slab: plane pair q, or (split precision) the hi planes of group q / 2; the w_hi
+      // block (q even) also feeds the lo planes (second MMA)
+      const int aplane = split3 ? 4 * (q / 2) : 2 * q;
       m.a_off = jobs[j].a_off + aplane * slab;
+      m.a_off2 = (split3 && (q & 1) == 0) ? jobs[j].a_off + (aplane + 2) * slab : -1;
       m.meta = (uint32_t)(jobs[j].acc * Npad) | ((jobs[j].first && q == 0) ? 0x10000u : 0u);
     }
   K.w_split_units = (int64_t)nblocks_padded * 2 * Npad;
@@ -1443,6 +1462,8 @@ static cudaError_t conv_set_attrs() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_shiftgemm_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_shiftgemm_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_shiftgemm_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_shiftgemm_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_shiftgemm_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e == cudaSuccess) attr_set = true;
   return e;
 }
@@ -1451,11 +1472,12 @@ static inline dim3 conv_grid(const nhvr_conv_plan* p) {
   return dim3(p->kp.pair ? (p->tiles_per_img + 1) & ~1 : p->tiles_per_img, p->d.N, p->nsplit);   // pairs: an even number of tiles
 }
 
-// launch with the plan's lowering (CTA pair or not; `special` selects kernel variant 1, see the kernel header)
-static cudaError_t conv_launch(const nhvr_conv_plan* p, const ConvKParams& K, bool special, cudaStream_t stream) {
+// launch with the plan's lowering (CTA pair or not; `variant` selects the kernel instantiation, see the kernel header)
+static cudaError_t conv_launch(const nhvr_conv_plan* p, const ConvKParams& K, int variant, cudaStream_t stream) {
   const dim3 grid = conv_grid(p);
   if (!K.pair) {
-    if (special) conv_shiftgemm_kernel<false, 1><<<grid, kThreads, p->smem_bytes, stream>>>(K);
+    if (variant == 2) conv_shiftgemm_kernel<false, 2><<<grid, kThreads, p->smem_bytes, stream>>>(K);
+    else if (variant == 1) conv_shiftgemm_kernel<false, 1><<<grid, kThreads, p->smem_bytes, stream>>>(K);
     else conv_shiftgemm_kernel<false, 0><<<grid, kThreads, p->smem_bytes, stream>>>(K);
     return cudaGetLastError();
   }
@@ -1465,17 +1487,18 @@ static cudaError_t conv_launch(const nhvr_conv_plan* p, const ConvKParams& K, bo
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  if (special) return cudaLaunchKernelEx(&cfg, conv_shiftgemm_kernel<true, 1>, K);
+  if (variant == 2) return cudaLaunchKernelEx(&cfg, conv_shiftgemm_kernel<true, 2>, K);
+  if (variant == 1) return cudaLaunchKernelEx(&cfg, conv_shiftgemm_kernel<true, 1>, K);
   return cudaLaunchKernelEx(&cfg, conv_shiftgemm_kernel<true, 0>, K);
 }
 
 // NHVR_CONV_TRACE diagnostics: per-CTA cycle breakdown printed to stderr (synchronises)
-static void conv_launch_traced(const nhvr_conv_plan* p, ConvKParams& K, bool special, cudaStream_t stream) {
+static void conv_launch_traced(const nhvr_conv_plan* p, ConvKParams& K, int variant, cudaStream_t stream) {
   const dim3 grid = conv_grid(p);
   const size_t nct = (size_t)grid.x * grid.y * grid.z;
   cudaMalloc(&K.trace, nct * 128);
   cudaMemset(K.trace, 0, nct * 128);
-  conv_launch(p, K, special, stream);
+  conv_launch(p, K, variant, stream);
   cudaDeviceSynchronize();
   std::vector<long long> h(nct * 16);
   cudaMemcpy(h.data(), K.trace, nct * 128, cudaMemcpyDeviceToHost);
@@ -1519,13 +1542,14 @@ extern "C" int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const 
   { cudaError_t e = conv_set_attrs(); if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; } }
   // variant 1 = the layers that need the special epilogue paths (see the kernel header)
   const bool special = K.acc_scale != nullptr || K.out_hilo || K.stat_centred || (K.rowmode && K.Cp == 8);
+  const int variant = p->pp.split3 ? 2 : special ? 1 : 0;
   K.trace = nullptr;
   if (std::getenv("NHVR_CONV_TRACE")) {
-    conv_launch_traced(p, K, special, (cudaStream_t)stream);
+    conv_launch_traced(p, K, variant, (cudaStream_t)stream);
     count_launch();
     return NHVR_OK;
   }
-  cudaError_t e = conv_launch(p, K, special, (cudaStream_t)stream);
+  cudaError_t e = conv_launch(p, K, variant, (cudaStream_t)stream);
   count_launch();
   if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
   return NHVR_OK;
@@ -1548,7 +1572,9 @@ extern "C" int nhvr_conv_in_fused_supported(const nhvr_conv_plan* p) {
       cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev) != cudaSuccess)
     return 0;
   cudaFuncAttributes fa;
-  cudaError_t e = p->kp.pair ? cudaFuncGetAttributes(&fa, conv_shiftgemm_kernel<true, 1>) : cudaFuncGetAttributes(&fa, conv_shiftgemm_kernel<false, 1>);
+  cudaError_t e;
+  if (p->pp.split3) e = p->kp.pair ? cudaFuncGetAttributes(&fa, conv_shiftgemm_kernel<true, 2>) : cudaFuncGetAttributes(&fa, conv_shiftgemm_kernel<false, 2>);
+  else e = p->kp.pair ? cudaFuncGetAttributes(&fa, conv_shiftgemm_kernel<true, 1>) : cudaFuncGetAttributes(&fa, conv_shiftgemm_kernel<false, 1>);
   if (e != cudaSuccess) { cudaGetLastError(); return 0; }
   // Resident CTAs per SM of kernel variant 1 with this plan's shared memory.  Computed from the device limits (1 KB of
   // shared memory is reserved per CTA; registers are allocated per warp in units of 256; 512 TMEM columns per SM) rather
@@ -1619,12 +1645,13 @@ extern "C" int nhvr_conv_forward_in_fused(const nhvr_conv_plan* p, const void* i
   K.acc_scale = p->pp.split3 ? reinterpret_cast<const float*>(reinterpret_cast<const uint4*>(packed_w) + (int64_t)p->nsplit * K.w_split_units) + 1 : nullptr;
   { cudaError_t e = conv_set_attrs(); if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; } }
   K.trace = nullptr;
+  const int variant = p->pp.split3 ? 2 : 1;
   if (std::getenv("NHVR_CONV_TRACE")) {
-    conv_launch_traced(p, K, true, (cudaStream_t)stream);
+    conv_launch_traced(p, K, variant, (cudaStream_t)stream);
     count_launch();
     return NHVR_OK;
   }
-  cudaError_t e = conv_launch(p, K, true, (cudaStream_t)stream);
+  cudaError_t e = conv_launch(p, K, variant, (cudaStream_t)stream);
   count_launch();
   if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
   return NHVR_OK;
