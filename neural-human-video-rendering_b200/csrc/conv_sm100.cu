@@ -1282,7 +1282,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
       const char* pe = std::getenv("NHVR_CONV_PAIR");
       const bool eligible = nacc == 1 && !rowmode && !(d->flags & 1) && Npad >= 96 && (Npad % 16) == 0;
       // split precision: also at N = 256 (the weight stream is twice as long per MMA block pair: 435 -> 419 us per 256 -> 256 layer)
-      // (stride-1 layers only: the stride-2 256-channel split-precision layer traps in pair mode - not investigated)
+      // (stride-1 layers only; see the single-slab-stage guard below)
       const int pair_max = (split3 && d->kind == NHVR_CONV && d->stride == 1) ? 256 : 192;
       pair = eligible && (pe ? std::atoi(pe) != 0 : (Npad > 128 && Npad <= pair_max)) ? 1 : 0;
     }
@@ -1307,6 +1307,14 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
     if (!ok && K.tmem_cols <= 256) ok = try_fit(kSmemTwoPerSm);
     if (!ok) ok = try_fit(kSmemOnePerSm);
     if (!ok) { delete p; return NHVR_ERR_SMEM; }
+  }
+  // A CTA pair with a SINGLE slab stage (possible in split precision only) traps on the GPU (measured: stride-2 256-channel
+  // and M-replicated split-precision layers under NHVR_CONV_PAIR; cause not found) - such plans fall back to single CTAs.
+  if (pair && SA == 1) {
+    pair = 0;
+    bool refit = K.tmem_cols <= 256 && try_fit(kSmemTwoPerSm);
+    if (!refit) refit = try_fit(kSmemOnePerSm);
+    if (!refit) { delete p; return NHVR_ERR_SMEM; }
   }
 
   // ---- jobs (grouped by accumulator so that "first" is well defined)
