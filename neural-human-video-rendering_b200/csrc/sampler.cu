@@ -163,9 +163,12 @@ extern "C" int nhvr_texture_sample(const float* uvp, const float* atlas, int32_t
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = (int)std::min<int64_t>((total + 127) / 128, (int64_t)148 * 16 * 8);
 #define NHVR_LAUNCH_SAMPLER(GG) \
-  texture_sample_kernel<GG, 1><<<blocks, 128, 0, st>>>(uvp, a4, N, H, W, S, Ctex, use_mask_texture, tex_out, part_out, tx)
-  static int minb = -1;           // experiments: NHVR_SAMPLER_MINB = 8 caps the Ctex <= 4 kernel at 64 registers (32 warps / SM)
-  if (minb < 0) { const char* e = std::getenv("NHVR_SAMPLER_MINB"); minb = e ? std::atoi(e) : 0; }
+  texture_sample_kernel<GG, (GG == 1 ? 6 : 1)><<<blocks, 128, 0, st>>>(uvp, a4, N, H, W, S, Ctex, use_mask_texture, tex_out, part_out, tx)
+  // Ctex <= 4: 8 resident blocks per SM asked for = 64 registers, 32 warps / SM.  Measured (tools/sampler_bench.py, us per launch at
+  // B = 8, 512^2; white-noise / smooth / 98 % flat UV): 64 registers 557 / 468 / 290, 80 registers 557 / 479 / 336; without any
+  // bound ptxas takes 254 registers (8 warps / SM): 457 vs 431 us in the frame step.  NHVR_SAMPLER_MINB=6 selects the 80-register build.
+  static int minb = -1;
+  if (minb < 0) { const char* e = std::getenv("NHVR_SAMPLER_MINB"); minb = e ? std::atoi(e) : 8; }
   switch (G) {
     case 1:
       if (minb >= 8) texture_sample_kernel<1, 8><<<blocks, 128, 0, st>>>(uvp, a4, N, H, W, S, Ctex, use_mask_texture, tex_out, part_out, tx);
