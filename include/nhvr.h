@@ -179,7 +179,9 @@ int nhvr_in_apply(const void* raw, const nhvr_act_desc* raw_desc, const double* 
  * stats: zeroed by the caller; on return its four slots per channel hold two replicas of {sum, sum of squares} (even / odd
  * tiles; no centring shift on this path).  sync: device uint32 [N] arrival counters, zeroed by the caller before every launch
  * (the engines keep them behind the statistics so that one fill re-arms both).
- * A wait that exceeds ~2 s traps (sticky CUDA error) instead of hanging the GPU. */
+ * A wait that exceeds ~2 s traps (sticky CUDA error) instead of hanging the GPU.  Consequently at most TWO such launches may be in
+ * flight on a device at a time (the engines use one stream per network: two); more concurrent launches, or a GPU time-sliced
+ * with another process for seconds, can exhaust the slots / the time limit and end in that trap. */
 int nhvr_conv_in_fused_supported(const nhvr_conv_plan* p);
 int nhvr_conv_forward_in_fused(const nhvr_conv_plan* p, const void* in, const void* packed_w, double* stats, float eps, int32_t act,
                                const void* residual, const nhvr_act_desc* res_desc, void* dst, const nhvr_act_desc* dst_desc,
