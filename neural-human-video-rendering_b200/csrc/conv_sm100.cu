@@ -901,8 +901,11 @@ __global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
       }
       float vals[8];
       // split precision: block qq = 2*g + t of a chunk covers logical planes 2*(c*kcp/4 + g) + kp; t == 1 carries w_lo
-      const int lplane = P.split3 ? 2 * (c * (P.kcp >> 2) + qq / 2) + kp : c * P.kcp + 2 * qq + kp;
+      // khalf (split precision, <= 8 input channels): K group 1 of every MMA is the LO plane of the same 8 channels, so block 0
+      // carries w_hi in both K groups (x_hi*w_hi + x_lo*w_hi in ONE MMA) and block 1 carries w_lo in K group 0 only
+      const int lplane = P.khalf ? 0 : P.split3 ? 2 * (c * (P.kcp >> 2) + qq / 2) + kp : c * P.kcp + 2 * qq + kp;
       const bool w_lo = P.split3 && (qq & 1);
+      if (P.khalf && w_lo && kp == 1) co = P.Cout;          // zero weights: the lo plane meets no w_lo
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int ci = P.kfold ? e : lplane * 8 + e;
@@ -1345,9 +1348,12 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   K.kcp = kcp; K.SA = SA; K.bpb = bpb; K.SB = SB;
   K.pair = pair;
   K.nchunks = C8 / kcp;
+  // split precision with a single logical input plane (<= 8 channels: the pose stem): the second K group of an MMA would be a zero
+  // plane; address the LO plane there instead (A descriptor K-group stride = two slab planes) - two MMAs per tap instead of three
+  const bool khalf = split3 && !kfold && !rowmode && gemm_k <= 8 && C8 == 4 && kcp == 4 && !std::getenv("NHVR_NO_KHALF");
   const int ksteps = kfold ? 1 : split3 ? 2 * (kcp / 4) : kcp / 2;      // weight blocks per (chunk, tap)
   K.mmas_per_chunk = K.njobs * ksteps;
-  K.a_lbo_units = kfold ? 1 : slab;
+  K.a_lbo_units = kfold ? 1 : khalf ? 2 * slab : slab;
   K.stages_per_chunk = K.mmas_per_chunk / bpb;           // bpb divides mmas_per_chunk by construction
   K.nblocks = K.nchunks * K.mmas_per_chunk;
   K.nbstages = K.nchunks * K.stages_per_chunk;
@@ -1359,7 +1365,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
       // block (q even) also feeds the lo planes (second MMA)
       const int aplane = split3 ? 4 * (q / 2) : 2 * q;
       m.a_off = jobs[j].a_off + aplane * slab;
-      m.a_off2 = (split3 && (q & 1) == 0) ? jobs[j].a_off + (aplane + 2) * slab : -1;
+      m.a_off2 = (split3 && !khalf && (q & 1) == 0) ? jobs[j].a_off + (aplane + 2) * slab : -1;
       m.meta = (uint32_t)(jobs[j].acc * Npad) | ((jobs[j].first && q == 0) ? 0x10000u : 0u);
     }
   K.w_split_units = (int64_t)nblocks_padded * 2 * Npad;
@@ -1383,6 +1389,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   PP.pair = pair; PP.bpb = bpb;
   PP.kfold = kfold ? 1 : 0;
   PP.split3 = split3 ? 1 : 0;
+  PP.khalf = khalf ? 1 : 0;
   K.stat_centred = (d->flags & 16) ? 1 : 0;
   K.out_hilo = (split3 && (d->epilogue == NHVR_EPI_RAW_STATS || d->epilogue == NHVR_EPI_RAW_P8)) ? 1 : 0;
   *out = p;
