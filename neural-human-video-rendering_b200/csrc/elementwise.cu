@@ -83,6 +83,80 @@ __global__ void __launch_bounds__(256) pack_nchw_kernel(const __grid_constant__ 
   }
 }
 
+// Row formulation of the pack: one warp per destination row, 4 columns per lane in flight, the hi AND the lo unit of a logical
+// plane written by the same thread (the flat kernel above reads every input twice for a split-precision destination and pays two
+// integer divisions per unit): the source row is resolved once per row, the 8 channel base pointers once per block.
+constexpr int kPackCols = 4;
+__global__ void __launch_bounds__(256) pack_nchw_rows_kernel(const __grid_constant__ PackParams2 P) {
+  const ActGeom& g = P.g;
+  const int CL = g.hilo ? g.C8 >> 1 : g.C8;                 // logical planes
+  const int np = blockIdx.y;
+  const int n = np / CL, p = np - n * CL;
+  const int ph = g.hilo ? hilo_plane(p) : p;
+  const int64_t HW = (int64_t)g.H * g.W;
+  // base pointer of each of the 8 channels of this logical plane (nullptr: beyond the concatenated sources -> zeros)
+  const float* chp[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    int c = p * 8 + e;
+    chp[e] = nullptr;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      if (s < P.nsrc && c >= 0) {
+        if (c < P.src_c[s]) { chp[e] = P.src[s] + ((int64_t)n * P.src_c[s] + c) * HW; c = -1; }
+        else c -= P.src_c[s];
+      }
+    }
+  }
+  uint4* dst = P.dst + ((int64_t)n * g.C8 + ph) * g.plane_units;
+  const int64_t dst_lo = 2 * g.plane_units;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool reflect = g.halo != NHVR_HALO_ZERO;
+  const int Hq = g.Hp >> 1, Wq = g.Wp >> 1;
+  for (int yy = blockIdx.x * 8 + warp; yy < g.Hp; yy += gridDim.x * 8) {
+    int y = yy - g.pad_t;
+    bool row_ok = (y >= 0) & (y < g.H);
+    if (!row_ok && reflect) { y = reflect_idx(y, g.H); row_ok = (y >= 0) & (y < g.H); }
+    const int64_t roff = (int64_t)y * g.W;
+    const int64_t d_even = g.split ? ((int64_t)(((yy & 1) << 1) | 0) * Hq + (yy >> 1)) * Wq : (int64_t)yy * g.Wp;
+    const int64_t d_odd = g.split ? ((int64_t)(((yy & 1) << 1) | 1) * Hq + (yy >> 1)) * Wq : 0;
+    for (int xx0 = lane; xx0 < g.Wp; xx0 += 32 * kPackCols) {
+      float v[kPackCols][8];
+      bool live[kPackCols];
+#pragma unroll
+      for (int j = 0; j < kPackCols; ++j) {
+        const int xx = xx0 + 32 * j;
+        int x = xx - g.pad_l;
+        live[j] = xx < g.Wp;
+        bool ok = row_ok && live[j];
+        if (ok && ((x < 0) | (x >= g.W))) {
+          if (reflect) { x = reflect_idx(x, g.W); ok = (x >= 0) & (x < g.W); } else ok = false;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[j][e] = (ok && chp[e]) ? __ldg(chp[e] + roff + x) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < kPackCols; ++j) {
+        if (!live[j]) continue;
+        const int xx = xx0 + 32 * j;
+        const int64_t du = g.split ? ((xx & 1) ? d_odd : d_even) + (xx >> 1) : d_even + xx;
+        uint4 o;
+        o.x = pack2(v[j][0], v[j][1], P.f16); o.y = pack2(v[j][2], v[j][3], P.f16);
+        o.z = pack2(v[j][4], v[j][5], P.f16); o.w = pack2(v[j][6], v[j][7], P.f16);
+        dst[du] = o;
+        if (g.hilo) {
+          uint4 l;
+          l.x = pack2(v[j][0] - unpack_lo(o.x, P.f16), v[j][1] - unpack_hi(o.x, P.f16), P.f16);
+          l.y = pack2(v[j][2] - unpack_lo(o.y, P.f16), v[j][3] - unpack_hi(o.y, P.f16), P.f16);
+          l.z = pack2(v[j][4] - unpack_lo(o.z, P.f16), v[j][5] - unpack_hi(o.z, P.f16), P.f16);
+          l.w = pack2(v[j][6] - unpack_lo(o.w, P.f16), v[j][7] - unpack_hi(o.w, P.f16), P.f16);
+          dst[du + dst_lo] = l;
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) unpack_nchw_kernel(const uint4* __restrict__ src, ActGeom g, float* __restrict__ dst,
                                                           int C, int f16) {
   const int np = blockIdx.y;
@@ -418,8 +492,18 @@ extern "C" int nhvr_pack_nchw(const float* const* src, const int32_t* src_c, int
   if (P.g.hilo && (P.g.C8 & 3)) return NHVR_ERR_SHAPE;
   if (csum > (P.g.hilo ? P.g.C8 / 2 : P.g.C8) * 8) return NHVR_ERR_SHAPE;
   const int planes = P.g.N * P.g.C8;
-  dim3 grid(grid_x_for((int64_t)P.g.Hp * P.g.Wp, planes), planes);
-  pack_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  static const char* rows_env = std::getenv("NHVR_PACK_ROWS");
+  if (!(rows_env && std::atoi(rows_env) == 0)) {
+    const int lplanes = P.g.N * (P.g.hilo ? P.g.C8 / 2 : P.g.C8);
+    // ~2 rows per warp while that still leaves >= ~4 waves of blocks
+    int gy = std::max(1, (P.g.Hp + 7) / 8);
+    const int cap = std::max(1, 148 * 8 * 4 / std::max(1, lplanes));
+    if (gy > cap) gy = std::max(cap, (P.g.Hp + 31) / 32);
+    pack_nchw_rows_kernel<<<dim3(gy, lplanes), 256, 0, (cudaStream_t)stream>>>(P);
+  } else {
+    dim3 grid(grid_x_for((int64_t)P.g.Hp * P.g.Wp, planes), planes);
+    pack_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  }
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
