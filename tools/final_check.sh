@@ -8,5 +8,5 @@ python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
 python - <<PY
 import json
 d=json.loads([l for l in open("gpurun_out/bench_final.json") if l.startswith("{")][0])
-print(d["value"], d["e2e"]["value"], d["ms_per_step"], d["roofline"]["frac"], d["train"]["steps_per_s"], d["train"]["e2e_step"]["steps_per_s"], d["cpu_baseline"]["value"], {k:(round(v["frac"],3), round(v["ms_per_step"],3)) for k,v in d["roofline_memory_kernels"].items()})
+print(d["value"], d["e2e"]["value"], d["ms_per_step"], d["roofline"]["frac"], d["train"]["steps_per_s"], d["train"]["e2e_step"]["steps_per_s"], d["cpu_baseline"]["value"], {k:(round(v["frac"],3), round(v["ms_per_frame_step"],3)) for k,v in d["roofline_memory_kernels"].items()})
 PY

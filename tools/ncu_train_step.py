@@ -10,16 +10,24 @@ from nhvr_b200.train import RenderTrainer, synthetic_train_batch
 
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
-pipe = RenderPipeline(**PIPE_KW).to(dev)
-netD = define_D(PIPE_KW["pose_nc"] + 3, 64, 3, "instance", False, 2, True)
-tr = RenderTrainer(pipe, netD)
-bt = synthetic_train_batch(8, 512, dev)
-z = torch.zeros(8, PIPE_KW["pose_nc"] - 3, 512, 512, device=dev)
-bt["pose"], bt["pose_prev"] = torch.cat([bt["pose"], z], 1), torch.cat([bt["pose_prev"], z], 1)
+if len(sys.argv) > 1 and sys.argv[1] == "uv":            # configs[1]: UV generator pre-train, 256^2, batch 16
+    from nhvr_b200.networks import define_G
+    from nhvr_b200.train import UVPretrainer, synthetic_densepose
+    tr_uv = UVPretrainer(define_G(3, 73, 64, "translate", 2, 5))
+    data = synthetic_densepose(16, 256, 256, dev)
+    step = lambda: tr_uv.step(*data)
+else:
+    pipe = RenderPipeline(**PIPE_KW).to(dev)
+    netD = define_D(PIPE_KW["pose_nc"] + 3, 64, 3, "instance", False, 2, True)
+    tr = RenderTrainer(pipe, netD)
+    bt = synthetic_train_batch(8, 512, dev)
+    z = torch.zeros(8, PIPE_KW["pose_nc"] - 3, 512, 512, device=dev)
+    bt["pose"], bt["pose_prev"] = torch.cat([bt["pose"], z], 1), torch.cat([bt["pose_prev"], z], 1)
+    step = lambda: tr.step(bt)
 for _ in range(3):
-    tr.step(bt)
+    step()
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-tr.step(bt)
+step()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
