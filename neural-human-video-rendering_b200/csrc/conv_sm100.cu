@@ -375,7 +375,10 @@ __global__ void __launch_bounds__(kThreads, V ? 2 : 1) conv_shiftgemm_kernel(con
       wait_b(0, 0);
       tc_fence_after();
       for (int c = 0; c < nchunks; ++c) {
-        if (SA == 1 && c > 0) wait_a(0, aph);                   // single slab stage: refilled only after the commit below
+        // single slab stage: refilled only after the commit below.  The first weight stage of the chunk is waited for HERE too, not
+        // before the previous chunk's last block: a CTA pair's relay warp forwards "slab full" before "weights full" of a chunk,
+        // and the slab of chunk c only refills after chunk c-1 is committed - pre-waiting the weights would close a cycle
+        if (SA == 1 && c > 0) { wait_a(0, aph); wait_b(bst, bph); }
         const uint32_t a_st_lo = a_lo0 + (uint32_t)ast * a_stage_u;
         const uint32_t keep_mask = (c == 0) ? 0u : 1u;          // chunk 0: the first MMA of an accumulator overwrites
         const int nast = (ast + 1 == SA) ? 0 : ast + 1;
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, V ? 2 : 1) conv_shiftgemm_kernel(con
           }
           // pre-wait what the next stage needs, then the last block of this stage
           if (s + 1 < spc) wait_b(nbst, nbph);
-          else if (c + 1 < nchunks) { if (SA > 1) wait_a(nast, naph); wait_b(nbst, nbph); }
+          else if (c + 1 < nchunks && SA > 1) { wait_a(nast, naph); wait_b(nbst, nbph); }
           if (mrep == 1) issue(std::false_type{}); else issue(std::true_type{});
           if (leader) { if (PAIR) umma2_commit(&b_empty[bst]); else umma_commit(&b_empty[bst]); }
           bst = nbst; bph = nbph;
@@ -1245,8 +1248,11 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
     // reads of the last tile run past the image into the tail slack of the buffer
     while (mmax > 1 && (int64_t)(mmax - 1) * K.Wrow + 2 * kTileM > kActSlackUnits) --mmax;
     // experiment: NHVR_CONV_PAIR=2 also pairs M-replicated layers (N >= 64): each CTA then reads A + B/2 per MMA
+    // Split precision: on by default (N >= 64) - the weight stream per MMA pair is twice as long there: UV head 2.51 -> 2.34 ms,
+    // stride-2 64 -> 128 278 -> 268 us (fp16: +2 % on the UV head, -3...-10 % on stems and stride-2 layers, so opt-in there).
     { const char* pe = std::getenv("NHVR_CONV_PAIR");
-      pair = (pe && std::atoi(pe) == 2 && nacc == 1 && Npad >= 64 && (Npad % 16) == 0) ? 1 : 0; }
+      const bool want = pe ? std::atoi(pe) == 2 : split3;
+      pair = (want && nacc == 1 && Npad >= 64 && (Npad % 16) == 0) ? 1 : 0; }
     for (int m = mmax; m >= 2 && !ok; --m) {
       const int xt = (K.Wv + kTileM - 1) / kTileM;
       const bool prefer_stk = d->kind != NHVR_CONV_DGRAD_S1 && xt * kTileM * 10 <= K.Wv * 11;
@@ -1285,8 +1291,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
       const char* pe = std::getenv("NHVR_CONV_PAIR");
       const bool eligible = nacc == 1 && !rowmode && !(d->flags & 1) && Npad >= 96 && (Npad % 16) == 0;
       // split precision: also at N = 256 (the weight stream is twice as long per MMA block pair: 435 -> 419 us per 256 -> 256 layer)
-      // (stride-1 layers only; see the single-slab-stage guard below)
-      const int pair_max = (split3 && d->kind == NHVR_CONV && d->stride == 1) ? 256 : 192;
+      const int pair_max = split3 ? 256 : 192;
       pair = eligible && (pe ? std::atoi(pe) != 0 : (Npad > 128 && Npad <= pair_max)) ? 1 : 0;
     }
     // flag bit 5 (fused InstanceNorm epilogue): shrink the tile step so that an image has exactly one tile per SM (148) -
@@ -1311,15 +1316,6 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
     if (!ok) ok = try_fit(kSmemOnePerSm);
     if (!ok) { delete p; return NHVR_ERR_SMEM; }
   }
-  // A CTA pair with a SINGLE slab stage (possible in split precision only) traps on the GPU (measured: stride-2 256-channel
-  // and M-replicated split-precision layers under NHVR_CONV_PAIR; cause not found) - such plans fall back to single CTAs.
-  if (pair && SA == 1) {
-    pair = 0;
-    bool refit = K.tmem_cols <= 256 && try_fit(kSmemTwoPerSm);
-    if (!refit) refit = try_fit(kSmemOnePerSm);
-    if (!refit) { delete p; return NHVR_ERR_SMEM; }
-  }
-
   // ---- jobs (grouped by accumulator so that "first" is well defined)
   std::vector<Tap> staps = taps;
   std::stable_sort(staps.begin(), staps.end(), [](const Tap& a, const Tap& b) { return a.acc < b.acc; });
