@@ -728,3 +728,15 @@ def test_native_adam_matches_torch(cuda_dev):
         y1, y1_ref = net(x), ref(x)
     assert (y1 - y0).abs().max().item() > 1e-5                     # the inference engine picked the new weights up
     assert (y1 - y1_ref).abs().max().item() <= 2e-2
+
+
+@pytest.mark.parametrize("N,C,H,W", [(2, 4, 37, 53), (1, 73, 40, 24), (3, 1, 66, 66), (8, 4, 512, 512)])
+def test_bias_grad_chunked(cuda_dev, N, C, H, W):
+    """nhvr_bias_grad over (channel, chunk) blocks: odd plane sizes (chunk starts that are not 16-byte aligned take the scalar
+    path), a single channel, and the RGB + mask head's shape."""
+    from nhvr_b200 import ops
+    g = torch.Generator().manual_seed(N * 100 + C)
+    x = torch.randn(N, C, H, W, generator=g).to(cuda_dev)
+    db = ops.bias_grad(x, 0.5)
+    ref = x.double().sum((0, 2, 3)) * 0.5
+    assert torch.allclose(db.double(), ref, rtol=1e-5, atol=1e-3 * (N * H * W) ** 0.5 * 1e-2)
