@@ -140,6 +140,14 @@ double nhvr_conv_flops(const nhvr_conv_plan* p);     /* algorithmic 2*k*k*Cin*Co
 int nhvr_conv_plan_info(const nhvr_conv_plan* p, int32_t* info, int32_t n);
 /* w: fp32, Conv2d layout [Cout][Cin][kh][kw] or ConvTranspose2d layout [Cin][Cout][kh][kw]. */
 int nhvr_conv_pack_weights(const nhvr_conv_plan* p, const float* w, void* packed, void* stream);
+/* The same packing for MANY layers in one launch (a training step re-packs every weight of every network after each optimiser
+ * update).  nhvr_conv_pack_record_fill writes one layer's record (nhvr_conv_pack_record_bytes() bytes, HOST memory; *units = the
+ * layer's packed 16-byte units) for the device pointers w / packed; the caller concatenates the records, copies them to the
+ * device once and calls nhvr_conv_pack_weights_batched(records, n, max units over the layers) whenever the weights changed.
+ * Not for split-precision plans (NHVR_ERR_UNSUPPORTED: their pack needs max|w| first). */
+size_t nhvr_conv_pack_record_bytes(void);
+int nhvr_conv_pack_record_fill(const nhvr_conv_plan* p, const float* w, void* packed, void* record_host, int64_t* units);
+int nhvr_conv_pack_weights_batched(const void* records_dev, int32_t n, int64_t max_units, void* stream);
 /* out / stats / bias meaning depends on the plan's epilogue:
  *  RAW_STATS    : out = P8 [N][Cout8][Ho][Wo] (no halo, Cout8 = ceil(Cout/8) rounded up to even); stats = double [N][Cout8*8][4]
  *                 = {sum (x-s), sum (x-s)^2, s, unused} per channel over H*W, zeroed by the caller (s = 0: plain sums) and

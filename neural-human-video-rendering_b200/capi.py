@@ -67,6 +67,9 @@ SYMBOLS = {
     "nhvr_conv_flops": (C.c_double, [_P]),
     "nhvr_conv_plan_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_int32]),
     "nhvr_conv_pack_weights": (C.c_int, [_P, _P, _P, _P]),
+    "nhvr_conv_pack_record_bytes": (C.c_size_t, []),
+    "nhvr_conv_pack_record_fill": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_int64)]),
+    "nhvr_conv_pack_weights_batched": (C.c_int, [_P, C.c_int32, C.c_int64, _P]),
     "nhvr_conv_forward": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(ActDesc), _P, _P]),
     "nhvr_conv_in_fused_supported": (C.c_int, [_P]),
     "nhvr_conv_forward_in_fused": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int32, _P, C.POINTER(ActDesc), _P, C.POINTER(ActDesc),

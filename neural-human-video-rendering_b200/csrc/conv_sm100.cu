@@ -863,7 +863,7 @@ __global__ void conv_weight_absmax_kernel(const float* __restrict__ w, int64_t n
   if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(out, __float_as_uint(m));
 }
 
-__global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
+NHVR_DEVINL void conv_pack_weights_body(const PackParams& P, int64_t u0, int64_t ustride) {
   const int64_t total = (int64_t)P.nsplit * P.nblocks_padded * 2 * P.Npad;
   // split precision: the lo parts of N(0, 0.02)-sized weights would be fp16 subnormals (18-19 significant bits instead
   // of 22), so the whole tensor is scaled by a power of two that puts max|w| into [8192, 16384); the conv epilogue
@@ -873,13 +873,13 @@ __global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
     const float amax = __uint_as_float(*reinterpret_cast<const uint32_t*>(P.tail));
     const int sh = amax > 0.f ? 13 - ilogbf(amax) : 0;
     wscale = ldexpf(1.f, sh);
-    if (blockIdx.x == 0 && threadIdx.x == 0) P.tail[1] = ldexpf(1.f, -sh);
+    if (u0 == 0) P.tail[1] = ldexpf(1.f, -sh);
   }
   // weight blocks per (chunk, tap): kcp/2 plane pairs; split precision: 2 per group of four physical planes - w_hi (feeds the
   // x_hi and the x_lo MMA) and w_lo (feeds x_hi)
   const int qsteps = P.kfold ? 1 : (P.split3 ? 2 * (P.kcp >> 2) : P.kcp >> 1);
   const int nblocks = P.nchunks * P.njobs * qsteps;
-  for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t u = u0; u < total; u += ustride) {
     const int nrow = (int)(u % P.Npad);
     int64_t t = u / P.Npad;
     const int kp = (int)(t & 1); t >>= 1;
@@ -937,6 +937,18 @@ __global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
     }
     P.dst[du] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
   }
+}
+
+__global__ void conv_pack_weights_kernel(const __grid_constant__ PackParams P) {
+  conv_pack_weights_body(P, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+}
+
+// every layer of a network in ONE launch (blockIdx.y = layer; parameter records in device memory): a training step re-packs all
+// weights of all networks for the forward and the dgrad convs after every optimiser update - 216 launches of ~6 us each
+// (profiles/r02b_ncu_launches_train.csv) otherwise
+__global__ void conv_pack_weights_batched_kernel(const PackParams* __restrict__ arr) {
+  const PackParams& P = arr[blockIdx.y];
+  conv_pack_weights_body(P, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 
 }  // namespace nhvr
@@ -1527,6 +1539,34 @@ static void conv_launch_traced(const nhvr_conv_plan* p, ConvKParams& K, int vari
       std::fprintf(stderr, "[cta] %zu img=%zu sm=%lld start=%.1f acc_full=%.1f end=%.1f\n", i, i / grid.x % grid.y, h[i * 16 + 8], (h[i * 16 + 9] - tmin) / 1900.0,
                    (h[i * 16 + 9] - tmin + h[i * 16 + 4]) / 1900.0, (h[i * 16 + 9] - tmin + h[i * 16 + 5]) / 1900.0);
   }
+}
+
+extern "C" size_t nhvr_conv_pack_record_bytes(void) { return sizeof(PackParams); }
+
+extern "C" int nhvr_conv_pack_record_fill(const nhvr_conv_plan* p, const float* w, void* packed, void* record_host, int64_t* units) {
+  if (!p || !w || !packed || !record_host) return NHVR_ERR_NULL;
+  if (((uintptr_t)packed & 15) != 0) return NHVR_ERR_ALIGN;
+  if (p->pp.split3) return NHVR_ERR_UNSUPPORTED;          // the split-precision pack needs the |w| maximum first: per-layer call
+  PackParams PP = p->pp;
+  PP.w = w;
+  PP.f16 = operand_f16();
+  PP.dst = reinterpret_cast<uint4*>(packed);
+  PP.tail = nullptr;
+  std::memcpy(record_host, &PP, sizeof(PP));
+  if (units) *units = (int64_t)PP.nsplit * PP.nblocks_padded * 2 * PP.Npad;
+  return NHVR_OK;
+}
+
+extern "C" int nhvr_conv_pack_weights_batched(const void* records_dev, int32_t n, int64_t max_units, void* stream) {
+  if (!records_dev) return NHVR_ERR_NULL;
+  if (n <= 0 || max_units <= 0) return NHVR_ERR_SHAPE;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((max_units + 255) / 256, 148 * 8 / std::max(1, std::min(n, 8))));
+  conv_pack_weights_batched_kernel<<<dim3(blocks, n), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const PackParams*>(records_dev));
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
+  return NHVR_OK;
 }
 
 extern "C" int nhvr_conv_forward(const nhvr_conv_plan* p, const void* in, const void* packed_w, const float* bias,

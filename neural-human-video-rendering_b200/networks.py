@@ -176,8 +176,7 @@ class _ChainEngine:
         return bool(L0.get("norm", True)) and not p0.transposed and p0.cin <= 32 and len(chain) > 1
 
     def pack_weights(self) -> None:
-        for L, plan in zip(self.chain, self.plans):
-            plan.pack_weights(L["params"].weight)
+        self._pack_batch = ops.pack_weights_all(self.plans, [L["params"].weight for L in self.chain], getattr(self, "_pack_batch", None))
         if self._centres_stem(self.chain):                       # the stem's filter summed over its taps (ops.stem_stat_shift)
             w0 = self.chain[0]["params"].weight.detach().float().sum((2, 3)).contiguous()
             if getattr(self, "_wsum", None) is None:
@@ -293,8 +292,7 @@ class _ChainEngine:
         extra_grads = {k: v for k, v in (extra_grads or {}).items() if v is not None}
         ver = tuple((Lr["params"].weight._version, getattr(Lr["params"], "ext_version", 0)) for Lr in self.chain)
         if ver != self._bwd_versions:                       # dgrad convs read the same weights, differently packed
-            for Lr, dp in zip(self.chain, B["dplans"]):
-                dp.pack_weights(Lr["params"].weight)
+            B["pack_batch"] = ops.pack_weights_all(B["dplans"], [Lr["params"].weight for Lr in self.chain], B.get("pack_batch"))
             self._bwd_versions = ver
         L = len(self.plans)
         if grad_out is None:

@@ -195,6 +195,51 @@ class ConvPlan:
                   "nhvr_conv_forward_in_fused")
 
 
+class PackBatch:
+    """All conv weights of a network packed by ONE launch (nhvr_conv_pack_weights_batched).  Built for a fixed set of
+    (plan, fp32 weight) pairs: the per-layer records hold raw device pointers, so the batch is valid as long as the weights'
+    data_ptr() do not change (train.ParamBucket keeps parameters in one flat buffer that Adam updates in place)."""
+
+    def __init__(self, plans: Sequence["ConvPlan"], weights: Sequence[torch.Tensor]):
+        lib = load()
+        rb = lib.nhvr_conv_pack_record_bytes()
+        host = (C.c_uint8 * (rb * len(plans)))()
+        self.ptrs = tuple(w.data_ptr() for w in weights)
+        self.max_units = 0
+        for i, (plan, w) in enumerate(zip(plans, weights)):
+            assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+            if plan.packed is None:
+                plan.packed = torch.empty(plan.weight_bytes, dtype=torch.uint8, device=w.device)
+            units = C.c_int64()
+            check(lib.nhvr_conv_pack_record_fill(plan.handle, w.data_ptr(), plan.packed.data_ptr(), C.byref(host, i * rb), C.byref(units)),
+                  "nhvr_conv_pack_record_fill")
+            self.max_units = max(self.max_units, units.value)
+        self.n = len(plans)
+        self.records = torch.frombuffer(bytearray(host), dtype=torch.uint8).to(weights[0].device)
+
+    def valid_for(self, weights: Sequence[torch.Tensor]) -> bool:
+        return self.ptrs == tuple(w.data_ptr() for w in weights)
+
+    def run(self) -> None:
+        check(load().nhvr_conv_pack_weights_batched(self.records.data_ptr(), self.n, self.max_units, stream_ptr()),
+              "nhvr_conv_pack_weights_batched")
+
+
+def pack_weights_all(plans: Sequence["ConvPlan"], weights: Sequence[torch.Tensor], cache: Optional["PackBatch"]) -> Optional["PackBatch"]:
+    """Pack every layer: one launch when the plans allow it (plain 16-bit operands, contiguous fp32 CUDA weights), else layer by layer.
+    Returns the batch to cache (None when the per-layer path was taken)."""
+    ws = [w.detach() for w in weights]
+    batchable = all((not pl.split3) for pl in plans) and all(w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() for w in ws)
+    if not batchable or __import__("os").environ.get("NHVR_PACK_BATCH") == "0":
+        for pl, w in zip(plans, ws):
+            pl.pack_weights(w)
+        return None
+    if cache is None or not cache.valid_for(ws) or cache.n != len(plans):
+        cache = PackBatch(plans, ws)
+    cache.run()
+    return cache
+
+
 class WgradPlan:
     """Weight-gradient plan of one forward conv (nhvr_wgrad_*): dW from the forward's P8 input and the output
     gradient stored in ``g_desc`` (which the matching dgrad conv also reads)."""
