@@ -314,6 +314,10 @@ int nhvr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
 /* AvgPool2d(3, stride 2, padding 1, count_include_pad=False) between discriminator scales (pix2pixHD
  * MultiscaleDiscriminator.downsample): in float [N][C][H][W] -> out float [N][C][(H+1)/2][(W+1)/2]. */
 int nhvr_avgpool3s2(const float* in, int32_t N, int32_t C, int32_t H, int32_t W, float* out, void* stream);
+/* nn.MaxPool2d(2, 2) between the VGG19 stages of the perceptual loss (pix2pixHD VGGLoss, on unless --no_vgg_loss; README.md:101).
+ * fp32 NCHW, output floor(H/2) x floor(W/2); the backward routes to the first maximum of each window (torch semantics). */
+int nhvr_maxpool2(const float* in, int32_t N, int32_t C, int32_t H, int32_t W, float* out, void* stream);
+int nhvr_maxpool2_bwd(const float* in, const float* grad_out, int32_t N, int32_t C, int32_t H, int32_t W, float* grad_in, void* stream);
 
 #ifdef __cplusplus
 }

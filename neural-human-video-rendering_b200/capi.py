@@ -103,6 +103,8 @@ SYMBOLS = {
     "nhvr_loss_temporal_bwd": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P]),
     "nhvr_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _P]),
     "nhvr_avgpool3s2": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "nhvr_maxpool2": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "nhvr_maxpool2_bwd": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
 }
 
 # fp16 operands are the default: measured on B200 at 512^2 against the fp32 oracle the temporal generator is

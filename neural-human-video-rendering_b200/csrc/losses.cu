@@ -322,6 +322,59 @@ extern "C" int nhvr_loss_pair_bwd(const float* a, const float* b, int64_t n, int
   loss_pair_bwd_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(a, b, n, mode, target, coef, grad_scale, accumulate, grad_a);
   NHVR_POST_LAUNCH();
 }
+// MaxPool2d(2, 2) of the VGG19 feature stack (the reference's perceptual loss, pix2pixHD VGGLoss; README.md:101).  fp32 NCHW, floor
+// output size; the backward routes each output gradient to the FIRST maximum of its window in row-major order (torch semantics).
+namespace nhvr {
+__global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__ in, int64_t planes, int H, int W, int Ho, int Wo,
+                                                       float* __restrict__ out) {
+  const int64_t total = planes * Ho * Wo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int xo = (int)(i % Wo), yo = (int)((i / Wo) % Ho);
+    const int64_t pl = i / ((int64_t)Wo * Ho);
+    const float* p = in + (pl * H + 2 * yo) * W + 2 * xo;
+    out[i] = fmaxf(fmaxf(p[0], p[1]), fmaxf(p[W], p[W + 1]));
+  }
+}
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const float* __restrict__ in, const float* __restrict__ gout, int64_t planes, int H,
+                                                           int W, int Ho, int Wo, float* __restrict__ gin) {
+  const int64_t total = planes * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const int64_t pl = i / ((int64_t)W * H);
+    const int yo = y >> 1, xo = x >> 1;
+    float g = 0.f;
+    if (yo < Ho && xo < Wo) {
+      const float* p = in + (pl * H + 2 * yo) * W + 2 * xo;
+      const float v[4] = {p[0], p[1], p[W], p[W + 1]};
+      int best = 0;
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (v[k] > v[best]) best = k;
+      if (best == ((y & 1) << 1 | (x & 1))) g = gout[(pl * Ho + yo) * Wo + xo];
+    }
+    gin[i] = g;
+  }
+}
+}  // namespace nhvr
+
+extern "C" int nhvr_maxpool2(const float* in, int32_t N, int32_t C, int32_t H, int32_t W, float* out, void* stream) {
+  if (!in || !out) return NHVR_ERR_NULL;
+  if (N <= 0 || C <= 0 || H < 2 || W < 2) return NHVR_ERR_SHAPE;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  const int Ho = H / 2, Wo = W / 2;
+  maxpool2_kernel<<<blocks_for((int64_t)N * C * Ho * Wo), 256, 0, (cudaStream_t)stream>>>(in, (int64_t)N * C, H, W, Ho, Wo, out);
+  NHVR_POST_LAUNCH();
+}
+extern "C" int nhvr_maxpool2_bwd(const float* in, const float* grad_out, int32_t N, int32_t C, int32_t H, int32_t W, float* grad_in,
+                                 void* stream) {
+  if (!in || !grad_out || !grad_in) return NHVR_ERR_NULL;
+  if (N <= 0 || C <= 0 || H < 2 || W < 2) return NHVR_ERR_SHAPE;
+  if (!arch_ok_cached()) return NHVR_ERR_ARCH;
+  const int Ho = H / 2, Wo = W / 2;
+  maxpool2_bwd_kernel<<<blocks_for((int64_t)N * C * H * W), 256, 0, (cudaStream_t)stream>>>(in, grad_out, (int64_t)N * C, H, W, Ho, Wo, grad_in);
+  NHVR_POST_LAUNCH();
+}
+
 extern "C" int nhvr_avgpool3s2_bwd(const float* grad_out, int32_t N, int32_t C, int32_t H, int32_t W, int32_t accumulate, float* grad_in,
                                    void* stream) {
   if (!grad_out || !grad_in) return NHVR_ERR_NULL;

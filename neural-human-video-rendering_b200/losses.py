@@ -195,3 +195,19 @@ class _TemporalLoss(torch.autograd.Function):
 
 def temporal_diff(out_t, out_prev, flow_inv, coef: float = 1.0):
     return _TemporalLoss.apply(out_t, out_prev.detach(), flow_inv, coef)
+
+
+VGG_WEIGHTS = (1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0)
+
+
+def vgg_diff(vgg, x: torch.Tensor, y: torch.Tensor, coef: float = 1.0):
+    """pix2pixHD ``VGGLoss``: sum_i w_i * L1(vgg(x)_i, vgg(y)_i.detach()), w = (1/32, 1/16, 1/8, 1/4, 1), gradient to x only
+    (networks.Vgg19B200; on unless --no_vgg_loss in the reference's training options)."""
+    fx = vgg(x)
+    with torch.no_grad():
+        fy = vgg(y.detach())
+    total = None
+    for w, a, b in zip(VGG_WEIGHTS, fx, fy):
+        t = l1_diff(a, b.detach(), coef * w)
+        total = t if total is None else total + t
+    return total

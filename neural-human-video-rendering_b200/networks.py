@@ -120,10 +120,12 @@ class _ChainEngine:
             # in_bufs[i] is written by the apply after conv i-1 (pack for i == 0): it must not be the live
             # residual source nor the buffer conv i-1 reads
             prev = self.in_bufs[-1] if self.in_bufs else None
-            chosen = None if train else next((b for b in pool if b is not live and b is not prev), None)
+            tapped = bool(chain[i].get("tap"))           # this layer's input is read back as a feature after the run: never reused
+            chosen = None if (train or tapped) else next((b for b in pool if b is not live and b is not prev), None)
             if chosen is None:
                 chosen = ops.P8Buffer(d.copy(), device)
-                pool.append(chosen)
+                if not tapped:
+                    pool.append(chosen)
             self.in_bufs.append(chosen)
             if i > 0 and chain[i - 1].get("res") == "add":
                 live = None                          # consumed by the apply that just wrote `chosen`
@@ -672,6 +674,100 @@ class MultiscaleDiscriminatorB200(nn.Module):
             if i != self.num_D - 1:
                 xd = [ops.avgpool3s2(t) for t in xd]
         return result
+
+
+
+# ----------------------------------------------------------------------------------------------
+# VGG19 feature stack of the perceptual loss (training side, optional)
+# ----------------------------------------------------------------------------------------------
+class Vgg19B200(nn.Module):
+    """The five feature taps of pix2pixHD's ``Vgg19`` (relu1_1, relu2_1, relu3_1, relu4_1, relu5_1 of torchvision
+    ``vgg19().features``) on the sm_100a conv kernels - the network behind ``VGGLoss``, which pix2pixHD (README.md:101: the
+    reference "borrows heavily" from it) adds to the generator objective unless ``--no_vgg_loss`` is given.
+    Parameter names equal torchvision's (``features.<idx>.weight``), so ``vgg19-*.pth`` loads unchanged; there is no ImageNet
+    checkpoint offline, the parity test uses random weights.  Frozen (requires_grad False): only input gradients are computed.
+
+    One conv chain per resolution (conv + bias + ReLU, zero padding, no norm), ``nhvr_maxpool2`` between them; a stage's first
+    activation is its feature tap (the chain engines expose the tensor that feeds conv 1)."""
+
+    STAGES = ((0, 2), (5, 7), (10, 12, 14, 16), (19, 21, 23, 25), (28,))
+    WIDTHS = {0: (3, 64), 2: (64, 64), 5: (64, 128), 7: (128, 128), 10: (128, 256), 12: (256, 256), 14: (256, 256), 16: (256, 256),
+              19: (256, 512), 21: (512, 512), 23: (512, 512), 25: (512, 512), 28: (512, 512)}
+
+    def __init__(self):
+        super().__init__()
+        mods: List[nn.Module] = []
+        for idx in range(30):
+            if idx in self.WIDTHS:
+                cin, cout = self.WIDTHS[idx]
+                m = _ConvParams(cin, cout, 3, pad=1)
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")    # torchvision's VGG init
+                nn.init.zeros_(m.bias)
+                mods.append(m)
+            else:
+                mods.append(_Slot("MaxPool2d(2, 2)" if idx in (4, 9, 18, 27) else "ReLU"))
+        self.features = nn.Sequential(*mods)
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self._engines: Dict[tuple, List[List[_ChainEngine]]] = {}
+
+    def _chain(self, stage: int) -> List[dict]:
+        # the activation that feeds a stage's SECOND conv is the stage's feature tap (relu<k>_1)
+        return [dict(params=self.features[i], halo=capi.HALO_ZERO, act=capi.ACT_RELU, res=None, norm=False, tap=(j == 1))
+                for j, i in enumerate(self.STAGES[stage])]
+
+    def _make_engines(self, N, H, W, dev, train) -> List[_ChainEngine]:
+        capi.require_device()
+        engs, h, w = [], H, W
+        for s in range(5):
+            cout = self.WIDTHS[self.STAGES[s][-1]][1]
+            engs.append(_ChainEngine(self._chain(s), N, h, w, dev, capi.ACT_RELU, cout, train=train))
+            h, w = h // 2, w // 2
+        return engs
+
+    def _stage_engines(self, N, H, W, dev, train) -> List[_ChainEngine]:
+        key = (N, H, W, dev.index, train)
+        pool = self._engines.setdefault(key, [])
+        if train:
+            engs = next((e for e in pool if not any(x.busy for x in e)), None)
+            if engs is None:
+                if len(pool) >= 4:
+                    raise NhvrError("more than 4 forward passes of the VGG stack are waiting for backward")
+                engs = self._make_engines(N, H, W, dev, True)
+                pool.append(engs)
+            for e in engs:
+                e.busy = True
+            return engs
+        if not pool:
+            pool.append(self._make_engines(N, H, W, dev, False))
+        return pool[0]
+
+    def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
+        x = x.contiguous().float()
+        if not x.is_cuda:
+            raise NhvrError("nhvr_b200 modules take CUDA tensors only (no CPU fallback)")
+        N, Cc, H, W = x.shape
+        if Cc != 3 or H < 16 or W < 16:
+            raise NhvrError("Vgg19B200 takes [N, 3, H >= 16, W >= 16] images, got %s" % (tuple(x.shape),))
+        train = torch.is_grad_enabled() and x.requires_grad
+        engs = self._stage_engines(N, H, W, x.device, train)
+        feats, h = [], x
+        for s, eng in enumerate(engs):
+            eng.maybe_repack()
+            n_feats = 1 if len(eng.plans) > 1 else 0
+            if train:
+                params = []
+                for Lr in eng.chain:
+                    params += [Lr["params"].weight, Lr["params"].bias]
+                outs = _ChainFunction.apply(eng, 1, n_feats, h, *params)
+                feat, out = (outs[0], outs[1]) if n_feats else (outs, outs)
+            else:
+                out = eng.run([h]).clone()
+                feat = eng.feature(1) if n_feats else out
+            feats.append(feat)
+            if s < 4:
+                h = ops.maxpool2(out)
+        return feats
 
 
 def define_D(input_nc, ndf, n_layers_D, norm="instance", use_sigmoid=False, num_D=1, getIntermFeat=False,

@@ -313,6 +313,32 @@ def avgpool3s2(x: torch.Tensor) -> torch.Tensor:
     return _AvgPoolFn.apply(x)
 
 
+class _MaxPool2Fn(torch.autograd.Function):
+    """MaxPool2d(2, 2) between the VGG19 stages (perceptual loss), forward and backward native."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous().float()
+        N, Cc, H, W = x.shape
+        out = torch.empty(N, Cc, H // 2, W // 2, dtype=torch.float32, device=x.device)
+        check(load().nhvr_maxpool2(x.data_ptr(), N, Cc, H, W, out.data_ptr(), stream_ptr()), "nhvr_maxpool2")
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        N, Cc, H, W = x.shape
+        g = g.contiguous().float()
+        gin = torch.empty_like(x)
+        check(load().nhvr_maxpool2_bwd(x.data_ptr(), g.data_ptr(), N, Cc, H, W, gin.data_ptr(), stream_ptr()), "nhvr_maxpool2_bwd")
+        return gin
+
+
+def maxpool2(x: torch.Tensor) -> torch.Tensor:
+    return _MaxPool2Fn.apply(x)
+
+
 def fold_unpack(dx: P8Buffer, pad_t: int, pad_l: int, reflect: bool, N: int, C8: int, H: int, W: int, channels: int,
                 scale: float) -> torch.Tensor:
     out = torch.empty(N, channels, H, W, dtype=torch.float32, device=dx.mem.device)

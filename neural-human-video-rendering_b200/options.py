@@ -172,6 +172,8 @@ class TrainOptions(BaseOptions):
         p.add_argument("--lambda_feat", type=float, default=10.0)
         p.add_argument("--no_ganFeat_loss", action="store_true")
         p.add_argument("--no_vgg_loss", action="store_true")
+        p.add_argument("--vgg_weights", type=str, default="",
+                       help="torchvision vgg19 state_dict (features.<idx>.*); without it the perceptual loss is skipped (no ImageNet weights offline)")
         p.add_argument("--no_lsgan", action="store_true")
         p.add_argument("--pool_size", type=int, default=0)
         p.add_argument("--lambda_L2", type=float, default=500.0, help="[REF pretrain_start.sh:31]")

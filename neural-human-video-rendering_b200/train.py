@@ -165,8 +165,10 @@ class RenderTrainer:
     """
 
     def __init__(self, pipe, netD, lr=2e-4, beta1=0.5, lambda_feat=10.0, lambda_l2=500.0, lambda_uv=1000.0, lambda_prob=10.0,
-                 lambda_temp=500.0, n_layers_D=3, num_D=2, distributed=False):
-        self.pipe, self.netD = pipe, netD
+                 lambda_temp=500.0, n_layers_D=3, num_D=2, distributed=False, vgg=None):
+        """vgg: a networks.Vgg19B200 (with ImageNet weights loaded) adds pix2pixHD's lambda_feat * VGGLoss(fake, real) to the generator
+        objective; None = --no_vgg_loss (the offline default: there is no ImageNet checkpoint to load)."""
+        self.pipe, self.netD, self.vgg = pipe, netD, vgg
         self.lam = dict(feat=lambda_feat, l2=lambda_l2, uv=lambda_uv, prob=lambda_prob, temp=lambda_temp)
         self.n_layers_D, self.num_D = n_layers_D, num_D
         # one flat bucket per network: its all-reduce starts when that network's backward ends and overlaps the rest
@@ -212,6 +214,8 @@ class RenderTrainer:
                   + losses.mse_diff(fake, real1, lam["l2"])
                   + losses.uv_prob_objective(r1["uvp"], batch["dp_i"], batch["dp_uv"], lam["uv"], lam["prob"])
                   + losses.temporal_diff(fake, r0["out"], batch["flow_inv"], lam["temp"]))
+        if self.vgg is not None:
+            loss_G = loss_G + losses.vgg_diff(self.vgg, fake, real1, lam["feat"])
         # ---- generator side (the discriminator's weights are frozen under loss_G: its backward yields input grads only)
         for b in self.buckets_G.values():
             b.zero_grad()

@@ -72,3 +72,10 @@ def flow_warp(img: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
 def temporal_loss(out_t: torch.Tensor, out_prev: torch.Tensor, flow_inv: torch.Tensor) -> torch.Tensor:
     """--lambda_Temp: L1(out_t - warp(out_{t-1}, flow_inv_t)) [REF pretrain_start.sh:21-22,37; SPEC D11]."""
     return F.l1_loss(out_t, flow_warp(out_prev, flow_inv))
+
+
+def vgg_loss(vgg, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """pix2pixHD ``VGGLoss``: sum_i w_i * L1(vgg(x)_i, vgg(y)_i.detach()), w = (1/32, 1/16, 1/8, 1/4, 1) [UPSTREAM models/networks.py]."""
+    w = (1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0)
+    fx, fy = vgg(x), vgg(y)
+    return sum(wi * torch.nn.functional.l1_loss(a, b.detach()) for wi, a, b in zip(w, fx, fy))

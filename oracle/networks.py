@@ -217,3 +217,35 @@ def define_D(input_nc: int, ndf: int, n_layers_D: int, norm: str = "instance", u
     net = MultiscaleDiscriminator(input_nc, ndf, n_layers_D, norm_layer, use_sigmoid, num_D, getIntermFeat)
     net.apply(weights_init)
     return net
+
+
+class Vgg19(nn.Module):
+    """pix2pixHD ``Vgg19``: torchvision ``vgg19().features`` cut into the five slices that end at relu1_1, relu2_1, relu3_1,
+    relu4_1, relu5_1 [UPSTREAM models/networks.py Vgg19; torchvision is not needed: the stack is 13 Conv2d(3x3, padding 1) + ReLU and
+    4 MaxPool2d(2, 2), parameter names ``features.<idx>``].  Weights: whatever the caller loads (random in the parity test)."""
+
+    CFG = (64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512)
+    CUTS = (2, 7, 12, 21, 30)
+
+    def __init__(self):
+        super().__init__()
+        layers, cin = [], 3
+        for v in self.CFG:
+            if v == "M":
+                layers.append(nn.MaxPool2d(2, 2))
+            else:
+                layers += [nn.Conv2d(cin, v, 3, padding=1), nn.ReLU(inplace=False)]
+                cin = v
+        self.features = nn.Sequential(*layers)
+        for m in self.features:
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+                nn.init.zeros_(m.bias)
+
+    def forward(self, x):
+        feats, lo = [], 0
+        for hi in self.CUTS:
+            x = self.features[lo:hi](x)
+            feats.append(x)
+            lo = hi
+        return feats

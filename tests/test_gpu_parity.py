@@ -740,3 +740,42 @@ def test_bias_grad_chunked(cuda_dev, N, C, H, W):
     db = ops.bias_grad(x, 0.5)
     ref = x.double().sum((0, 2, 3)) * 0.5
     assert torch.allclose(db.double(), ref, rtol=1e-5, atol=1e-3 * (N * H * W) ** 0.5 * 1e-2)
+
+
+def test_vgg19_features_and_perceptual_loss(cuda_dev):
+    """pix2pixHD's VGGLoss (on unless --no_vgg_loss): the five VGG19 feature taps, the weighted L1 loss and its gradient with
+    respect to the generated image, random weights on both sides (there is no ImageNet checkpoint offline)."""
+    from nhvr_b200 import capi, losses as L
+    from nhvr_b200.networks import Vgg19B200
+    from oracle.networks import Vgg19
+    from oracle.losses import vgg_loss
+    prev = capi.operand_dtype()
+    capi.set_operand_dtype("f16")
+    try:
+        torch.manual_seed(5)
+        ref = Vgg19().to(cuda_dev).eval()
+        net = Vgg19B200().to(cuda_dev)
+        net.load_state_dict(ref.state_dict())
+        x = (torch.rand(2, 3, 64, 96, device=cuda_dev) * 2 - 1).requires_grad_(True)
+        y = torch.rand(2, 3, 64, 96, device=cuda_dev) * 2 - 1
+        with torch.no_grad():
+            fa, fb = net(x.detach()), ref(x.detach())
+        for a, b in zip(fa, fb):
+            assert a.shape == b.shape
+            assert (a - b).abs().max().item() <= 2e-2 * max(1.0, b.abs().max().item()), (a.shape, (a - b).abs().max().item(), b.abs().max().item())
+        loss = L.vgg_diff(net, x, y, 10.0)
+        loss.backward()
+        xr = x.detach().clone().requires_grad_(True)
+        loss_r = 10.0 * vgg_loss(ref, xr, y)
+        loss_r.backward()
+        assert abs(loss.item() - loss_r.item()) <= 1e-2 * abs(loss_r.item()), (loss.item(), loss_r.item())
+        cos = torch.nn.functional.cosine_similarity(x.grad.flatten().double(), xr.grad.flatten().double(), dim=0).item()
+        rel = ((x.grad - xr.grad).double().norm() / xr.grad.double().norm()).item()
+        assert cos >= 0.99 and rel <= 0.15, (cos, rel)
+        # odd sizes: floor pooling
+        with torch.no_grad():
+            z = torch.rand(1, 3, 50, 38, device=cuda_dev)
+            for a, b in zip(net(z), ref(z)):
+                assert a.shape == b.shape and (a - b).abs().max().item() <= 2e-2 * max(1.0, b.abs().max().item())
+    finally:
+        capi.set_operand_dtype(prev)

@@ -56,9 +56,20 @@ def main(argv=None):
     if opt.continue_train:
         load_pipeline(pipe, os.path.join(opt.checkpoints_dir, opt.name), opt.which_epoch)
     netD = define_D(opt.pose_nc + 3, opt.ndf, opt.n_layers_D, "instance", False, opt.num_D, not opt.no_ganFeat_loss, gpu_ids=[local])
+    vgg = None
+    if not opt.no_vgg_loss:                      # pix2pixHD default: VGGLoss on; it needs the ImageNet vgg19 weights
+        if opt.vgg_weights and os.path.isfile(opt.vgg_weights):
+            from nhvr_b200.networks import Vgg19B200
+            vgg = Vgg19B200()
+            sd = torch.load(opt.vgg_weights, map_location="cpu")
+            vgg.load_state_dict({k: v for k, v in sd.items() if k.startswith("features.") and int(k.split(".")[1]) <= 28})
+            vgg = vgg.to(dev)
+            print("[train.py] perceptual loss: loaded", opt.vgg_weights)
+        else:
+            print("[train.py] perceptual (VGG) loss skipped: pass --vgg_weights <vgg19 state_dict> (no ImageNet weights offline)")
     trainer = RenderTrainer(pipe, netD, lr=opt.lr, beta1=opt.beta1, lambda_feat=opt.lambda_feat, lambda_l2=opt.lambda_L2,
                             lambda_uv=opt.lambda_UV, lambda_prob=opt.lambda_Prob, lambda_temp=opt.lambda_Temp,
-                            n_layers_D=opt.n_layers_D, num_D=opt.num_D, distributed=world > 1)
+                            n_layers_D=opt.n_layers_D, num_D=opt.num_D, distributed=world > 1, vgg=vgg)
     batch = synthetic_train_batch(opt.batchSize, opt.loadSize, dev, seed=rank)
     if opt.pose_nc > 3:
         z = torch.zeros(opt.batchSize, opt.pose_nc - 3, opt.loadSize, opt.loadSize, device=dev)
