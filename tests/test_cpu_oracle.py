@@ -187,3 +187,22 @@ def test_independent_numpy_restatement_agrees_with_the_torch_oracle(gold):
     assert p.shape == (2, 1, 9, 11) and p[0, 0, 0, 0] == x[0, 0, 2, 2] and p[0, 0, 8, 10] == x[0, 0, 2, 4]
     a = R.avgpool3s2(x)
     assert a.shape == (2, 1, 3, 4) and a[0, 0, 0, 0] == x[0, 0, :2, :2].mean() and a[0, 0, 2, 3] == x[0, 0, 3:5, 5:7].mean()
+
+
+def test_vgg19_oracle_and_module_share_torchvision_parameter_names():
+    """The perceptual-loss stack: five taps at /1, /2, /4, /8, /16 resolution; the B200 module holds the same ``features.<idx>`` keys
+    (a torchvision vgg19 checkpoint loads into both)."""
+    import torch
+    from oracle.networks import Vgg19
+    from oracle.losses import vgg_loss
+    from nhvr_b200.networks import Vgg19B200
+    torch.manual_seed(0)
+    ref = Vgg19().eval()
+    x = torch.rand(1, 3, 32, 48)
+    feats = ref(x)
+    assert [tuple(f.shape[1:]) for f in feats] == [(64, 32, 48), (128, 16, 24), (256, 8, 12), (512, 4, 6), (512, 2, 3)]
+    net = Vgg19B200()
+    assert sorted(net.state_dict().keys()) == sorted(ref.state_dict().keys())
+    net.load_state_dict(ref.state_dict())
+    assert not any(p.requires_grad for p in net.parameters())
+    assert float(vgg_loss(ref, x, x)) == 0.0 and float(vgg_loss(ref, x, torch.rand(1, 3, 32, 48))) > 0.0
