@@ -18,3 +18,12 @@ $NCU --set full --import-source on -k regex:conv_shiftgemm --launch-skip 21 --la
 $NCU --set full -k regex:in_apply_rows --launch-skip 1 --launch-count 1 -o $OUT/r02b_ncu_inapply_hilo_full -f python tools/ncu_step.py strict > /dev/null 2>&1
 $NCU --set full -k regex:texture_sample --launch-count 1 -o $OUT/r02b_ncu_sampler_full -f python tools/ncu_step.py strict > /dev/null 2>&1
 ls -la $OUT/*.ncu-rep $OUT/r02b_*.csv
+# per-launch step profiles (event-bracketed, un-graphed) and per-CTA cycle traces (NHVR_CONV_TRACE) behind the tables of DESIGN.md 5.1
+python tools/step_profile.py 8 split3 512 split3 > $OUT/r02b_step_profile_strict_c8.log 2>&1
+python tools/step_profile.py 8 f16 512 f16 > $OUT/r02b_step_profile_fast_c8.log 2>&1
+bash tools/fused_sweep.sh > $OUT/r02b_fused_sweep.log 2>&1
+bash tools/layer_traces.sh > $OUT/r02b_layer_traces.log 2>&1
+# training: launch lists of one end-to-end step and one UV pre-train step
+$NCU --metrics gpu__time_duration.sum --csv --log-file $OUT/r02b_ncu_launches_train.csv python tools/ncu_train_step.py > /dev/null 2>&1
+$NCU --metrics gpu__time_duration.sum --csv --log-file $OUT/r02b_ncu_launches_train_uv.csv python tools/ncu_train_step.py uv > /dev/null 2>&1
+# summaries are made on the CPU box: python tools/ncu_summarise.py launches|traffic ...
