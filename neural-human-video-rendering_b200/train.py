@@ -169,6 +169,7 @@ class RenderTrainer:
         """vgg: a networks.Vgg19B200 (with ImageNet weights loaded) adds pix2pixHD's lambda_feat * VGGLoss(fake, real) to the generator
         objective; None = --no_vgg_loss (the offline default: there is no ImageNet checkpoint to load)."""
         self.pipe, self.netD, self.vgg = pipe, netD, vgg
+        self.batch_d = __import__("os").environ.get("NHVR_BATCH_D", "1") != "0"
         self.lam = dict(feat=lambda_feat, l2=lambda_l2, uv=lambda_uv, prob=lambda_prob, temp=lambda_temp)
         self.n_layers_D, self.num_D = n_layers_D, num_D
         # one flat bucket per network: its all-reduce starts when that network's backward ends and overlaps the rest
@@ -188,7 +189,7 @@ class RenderTrainer:
         """The discriminator runs twice per scale under its own loss (fake detached, real): its bucket is complete after
         2 * num_D weight-gradient backwards."""
         self._d_backwards += 1
-        if self._d_backwards == 2 * self.num_D:
+        if self._d_backwards == (1 if self.batch_d else 2) * self.num_D:
             self.bucket_D.all_reduce_async()
 
     def step(self, batch: dict) -> dict:
@@ -201,8 +202,16 @@ class RenderTrainer:
         r1 = pipe.forward_train(pose1, r0["out"])
         fake = r1["out"]
         # ---- discriminator passes (no weight update in between)
-        pred_fake_d = D(pose1, fake.detach())
-        pred_real = D(pose1, real1)
+        if self.batch_d:
+            # fake (detached) and real through the discriminator as ONE batch of 2N: InstanceNorm is per sample, so the values are
+            # those of two separate passes, with half the launches and twice the tiles per launch
+            both = D(torch.cat([pose1, pose1], 0), torch.cat([fake.detach(), real1], 0))
+            n = fake.shape[0]
+            pred_fake_d = [[t[:n] for t in s] for s in both]
+            pred_real = [[t[n:] for t in s] for s in both]
+        else:
+            pred_fake_d = D(pose1, fake.detach())
+            pred_real = D(pose1, real1)
         loss_D = losses.lsgan_diff(pred_fake_d, False, 0.5) + losses.lsgan_diff(pred_real, True, 0.5)
         for p in D.parameters():
             p.requires_grad_(False)
