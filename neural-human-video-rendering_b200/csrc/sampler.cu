@@ -220,8 +220,8 @@ namespace nhvr {
 //   d tex_c / d U_k     = P_k * ds_kc/dfx * (S-1)/2 * [0 <= U/2+1/2 <= 1]          (same for V)
 //   d tex_c / d T_k[corner] = P_k * w_corner
 // Atlas gradient: vector reductions into a channels-last fp32 buffer [24][S][S][4G] (zeroed by the caller).
-template <int G>
-__global__ void __launch_bounds__(128) texture_sample_bwd_kernel(const float* __restrict__ uvp, const float4* __restrict__ atlas,
+template <int G, int MINB>
+__global__ void __launch_bounds__(128, MINB) texture_sample_bwd_kernel(const float* __restrict__ uvp, const float4* __restrict__ atlas,
                                                                  const float* __restrict__ gtex, int N, int H, int W, int S, int Ctex,
                                                                  int use_mask, float* __restrict__ guvp, float* __restrict__ gatlas) {
   const int64_t HW = (int64_t)H * W;
@@ -351,9 +351,16 @@ extern "C" int nhvr_texture_sample_bwd(const float* uvp, const float* atlas, con
   const int blocks = (int)std::min<int64_t>((total + 127) / 128, (int64_t)148 * 16 * 8);
   const float4* a4 = reinterpret_cast<const float4*>(atlas);
   cudaStream_t st = (cudaStream_t)stream;
-#define NHVR_LAUNCH_SBWD(GG) texture_sample_bwd_kernel<GG><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, use_mask_texture, grad_uvp, grad_atlas)
+#define NHVR_LAUNCH_SBWD(GG) texture_sample_bwd_kernel<GG, 1><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, use_mask_texture, grad_uvp, grad_atlas)
+  static int minb = -1;           // NHVR_SAMPLER_BWD_MINB = 3 (165 registers) | 4 (128, default) | 6 (80) | 8 (64): measured 1.56 / 1.46 / 1.71 / 1.85 ms at 8 x 512^2
+  if (minb < 0) { const char* e = std::getenv("NHVR_SAMPLER_BWD_MINB"); minb = e ? std::atoi(e) : 4; }
   switch (G) {
-    case 1: NHVR_LAUNCH_SBWD(1); break;
+    case 1:
+      if (minb >= 8) texture_sample_bwd_kernel<1, 8><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, use_mask_texture, grad_uvp, grad_atlas);
+      else if (minb >= 6) texture_sample_bwd_kernel<1, 6><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, use_mask_texture, grad_uvp, grad_atlas);
+      else if (minb >= 4) texture_sample_bwd_kernel<1, 4><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, use_mask_texture, grad_uvp, grad_atlas);
+      else texture_sample_bwd_kernel<1, 3><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, use_mask_texture, grad_uvp, grad_atlas);
+      break;
     case 2: NHVR_LAUNCH_SBWD(2); break;
     case 3: NHVR_LAUNCH_SBWD(3); break;
     case 4: NHVR_LAUNCH_SBWD(4); break;
