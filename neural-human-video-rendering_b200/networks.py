@@ -307,6 +307,12 @@ class _ChainEngine:
         dbs: List[Optional[torch.Tensor]] = [None] * L
         if need_weight_grad:
             dbs[L - 1] = ops.bias_grad(g_pre, inv_S)
+            b_last = self.chain[L - 1]["params"].bias
+            if getattr(b_last, "_nhvr_direct_grad", False) and b_last.grad is not None:
+                b_last.grad.add_(dbs[L - 1])                 # lands in the flat bucket now: the tail all-reduce below needs it
+                dbs[L - 1] = None
+        mid = L // 2 if (need_weight_grad and L >= 8 and getattr(self, "mid_backward", None) is not None
+                         and all(Lr.get("norm", True) for Lr in self.chain[L // 2:L - 1])) else -1
         ops.pack_nchw([g_pre], B["G"][L - 1])
         dWs: List[Optional[torch.Tensor]] = [None] * L
         dy_total: Dict[int, ops.P8Buffer] = {}
@@ -323,6 +329,10 @@ class _ChainEngine:
                     dW = torch.empty_like(wgt, dtype=torch.float32)
                     B["wplans"][i].run(self.in_bufs[i], B["G"][i], B["ws"], dW, inv_S)
                     dWs[i] = dW
+            if i == mid:
+                # every weight gradient of layers >= mid is in the bucket (their biases sit in front of an InstanceNorm: zero
+                # gradient, never written): reduce that half under the backward of the first half
+                self.mid_backward(2 * mid)
             if i == 0 and not need_input_grad:
                 break
             dX = B["dX"][i]
@@ -517,6 +527,7 @@ class GlobalGeneratorB200(nn.Module):
                 pool.append(eng)
             eng.busy = True
             eng.after_backward = getattr(self, "_after_backward", None)
+            eng.mid_backward = getattr(self, "_mid_backward", None)
             eng.maybe_repack()
             return eng
         key = (N, H, W, dev.index, train, self.precision)

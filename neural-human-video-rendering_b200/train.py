@@ -82,24 +82,44 @@ class ParamBucket:
             off += k
         self.lr, self.b1, self.b2, self.eps = lr, beta1, beta2, eps
         self.steps = 0
-        self.work = None
+        self.works: list = []
+        self._tail_from = None
         self.world = 1
         self.owners = [m for o in owners for m in o.modules()]
 
     def zero_grad(self) -> None:
         self.flat_g.zero_()
 
+    def _offset_of_param(self, index: int) -> int:
+        return sum(p.numel() for p in self.params[:index])
+
+    def all_reduce_tail_async(self, first_param: int, group=None) -> None:
+        """First of two buckets: the gradients of parameters[first_param:] are complete (the chain's backward has passed the layer
+        that owns them - networks._ChainEngine ``mid_backward`` hook) and are reduced under the rest of the backward."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1 or self._tail_from is not None:
+            return
+        off = self._offset_of_param(first_param)
+        if off <= 0 or off >= self.n:
+            return
+        self.world = dist.get_world_size(group)
+        self._tail_from = off
+        self.works.append(dist.all_reduce(self.flat_g[off:], op=dist.ReduceOp.SUM, group=group, async_op=True))
+
     def all_reduce_async(self, group=None) -> None:
+        """The bucket (or, after all_reduce_tail_async, its remaining head) - launched when the network's backward has finished."""
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
         self.world = dist.get_world_size(group)
-        self.work = dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        buf = self.flat_g if self._tail_from is None else self.flat_g[:self._tail_from]
+        self.works.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group, async_op=True))
 
     def wait(self) -> None:
-        if self.work is not None:
-            self.work.wait()
-            self.work = None
+        for w in self.works:
+            w.wait()
+        self.works = []
+        self._tail_from = None
 
     def adam_step(self) -> None:
         self.wait()
@@ -131,6 +151,7 @@ class UVPretrainer:
         self.distributed = distributed
         if distributed:
             self.net._after_backward = self.bucket.all_reduce_async
+            self.net._mid_backward = self.bucket.all_reduce_tail_async      # two buckets: the second half of the layers goes first
 
     def step(self, pose: torch.Tensor, dp_i: torch.Tensor, dp_uv: torch.Tensor) -> torch.Tensor:
         self.bucket.zero_grad()
@@ -183,6 +204,7 @@ class RenderTrainer:
         if distributed:
             for name in ("netG", "netBG", "netTransG"):
                 getattr(pipe, name)._after_backward = self.buckets_G[name].all_reduce_async
+                getattr(pipe, name)._mid_backward = self.buckets_G[name].all_reduce_tail_async
             netD._after_backward = self._d_backward_done
 
     def _d_backward_done(self) -> None:
