@@ -100,6 +100,102 @@ __global__ void __launch_bounds__(128, MINB) texture_sample_kernel(const float* 
   }
 }
 
+// ---- lean variant (Ctex <= 4, 73 * H * W < 2^31; the default there): the same arithmetic for part / texel, written for instruction count.
+// cuobjdump counts 2928 SASS instructions per pixel in the kernel above (1017 integer / address, 1027 fp32, 169 loads) against 304
+// bytes of algorithmic traffic.  Here 1640: one image per blockIdx.y, 32-bit element indices widened once per load,
+// u = fma.rn.sat(U, 0.5, 0.5) (one instruction; identical to clamp(0.5 * U + 0.5) because the product is exact), chained FMAs
+// for the blend, no .w channel for Ctex <= 3, the arg-max select chain and the texel select only when the indices are asked for
+// (IDX), the texel of the arg-max part recomputed once after the loop.
+// Measured (tools/sampler_bench.py, 8 x 512^2, us; profiles/r02c_sampler_lean.md): 44 % fewer instructions buy NOTHING where the lanes
+// of a warp scatter over the atlas (white-noise UV 561 vs 557, smooth UV 467 vs 467: the L1 wavefront queue is the limit, ncu
+// l1tex__data_pipe_lsu_wavefronts 81 %, ~13 lines per gather) and 21 % where they do not (98 % flat stick-figure UV: 229 vs 290);
+// occupancy matters more than instructions (same code at 80 / 96 registers: 264 / 308 us flat), so the 64-register build is the default.
+NHVR_DEVINL float fma_sat_half(float t) {
+  float r;
+  asm("fma.rn.sat.f32 %0, %1, 0f3F000000, 0f3F000000;" : "=f"(r) : "f"(t));
+  return r;
+}
+NHVR_DEVINL float ex2_approx(float t) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+  return r;
+}
+
+template <int NCH, bool IDX, int MINB>
+__global__ void __launch_bounds__(128, MINB) texture_sample_lean_kernel(const float* __restrict__ uvp, const float4* __restrict__ atlas,
+                                                                  int HW, int S, int Ctex, int use_mask, float* __restrict__ tex_out,
+                                                                  uint8_t* __restrict__ part_out, short2* __restrict__ texel_out) {
+  const int n = blockIdx.y;
+  const float* __restrict__ img = uvp + (size_t)n * 73u * (size_t)HW;
+  const float sm1 = (float)(S - 1);
+  const int SS = S * S;
+  for (int pix = blockIdx.x * 128 + threadIdx.x; pix < HW; pix += gridDim.x * 128) {
+    const float* __restrict__ base = img + pix;
+    float lg[25];
+#pragma unroll
+    for (int k = 0; k < 25; ++k) lg[k] = __ldg(base + (unsigned)(k * HW));
+    float mx = lg[0];
+    int part = 0;
+    if (IDX) {
+#pragma unroll
+      for (int k = 1; k < 25; ++k)
+        if (lg[k] > mx) { mx = lg[k]; part = k; }
+    } else {
+#pragma unroll
+      for (int k = 1; k < 25; ++k) mx = fmaxf(mx, lg[k]);
+    }
+    const float kLog2e = 1.4426950408889634f;
+    const float nmx = -mx * kLog2e;
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) { lg[k] = ex2_approx(fmaf(lg[k], kLog2e, nmx)); den += lg[k]; }
+    const float inv_den = 1.f / den;
+
+    float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+#pragma unroll
+    for (int k = 1; k <= kParts; ++k) {
+      const float u = fma_sat_half(__ldg(base + (unsigned)((24 + k) * HW)));
+      const float v = fma_sat_half(__ldg(base + (unsigned)((48 + k) * HW)));
+      const float fx = __fmul_rn(u, sm1), fy = __fmul_rn(v, sm1);
+      const float x0f = floorf(fx), y0f = floorf(fy);
+      const int x0 = (int)x0f, y0 = (int)y0f;
+      const int x1 = min(x0 + 1, S - 1), y1 = min(y0 + 1, S - 1);
+      const float wx = fx - x0f, wy = fy - y0f;
+      const float pk = lg[k] * inv_den;
+      const float c0 = (1.f - wy) * pk, c1 = wy * pk, omx = 1.f - wx;
+      const float w00 = c0 * omx, w01 = c0 * wx, w10 = c1 * omx, w11 = c1 * wx;
+      // one 32-bit texel index per corner (24 * S * S < 2^31, checked by the host), widened once by the load's address
+      const int r0 = y0 * S + (k - 1) * SS, r1 = y1 * S + (k - 1) * SS;
+      const float4 a = __ldg(atlas + (unsigned)(r0 + x0)), b = __ldg(atlas + (unsigned)(r0 + x1));
+      const float4 c = __ldg(atlas + (unsigned)(r1 + x0)), d = __ldg(atlas + (unsigned)(r1 + x1));
+      ax = fmaf(w11, d.x, fmaf(w10, c.x, fmaf(w01, b.x, fmaf(w00, a.x, ax))));
+      ay = fmaf(w11, d.y, fmaf(w10, c.y, fmaf(w01, b.y, fmaf(w00, a.y, ay))));
+      az = fmaf(w11, d.z, fmaf(w10, c.z, fmaf(w01, b.z, fmaf(w00, a.z, az))));
+      if (NCH > 3) aw = fmaf(w11, d.w, fmaf(w10, c.w, fmaf(w01, b.w, fmaf(w00, a.w, aw))));
+    }
+    float norm = 1.f;
+    if (!use_mask) norm = 1.f / (1.f - lg[0] * inv_den + 1e-6f);
+    float* o = tex_out + (size_t)n * (size_t)Ctex * (size_t)HW + pix;
+    o[0] = ax * norm;
+    if (Ctex > 1) o[(unsigned)HW] = ay * norm;
+    if (Ctex > 2) o[(unsigned)(2 * HW)] = az * norm;
+    if (NCH > 3 && Ctex > 3) o[(unsigned)(3 * HW)] = aw * norm;
+    if (IDX) {
+      const size_t idx = (size_t)n * (size_t)HW + pix;
+      if (part_out) part_out[idx] = (uint8_t)part;
+      if (texel_out) {
+        short2 texel = make_short2(0, 0);
+        if (part > 0) {
+          const float u = fma_sat_half(__ldg(base + (unsigned)((24 + part) * HW)));
+          const float v = fma_sat_half(__ldg(base + (unsigned)((48 + part) * HW)));
+          texel = make_short2((short)(int)floorf(__fmul_rn(u, sm1)), (short)(int)floorf(__fmul_rn(v, sm1)));
+        }
+        texel_out[idx] = texel;
+      }
+    }
+  }
+}
+
 // Measured alternatives (profiles/r02b_sampler.md): a "pair" atlas (texel + right neighbour in one 32-byte record, one LDG.E.256
 // per bilinear row) and a "quad" atlas with four lanes per (pixel, part) were built in round 2.  Neither beats this kernel: the
 // gathers are bound by distinct L1 line misses (2 per pixel and part either way) and by issue latency (IPC ~1 of 4), not by
@@ -162,6 +258,28 @@ extern "C" int nhvr_texture_sample(const float* uvp, const float* atlas, int32_t
   short2* tx = reinterpret_cast<short2*>(texel_out);
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = (int)std::min<int64_t>((total + 127) / 128, (int64_t)148 * 16 * 8);
+  // lean variant (see texture_sample_lean_kernel): Ctex <= 4 and 32-bit element indices; NHVR_SAMPLER_LEAN=0 selects the general kernel
+  static int lean = -1;
+  if (lean < 0) { const char* e = std::getenv("NHVR_SAMPLER_LEAN"); lean = e ? std::atoi(e) : 1; }
+  const int64_t HW64 = (int64_t)H * W;
+  if (lean && G == 1 && 73 * HW64 < (int64_t)1 << 31 && (int64_t)24 * S * S < (int64_t)1 << 31 && N <= 65535) {
+    const int HWi = (int)HW64;
+    const dim3 grid((unsigned)std::min<int64_t>((HW64 + 127) / 128, (int64_t)1 << 20), (unsigned)N);
+    const bool idx = part_out || texel_out;
+    static int lean_minb = -1;
+    if (lean_minb < 0) { const char* e = std::getenv("NHVR_SAMPLER_LEAN_MINB"); lean_minb = e ? std::atoi(e) : 8; }
+#define NHVR_LAUNCH_LEAN(NCH, IDX) \
+    do { if (lean_minb >= 8) texture_sample_lean_kernel<NCH, IDX, 8><<<grid, 128, 0, st>>>(uvp, a4, HWi, S, Ctex, use_mask_texture, tex_out, part_out, tx); \
+         else if (lean_minb >= 6) texture_sample_lean_kernel<NCH, IDX, 6><<<grid, 128, 0, st>>>(uvp, a4, HWi, S, Ctex, use_mask_texture, tex_out, part_out, tx); \
+         else texture_sample_lean_kernel<NCH, IDX, 5><<<grid, 128, 0, st>>>(uvp, a4, HWi, S, Ctex, use_mask_texture, tex_out, part_out, tx); } while (0)
+    if (Ctex <= 3) { if (idx) NHVR_LAUNCH_LEAN(3, true); else NHVR_LAUNCH_LEAN(3, false); }
+    else { if (idx) NHVR_LAUNCH_LEAN(4, true); else NHVR_LAUNCH_LEAN(4, false); }
+#undef NHVR_LAUNCH_LEAN
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { note_cuda_error(e); return NHVR_ERR_CUDA; }
+    return NHVR_OK;
+  }
 #define NHVR_LAUNCH_SAMPLER(GG) \
   texture_sample_kernel<GG, (GG == 1 ? 6 : 1)><<<blocks, 128, 0, st>>>(uvp, a4, N, H, W, S, Ctex, use_mask_texture, tex_out, part_out, tx)
   // Ctex <= 4: 8 resident blocks per SM asked for = 64 registers, 32 warps / SM.  Measured (tools/sampler_bench.py, us per launch at
