@@ -868,12 +868,29 @@ __global__ void __launch_bounds__(256, MINB) in_bwd_rows_kernel(const __grid_con
   const int64_t np = blockIdx.y;
   const int n = (int)(np / P.C8), p = (int)(np - (int64_t)n * P.C8);
   float scale[8], shift[8], m1[8], m2[8];
-  fwd_norm_params(P, np, scale, shift);
+  // (rstd, -mean * rstd) of the plane's 8 channels are formed in fp64 (norm_params8) by 8 lanes, one channel each, and broadcast through
+  // shared memory like in_apply_rows_kernel does (16 % fewer instructions).  Measured: no change in time (7.5 ms per end-to-end training
+  // step either way; two rows per warp in the apply pass: none either) - ncu (profiles/r02c_inbwd_metrics.csv) shows issue slots 58-74 % busy at
+  // 17-44 % of DRAM throughput with 27 warps resident, yet neither fewer instructions nor more loads in flight per lane (variants
+  // above) move it: the passes behave latency-bound on their few-KB-per-warp row segments
+  __shared__ float s_np[32];
+  if (threadIdx.x < 8) {
+    const double2* s2 = reinterpret_cast<const double2*>(P.stats + np * 32);
+    const double2 q = s2[2 * threadIdx.x], r = s2[2 * threadIdx.x + 1];
+    const double m0 = q.x * (double)P.inv_hw;
+    const double var = fmax(q.y * (double)P.inv_hw - m0 * m0, 0.0);
+    const float rstd = rsqrtf((float)var + P.eps);
+    s_np[threadIdx.x] = rstd;
+    s_np[8 + threadIdx.x] = -(float)(m0 + r.x) * rstd;
+  } else if (PASS == 1 && threadIdx.x >= 32 && threadIdx.x < 48) {
+    s_np[threadIdx.x - 16] = P.sums[np * 16 + (threadIdx.x - 32)] * P.inv_hw;      // [16 + 2e] = m1[e], [17 + 2e] = m2[e]
+  }
+  __syncthreads();
 #pragma unroll
-  for (int e = 0; e < 8; ++e) { m1[e] = 0.f; m2[e] = 0.f; }
+  for (int e = 0; e < 8; ++e) { scale[e] = s_np[e]; shift[e] = s_np[8 + e]; m1[e] = 0.f; m2[e] = 0.f; }
   if (PASS == 1) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { m1[e] = P.sums[np * 16 + 2 * e] * P.inv_hw; m2[e] = P.sums[np * 16 + 2 * e + 1] * P.inv_hw; }
+    for (int e = 0; e < 8; ++e) { m1[e] = s_np[16 + 2 * e]; m2[e] = s_np[17 + 2 * e]; }
   }
   float s1[8], s2[8];
 #pragma unroll
