@@ -1123,7 +1123,25 @@ extern "C" int nhvr_in_bwd(const void* dx, int32_t dx_H, int32_t dx_W, int32_t p
     // 8.14 / 1.98, 7.24 / 1.71, 7.77 / 1.72, 7.26 / 1.60 -> occupancy beats loads in flight per thread; default 3
     static int variant = -1;
     if (variant < 0) { const char* ev = std::getenv("NHVR_BWD_VARIANT"); variant = ev ? std::atoi(ev) : 3; }
-    const dim3 g0(std::max(1, (P.f.H + 31) / 32), planes), g1(std::max(1, (P.gg.Hp + 7) / 8), planes);
+    // reduce pass: every block does the same work and 4 blocks fit an SM, so the launch runs in rounds of 148 * 4 blocks.  Row blocks per
+    // plane are chosen to minimise rounds x rows per warp (128^2 x 192 planes: 4 row blocks = 768 blocks = 2 rounds of 4 rows; 16 row blocks
+    // = 3072 blocks = 6 rounds of 1 row); ties go to the finer split.  NHVR_BWD_GX0 forces a value.
+    int gx0 = std::max(1, (P.f.H + 31) / 32);
+    {
+      static int force = -1;
+      if (force < 0) { const char* e = std::getenv("NHVR_BWD_GX0"); force = e ? std::atoi(e) : 0; }
+      if (force > 0) gx0 = force;
+      else {
+        const int slots = 148 * 4, gmax = std::max(1, (P.f.H + 7) / 8);
+        long best = -1;
+        for (int gx = 1; gx <= gmax; ++gx) {
+          const long rounds = ((long)gx * planes + slots - 1) / slots, rows = (P.f.H + gx * 8 - 1) / (gx * 8);
+          const long cost = rounds * rows * 64 + rounds;          // + a little per round (block prologue, atomics)
+          if (best < 0 || cost <= best) { best = cost; gx0 = gx; }
+        }
+      }
+    }
+    const dim3 g0(gx0, planes), g1(std::max(1, (P.gg.Hp + 7) / 8), planes);
     if (variant == 1) { in_bwd_rows_kernel<0, 2, 3><<<g0, 256, 0, s>>>(P); NHVR_POST(); in_bwd_rows_kernel<1, 2, 3><<<g1, 256, 0, s>>>(P); }
     else if (variant == 2) { in_bwd_rows_kernel<0, 2, 4><<<g0, 256, 0, s>>>(P); NHVR_POST(); in_bwd_rows_kernel<1, 2, 4><<<g1, 256, 0, s>>>(P); }
     else if (variant == 3) { in_bwd_rows_kernel<0, 1, 4><<<g0, 256, 0, s>>>(P); NHVR_POST(); in_bwd_rows_kernel<1, 1, 4><<<g1, 256, 0, s>>>(P); }

@@ -341,7 +341,7 @@ namespace nhvr {
 template <int G, int MINB>
 __global__ void __launch_bounds__(128, MINB) texture_sample_bwd_kernel(const float* __restrict__ uvp, const float4* __restrict__ atlas,
                                                                  const float* __restrict__ gtex, int N, int H, int W, int S, int Ctex,
-                                                                 int use_mask, float* __restrict__ guvp, float* __restrict__ gatlas) {
+                                                                 int use_mask, float* __restrict__ guvp, float* __restrict__ gatlas, int agg) {
   const int64_t HW = (int64_t)H * W;
   const int64_t total = (int64_t)N * HW;
   const float sm1 = (float)(S - 1);
@@ -350,6 +350,7 @@ __global__ void __launch_bounds__(128, MINB) texture_sample_bwd_kernel(const flo
     const int64_t pix = idx - (int64_t)n * HW;
     const float* base = uvp + (int64_t)n * 73 * HW + pix;
     float* gb = guvp + (int64_t)n * 73 * HW + pix;
+    const bool full_warp = agg && __activemask() == 0xffffffffu;
     float g[4 * G];
 #pragma unroll
     for (int c = 0; c < 4 * G; ++c) g[c] = c < Ctex ? __ldg(gtex + ((int64_t)n * Ctex + c) * HW + pix) : 0.f;
@@ -383,6 +384,14 @@ __global__ void __launch_bounds__(128, MINB) texture_sample_bwd_kernel(const flo
       const int x1 = min(x0 + 1, S - 1), y1 = min(y0 + 1, S - 1);
       const float wx = fx - x0f, wy = fy - y0f;
       const float pk = lg[k] * inv_den;
+      // warp-uniform (U, V) of this part (see the atlas gradient below); only full warps take the aggregated path
+      bool wu = false;
+      if (full_warp) {
+        int pu, pv;
+        __match_all_sync(0xffffffffu, __float_as_uint(tu), &pu);
+        __match_all_sync(0xffffffffu, __float_as_uint(tv), &pv);
+        wu = pu && pv;
+      }
       const int64_t tb = (int64_t)(k - 1) * S * S;
       const int64_t i00 = (tb + (int64_t)y0 * S + x0) * G, i01 = (tb + (int64_t)y0 * S + x1) * G;
       const int64_t i10 = (tb + (int64_t)y1 * S + x0) * G, i11 = (tb + (int64_t)y1 * S + x1) * G;
@@ -399,7 +408,26 @@ __global__ void __launch_bounds__(128, MINB) texture_sample_bwd_kernel(const flo
           dfx += gc * ((1.f - wy) * (bv[e] - av[e]) + wy * (dv[e] - cv[e]));
           dfy += gc * ((1.f - wx) * (cv[e] - av[e]) + wx * (dv[e] - bv[e]));
         }
-        // atlas gradient (vector reduction per corner)
+        // atlas gradient (vector reduction per corner).  Stick-figure pose maps are flat over most of the image, so whole warps
+        // hit the SAME four texels of every part and 2 M same-address reductions per corner serialise in L2: when U and V of this
+        // part are bit-identical across a full warp (hence the corner indices and weights too), the warp first sums pk * g over
+        // its lanes and one lane issues the four reductions.
+        if (wu) {
+          float t0 = pk * g[q * 4], t1 = pk * g[q * 4 + 1], t2 = pk * g[q * 4 + 2], t3 = pk * g[q * 4 + 3];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            t0 += __shfl_xor_sync(0xffffffffu, t0, o); t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+            t2 += __shfl_xor_sync(0xffffffffu, t2, o); t3 += __shfl_xor_sync(0xffffffffu, t3, o);
+          }
+          if ((threadIdx.x & 31) == 0) {
+            float* gw = gatlas;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gw + (i00 + q) * 4), "f"(w00 * t0), "f"(w00 * t1), "f"(w00 * t2), "f"(w00 * t3) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gw + (i01 + q) * 4), "f"(w01 * t0), "f"(w01 * t1), "f"(w01 * t2), "f"(w01 * t3) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gw + (i10 + q) * 4), "f"(w10 * t0), "f"(w10 * t1), "f"(w10 * t2), "f"(w10 * t3) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gw + (i11 + q) * 4), "f"(w11 * t0), "f"(w11 * t1), "f"(w11 * t2), "f"(w11 * t3) : "memory");
+          }
+          continue;
+        }
         const float s00 = pk * w00, s01 = pk * w01, s10 = pk * w10, s11 = pk * w11;
         float* ga = gatlas;
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ga + (i00 + q) * 4), "f"(s00 * g[q * 4]), "f"(s00 * g[q * 4 + 1]),
@@ -469,15 +497,17 @@ extern "C" int nhvr_texture_sample_bwd(const float* uvp, const float* atlas, con
   const int blocks = (int)std::min<int64_t>((total + 127) / 128, (int64_t)148 * 16 * 8);
   const float4* a4 = reinterpret_cast<const float4*>(atlas);
   cudaStream_t st = (cudaStream_t)stream;
-#define NHVR_LAUNCH_SBWD(GG) texture_sample_bwd_kernel<GG, 1><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, use_mask_texture, grad_uvp, grad_atlas)
+#define NHVR_LAUNCH_SBWD(GG) texture_sample_bwd_kernel<GG, 1><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, use_mask_texture, grad_uvp, grad_atlas, agg)
+  static int agg = -1;            // warp-aggregated atlas reductions for warp-uniform (U, V); NHVR_SAMPLER_BWD_AGG=0 disables
+  if (agg < 0) { const char* e = std::getenv("NHVR_SAMPLER_BWD_AGG"); agg = e ? std::atoi(e) : 1; }
   static int minb = -1;           // NHVR_SAMPLER_BWD_MINB = 3 (165 registers) | 4 (128, default) | 6 (80) | 8 (64): measured 1.56 / 1.46 / 1.71 / 1.85 ms at 8 x 512^2
   if (minb < 0) { const char* e = std::getenv("NHVR_SAMPLER_BWD_MINB"); minb = e ? std::atoi(e) : 4; }
   switch (G) {
     case 1:
-      if (minb >= 8) texture_sample_bwd_kernel<1, 8><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, use_mask_texture, grad_uvp, grad_atlas);
-      else if (minb >= 6) texture_sample_bwd_kernel<1, 6><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, use_mask_texture, grad_uvp, grad_atlas);
-      else if (minb >= 4) texture_sample_bwd_kernel<1, 4><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, use_mask_texture, grad_uvp, grad_atlas);
-      else texture_sample_bwd_kernel<1, 3><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, use_mask_texture, grad_uvp, grad_atlas);
+      if (minb >= 8) texture_sample_bwd_kernel<1, 8><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, use_mask_texture, grad_uvp, grad_atlas, agg);
+      else if (minb >= 6) texture_sample_bwd_kernel<1, 6><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, use_mask_texture, grad_uvp, grad_atlas, agg);
+      else if (minb >= 4) texture_sample_bwd_kernel<1, 4><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, use_mask_texture, grad_uvp, grad_atlas, agg);
+      else texture_sample_bwd_kernel<1, 3><<<blocks, 128, 0, st>>>(uvp, a4, grad_tex, N, H, W, S, Ctex, use_mask_texture, grad_uvp, grad_atlas, agg);
       break;
     case 2: NHVR_LAUNCH_SBWD(2); break;
     case 3: NHVR_LAUNCH_SBWD(3); break;

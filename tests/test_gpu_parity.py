@@ -570,6 +570,30 @@ def test_sampler_and_composite_backward_exact(cuda_dev):
     assert (fgm.grad - f2.grad).abs().max().item() <= 1e-5 and (bg.grad - b2.grad).abs().max().item() <= 1e-5
 
 
+def test_sampler_backward_flat_uv_takes_the_aggregated_path(cuda_dev):
+    """Stick-figure pose maps give IUV that is constant over most of a frame: whole warps then add to the same four texels of
+    every part and nhvr_texture_sample_bwd sums a warp's contributions before ONE lane issues the reductions.  Flat, half-flat
+    (warps that mix uniform and varying lanes take the per-lane path) and ragged-tail shapes against autograd on the oracle."""
+    from nhvr_b200 import ops
+    from oracle.texture import texture_sample
+    torch.manual_seed(72)
+    for (N, H, W) in ((2, 16, 64), (1, 9, 50)):               # W = 50: warps straddle rows and the last warp is partial
+        base = torch.randn(1, 73, 1, 1, device=cuda_dev).expand(N, 73, H, W).clone()
+        base[:, :, H // 2:, : W // 2] = torch.randn(N, 73, H - H // 2, W // 2, device=cuda_dev)      # one varying quadrant
+        base[0, 25:, 0, :32] = 5.0                                                                     # a full warp at u = v = 1 (clamped)
+        uvp = base.clone().requires_grad_(True)
+        atlas = smooth_atlas(3, 16, cuda_dev, seed=5).requires_grad_(True)
+        u2, a2 = uvp.detach().clone().requires_grad_(True), atlas.detach().clone().requires_grad_(True)
+        w = torch.randn(N, 3, H, W, device=cuda_dev)
+        for use_mask in (True, False):
+            for t in (uvp, atlas, u2, a2):
+                t.grad = None
+            (ops.texture_sample_diff(uvp, atlas, use_mask) * w).sum().backward()
+            (texture_sample(u2, a2, use_mask)[0] * w).sum().backward()
+            assert (uvp.grad - u2.grad).abs().max().item() <= 1e-3 * u2.grad.abs().max().item(), (N, H, W, use_mask)
+            assert (atlas.grad - a2.grad).abs().max().item() <= 1e-3 * a2.grad.abs().max().item(), (N, H, W, use_mask)
+
+
 def test_discriminator_backward_parity(cuda_dev):
     """D and G objectives through the multiscale PatchGAN (LSGAN + feature matching): gradients w.r.t. the
     discriminator's parameters and w.r.t. its input image (what the generator receives) vs torch autograd."""

@@ -32,3 +32,22 @@ for name, uvp in cases.items():
         ms = e0.elapsed_time(e1) / 10
         res[label] = (tex.clone(), part.clone(), texel.clone())
         print("%-32s %-12s %8.1f us  %7.1f GB/s algorithmic  (MINB=%s)" % (name, label, ms * 1e3, algo / ms / 1e6, os.environ.get("NHVR_SAMPLER_MINB", "6")))
+
+# backward (nhvr_texture_sample_bwd through the C-ABI): NHVR_SAMPLER_BWD_AGG=0 disables the warp-aggregated atlas reductions
+from nhvr_b200.capi import load, check
+from nhvr_b200.ops import stream_ptr
+gtex = torch.randn(B, 3, SZ, SZ, device=dev)
+for name, uvp in cases.items():
+    guvp = torch.empty_like(uvp); gacl = torch.zeros_like(acl)
+    run = lambda: check(load().nhvr_texture_sample_bwd(uvp.data_ptr(), acl.data_ptr(), gtex.data_ptr(), B, SZ, SZ, 200, 3, 1,
+                                                       guvp.data_ptr(), gacl.data_ptr(), stream_ptr()), "nhvr_texture_sample_bwd")
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        run()
+    e1.record(); torch.cuda.synchronize()
+    print("%-32s backward     %8.1f us  (AGG=%s)  atlas grad checksum %.6e" % (name, e0.elapsed_time(e1) / 5 * 1e3, os.environ.get("NHVR_SAMPLER_BWD_AGG", "1"),
+                                                                              gacl.double().sum().item() / 7))
