@@ -639,9 +639,12 @@ def test_forward_without_backward_does_not_pin_engines(cuda_dev):
     assert len(pool) <= 2
 
 
-def test_full_training_step_runs_and_matches_oracle_losses(cuda_dev):
+@pytest.mark.parametrize("poses", ["smooth", "stick_figures"])
+def test_full_training_step_runs_and_matches_oracle_losses(cuda_dev, poses):
     """configs[2] in miniature: one RenderTrainer step (D step + G step) — its loss values against the oracle's
-    formulas on the same weights/batch, and a few steps of Adam change every parameter group."""
+    formulas on the same weights/batch, and a few steps of Adam change every parameter group.  `stick_figures`: the pose maps are
+    the reference's real input (BODY_25 stick figures rasterised from the bundled keypoints, ~98 % flat background): InstanceNorm of
+    nearly constant planes in the fp16 training engines, and the warp-aggregated atlas reductions of the lookup's backward."""
     from nhvr_b200.networks import define_D
     from nhvr_b200.train import RenderTrainer, synthetic_train_batch
     from oracle import losses as O
@@ -653,6 +656,12 @@ def test_full_training_step_runs_and_matches_oracle_losses(cuda_dev):
     netD = define_D(6, 16, 3, "instance", False, 2, True)
     netD.load_state_dict(refD.state_dict())
     batch = synthetic_train_batch(2, 64, cuda_dev, seed=5)
+    if poses == "stick_figures":
+        import numpy as np
+        from nhvr_b200 import pose as posemod
+        kps = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "keypoints_body25.npy"))
+        maps = torch.from_numpy(posemod.pose_maps(kps[[0, 1, 40, 41]], 64, 3)).to(cuda_dev)        # frames (t-1, t) of two samples
+        batch["pose_prev"], batch["pose"] = maps[[0, 2]].contiguous(), maps[[1, 3]].contiguous()
     # oracle losses at the initial weights
     with torch.no_grad():
         def frame(pose, prev):
@@ -676,6 +685,8 @@ def test_full_training_step_runs_and_matches_oracle_losses(cuda_dev):
     for _ in range(2):
         out = trainer.step(batch)
     assert torch.isfinite(out["loss_G"]) and torch.isfinite(out["loss_D"])
+    from nhvr_b200 import capi
+    capi.check_overflow()                 # no fp16 overflow of a conv output / gradient on the way
     changed = [k for k, v in list(pipe.named_parameters()) + list(netD.named_parameters())
                if not k.endswith(".bias") and (v.detach() - before[k]).abs().max().item() > 0]
     assert any(k.startswith("netTransG") for k in changed) and any(k.startswith("netG") for k in changed)
