@@ -20,6 +20,12 @@ else:
     netD = define_D(PIPE_KW["pose_nc"] + 3, 64, 3, "instance", False, 2, True)
     tr = RenderTrainer(pipe, netD)
     batch = synthetic_train_batch(8, 512, dev)
+    if "--stick" in sys.argv:      # the reference's real input: BODY_25 stick figures rasterised from the bundled keypoints (~98 % flat)
+        import numpy as np
+        from nhvr_b200 import pose as posemod
+        kps = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "keypoints_body25.npy"))
+        maps = torch.from_numpy(posemod.pose_maps(kps[:16], 512, 3)).to(dev)
+        batch["pose_prev"], batch["pose"] = maps[0::2].contiguous(), maps[1::2].contiguous()
     z = torch.zeros(8, PIPE_KW["pose_nc"] - 3, 512, 512, device=dev)            # the zero LaplaceProj channels of --use_laplace
     batch["pose"], batch["pose_prev"] = torch.cat([batch["pose"], z], 1), torch.cat([batch["pose_prev"], z], 1)
     step = lambda: tr.step(batch)
