@@ -402,13 +402,17 @@ extern "C" int nhvr_wgrad_plan_create(const nhvr_conv_desc* fwd, nhvr_wgrad_plan
   // Cost model per (chunk, all input channels): tensor time ~ ntaps * (CinP/nci) * 8 MMAs * cycles(nci), operand
   // staging ~ ngroups * (CinP/nci) * stage_bytes / ~24 B per cycle; a stage must fit at least twice.
   double best_cost = 1e30;
-  for (int cand : {64, 48, 32, 16}) {
+  int force_nci = 0;                      // experiments: NHVR_WGRAD_NCI=<input channels per CTA>
+  if (const char* e = std::getenv("NHVR_WGRAD_NCI")) force_nci = std::atoi(e);
+  for (int cand : {128, 96, 64, 48, 32, 16}) {
     if (W.CinP % cand) continue;
+    if (cand > 64 && force_nci != cand) continue;
+    if (force_nci && force_nci != cand && W.CinP % force_nci == 0 && force_nci <= W.CinP) continue;
     const int ngroups = (W.ntaps_total * cand + 511) / 512;
     const size_t stage = (size_t)16 * gslab * 16 + (size_t)(cand / 8) * W.xslab_units * 16;
     const int S = (int)std::min<size_t>(4, (size_t)(210 * 1024) / stage);
     if (S < 1) continue;
-    const double cyc = cand == 64 ? 48.0 : cand == 48 ? 44.0 : cand == 32 ? 40.0 : 39.0;
+    const double cyc = cand == 128 ? 66.0 : cand == 96 ? 56.0 : cand == 64 ? 48.0 : cand == 48 ? 44.0 : cand == 32 ? 40.0 : 39.0;
     const double blocks = (double)W.CinP / cand;
     const double t_mma = W.ntaps_total * blocks * 8.0 * cyc;
     const double t_ld = ngroups * blocks * (double)stage / 24.0;
