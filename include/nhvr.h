@@ -87,6 +87,8 @@ typedef struct nhvr_conv_desc {
                                    is written as a hilo activation too.  fp32-class results at 3x the tensor work: used by
                                    the UV generator, whose output error is multiplied by the texture gradient in the lookup
                                    (inference only: no dgrad / wgrad plans for it)
+                            bit 6: with bit 3: no w_lo blocks - two MMAs per K step (x_hi*w_hi + x_lo*w_hi): the activations keep
+                                   ~22 bits, the weights are rounded to 16 (the temporal generator of the "strict2" preset)
                             bit 2: the input may use the single-plane tap-paired format (Cin <= 8 stride-1 convs:
                                    K group 1 of every MMA is the same plane one pixel to the right, so an MMA covers
                                    two filter columns).  Changes nhvr_conv_input_desc (C8 = 1): set it only when

@@ -94,6 +94,7 @@ struct PackParams {
   int32_t kfold;               // tap pairing: K group kp of a block = filter column job_tap%kw + kp, channels 0..7
   int32_t khalf;               // split precision, single logical input plane: K group 1 = the lo plane (see the plan builder)
   int32_t split3;              // split precision: blocks (hi*w_hi, hi*w_lo, lo*w_hi) per group of four physical planes
+  int32_t nowlo;               // split precision without the w_lo blocks (conv desc flag bit 6): x_hi*w_hi + x_lo*w_hi only
   int32_t pair, bpb;           // CTA-pair layout: [stage of bpb blocks][rank][bpb][2][Npad/2][8]
   int16_t job_tap[kMaxJobs];   // r*kw + s of each job
 };

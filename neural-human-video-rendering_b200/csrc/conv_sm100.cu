@@ -877,7 +877,8 @@ NHVR_DEVINL void conv_pack_weights_body(const PackParams& P, int64_t u0, int64_t
   }
   // weight blocks per (chunk, tap): kcp/2 plane pairs; split precision: 2 per group of four physical planes - w_hi (feeds the
   // x_hi and the x_lo MMA) and w_lo (feeds x_hi)
-  const int qsteps = P.kfold ? 1 : (P.split3 ? 2 * (P.kcp >> 2) : P.kcp >> 1);
+  // split precision without w_lo (PackParams::nowlo): only the w_hi block of every group of four physical planes
+  const int qsteps = P.kfold ? 1 : (P.split3 ? (P.nowlo ? 1 : 2) * (P.kcp >> 2) : P.kcp >> 1);
   const int nblocks = P.nchunks * P.njobs * qsteps;
   for (int64_t u = u0; u < total; u += ustride) {
     const int nrow = (int)(u % P.Npad);
@@ -906,8 +907,8 @@ NHVR_DEVINL void conv_pack_weights_body(const PackParams& P, int64_t u0, int64_t
       // split precision: block qq = 2*g + t of a chunk covers logical planes 2*(c*kcp/4 + g) + kp; t == 1 carries w_lo
       // khalf (split precision, <= 8 input channels): K group 1 of every MMA is the LO plane of the same 8 channels, so block 0
       // carries w_hi in both K groups (x_hi*w_hi + x_lo*w_hi in ONE MMA) and block 1 carries w_lo in K group 0 only
-      const int lplane = P.khalf ? 0 : P.split3 ? 2 * (c * (P.kcp >> 2) + qq / 2) + kp : c * P.kcp + 2 * qq + kp;
-      const bool w_lo = P.split3 && (qq & 1);
+      const int lplane = P.khalf ? 0 : P.split3 ? 2 * (c * (P.kcp >> 2) + (P.nowlo ? qq : qq / 2)) + kp : c * P.kcp + 2 * qq + kp;
+      const bool w_lo = P.split3 && !P.nowlo && (qq & 1);
       if (P.khalf && w_lo && kp == 1) co = P.Cout;          // zero weights: the lo plane meets no w_lo
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -976,6 +977,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   int C8 = round_up((gemm_k + 7) / 8, 2);   // K = 16 per MMA -> an even number of planes
   // split precision (flag bit 3): hilo input, C8 counts PHYSICAL planes (groups of four), three MMAs per K step
   const bool split3 = (d->flags & 8) != 0;
+  const bool nowlo = split3 && (d->flags & 64) != 0;           // flag bit 6: two MMAs per K step (x_hi*w_hi + x_lo*w_hi), no w_lo blocks
   if (split3 && d->kind == NHVR_CONV_DGRAD_S1) { delete p; return NHVR_ERR_UNSUPPORTED; }
   if (split3) C8 *= 2;
   // Tap pairing (flag bit 2, <= 8 input channels, e.g. the 3-channel pose stem): ONE plane; K group 1 of every MMA is the
@@ -1194,7 +1196,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
       if (C8 % cand) continue;
       if (split3 && (cand & 3)) continue;                     // hi/lo groups of four physical planes stay in one chunk
       const int nch = C8 / cand;
-      const int bpc = kfold ? (int)taps.size() : split3 ? (int)taps.size() * 2 * (cand / 4) : (int)taps.size() * cand / 2;   // weight blocks per chunk
+      const int bpc = kfold ? (int)taps.size() : split3 ? (int)taps.size() * (nowlo ? 1 : 2) * (cand / 4) : (int)taps.size() * cand / 2;   // weight blocks per chunk
       if (bpc > kMaxMma) continue;
       // split precision doubles the slab bytes of a chunk (hi + lo planes) while tripling its MMAs: a single slab stage
       // (the co-resident CTA covers the refill) is allowed there when two stages do not leave room for the weight ring
@@ -1359,7 +1361,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   // split precision with a single logical input plane (<= 8 channels: the pose stem): the second K group of an MMA would be a zero
   // plane; address the LO plane there instead (A descriptor K-group stride = two slab planes) - two MMAs per tap instead of three
   const bool khalf = split3 && !kfold && !rowmode && gemm_k <= 8 && C8 == 4 && kcp == 4 && !std::getenv("NHVR_NO_KHALF");
-  const int ksteps = kfold ? 1 : split3 ? 2 * (kcp / 4) : kcp / 2;      // weight blocks per (chunk, tap)
+  const int ksteps = kfold ? 1 : split3 ? (nowlo ? 1 : 2) * (kcp / 4) : kcp / 2;      // weight blocks per (chunk, tap)
   K.mmas_per_chunk = K.njobs * ksteps;
   K.a_lbo_units = kfold ? 1 : khalf ? 2 * slab : slab;
   K.stages_per_chunk = K.mmas_per_chunk / bpb;           // bpb divides mmas_per_chunk by construction
@@ -1371,9 +1373,9 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
       ConvMma& m = K.mma[j * ksteps + q];
       // A planes of step q inside the chunk slab: plane pair q, or (split precision) the hi planes of group q / 2; the w_hi
       // block (q even) also feeds the lo planes (second MMA)
-      const int aplane = split3 ? 4 * (q / 2) : 2 * q;
+      const int aplane = split3 ? 4 * (nowlo ? q : q / 2) : 2 * q;
       m.a_off = jobs[j].a_off + aplane * slab;
-      m.a_off2 = (split3 && !khalf && (q & 1) == 0) ? jobs[j].a_off + (aplane + 2) * slab : -1;
+      m.a_off2 = (split3 && !khalf && (nowlo || (q & 1) == 0)) ? jobs[j].a_off + (aplane + 2) * slab : -1;
       m.meta = (uint32_t)(jobs[j].acc * Npad) | ((jobs[j].first && q == 0) ? 0x10000u : 0u);
     }
   K.w_split_units = (int64_t)nblocks_padded * 2 * Npad;
@@ -1397,6 +1399,7 @@ extern "C" int nhvr_conv_plan_create(const nhvr_conv_desc* d, nhvr_conv_plan** o
   PP.pair = pair; PP.bpb = bpb;
   PP.kfold = kfold ? 1 : 0;
   PP.split3 = split3 ? 1 : 0;
+  PP.nowlo = nowlo ? 1 : 0;
   PP.khalf = khalf ? 1 : 0;
   K.stat_centred = (d->flags & 16) ? 1 : 0;
   K.out_hilo = (split3 && (d->epilogue == NHVR_EPI_RAW_STATS || d->epilogue == NHVR_EPI_RAW_P8)) ? 1 : 0;

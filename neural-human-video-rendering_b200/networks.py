@@ -75,7 +75,7 @@ class _ChainEngine:
     """
 
     def __init__(self, chain: List[dict], N: int, H: int, W: int, device, final_act: int, out_channels: int, train: bool = False,
-                 split3: bool = False):
+                 split3: bool = False, no_wlo: bool = False):
         """split3: split-precision inference engine (include/nhvr.h conv flag bit 3): every activation is a hilo pair,
         every K step three MMAs - fp32-class results at 3x the tensor work (no backward)."""
         assert not (train and split3), "split precision is an inference format"
@@ -99,7 +99,7 @@ class _ChainEngine:
             else:
                 epi, act = capi.EPI_BIAS_ACT_P8, L["act"]        # conv + bias + activation, no norm (D layer 0)
             plan = ops.ConvPlan(capi.CONV_TRANSPOSE if p.transposed else capi.CONV, p.cin, p.cout, p.k, p.stride, p.pad,
-                                N, h, w, L["halo"], epi, act, allow_tap_pairing=not train, split3=split3,
+                                N, h, w, L["halo"], epi, act, allow_tap_pairing=not train, split3=split3, no_wlo=no_wlo,
                                 centred_stats=(i == 0 and self._centres_stem(chain)),
                                 align_tiles=want_fused and bool(L.get("res")) and bool(__import__("os").environ.get("NHVR_ALIGN_TILES")))
             plan.label = ("head" if last else "stem" if i == 0 else "res" if L.get("res") else "up" if p.transposed
@@ -486,12 +486,13 @@ class GlobalGeneratorB200(nn.Module):
         self.model = nn.Sequential(*model)
         self._engines: Dict[tuple, _ChainEngine] = {}
         # inference precision: "f16" = one 16-bit operand per value (the global operand type, see capi.DEFAULT_OPERAND);
-        # "split3" = split precision (hi + lo operands, 3 MMAs per K step, fp32-class results)
+        # "split3" = split precision (hi + lo operands, 3 MMAs per K step, fp32-class results);
+        # "split2" = hi + lo activations, 16-bit weights (2 MMAs per K step: x_hi*w + x_lo*w)
         self.precision = "f16"
 
     def set_precision(self, precision: str) -> "GlobalGeneratorB200":
-        if precision not in ("f16", "split3"):
-            raise NhvrError("precision must be 'f16' or 'split3', got %r" % (precision,))
+        if precision not in ("f16", "split3", "split2"):
+            raise NhvrError("precision must be 'f16', 'split3' or 'split2', got %r" % (precision,))
         self.precision = precision
         return self
 
@@ -537,7 +538,7 @@ class GlobalGeneratorB200(nn.Module):
             if dev.type != "cuda":
                 raise NhvrError("GlobalGeneratorB200 parameters must live on a CUDA device (call .cuda()); no CPU path")
             eng = _ChainEngine(self._chain(), N, H, W, dev, self._final_act(), self.output_nc, train=train,
-                               split3=self.precision == "split3")
+                               split3=self.precision in ("split3", "split2"), no_wlo=self.precision == "split2")
             self._engines[key] = eng
         eng.maybe_repack()
         return eng

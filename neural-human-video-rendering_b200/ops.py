@@ -112,13 +112,14 @@ class ConvPlan:
     """One conv layer lowered to the tcgen05 shift-GEMM kernel (nhvr_conv_plan_*)."""
 
     def __init__(self, kind, Cin, Cout, k, stride, pad, N, H, W, halo, epilogue, act=capi.ACT_NONE, in_extra_rows=0,
-                 in_extra_cols=0, out_hw=(0, 0), allow_tap_pairing: bool = False, split3: bool = False, centred_stats: bool = False,
+                 in_extra_cols=0, out_hw=(0, 0), allow_tap_pairing: bool = False, split3: bool = False, centred_stats: bool = False, no_wlo: bool = False,
                  align_tiles: bool = False):
         """allow_tap_pairing: flag bit 2 of nhvr_conv_desc - the input may use the single-plane tap-paired format
         (only when no wgrad plan reads the same input buffer, i.e. inference engines).
-        split3: flag bit 3 - split precision (hilo input / weights, three MMAs per K step, hilo RAW output)."""
+        split3: flag bit 3 - split precision (hilo input / weights, three MMAs per K step, hilo RAW output).
+        no_wlo: flag bit 6 (with split3) - no w_lo blocks: two MMAs per K step, weights rounded to 16 bits."""
         d = ConvDesc()
-        d.flags = (4 if allow_tap_pairing and not split3 else 0) | (8 if split3 else 0) | (16 if centred_stats else 0) | (32 if align_tiles else 0)
+        d.flags = (4 if allow_tap_pairing and not split3 else 0) | (8 if split3 else 0) | (16 if centred_stats else 0) | (32 if align_tiles else 0) | (64 if (no_wlo and split3) else 0)
         self.split3 = split3
         d.in_extra_rows, d.in_extra_cols = in_extra_rows, in_extra_cols
         d.out_h, d.out_w = out_hw

@@ -95,7 +95,7 @@ class BaseOptions:
         p.add_argument("--n_clusters", type=int, default=10)
         # B200 additions (not reference flags)
         p.add_argument("--clips_in_flight", type=int, default=1, help="independent clips advanced in lock-step per GPU")
-        p.add_argument("--precision", type=str, default="strict", choices=["strict", "balanced", "fast"],
+        p.add_argument("--precision", type=str, default="strict", choices=["strict", "strict2", "balanced", "fast"],
                        help="inference operand precision preset (pipeline.RenderPipeline)")
         self.initialized = True
 

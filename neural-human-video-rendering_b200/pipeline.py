@@ -30,7 +30,7 @@ from .networks import define_G
 
 N_PARTS = 24
 UV_CHANNELS = 25 + 2 * N_PARTS
-PRECISION_PRESETS = {"strict": ("split3", "split3"), "balanced": ("split3", "f16"), "fast": ("f16", "f16")}
+PRECISION_PRESETS = {"strict": ("split3", "split3"), "strict2": ("split3", "split2"), "balanced": ("split3", "f16"), "fast": ("f16", "f16")}
 
 
 @contextlib.contextmanager
@@ -57,10 +57,12 @@ class RenderPipeline(nn.Module):
         """precision: inference operand precision preset (measured parity per mode in profiles/):
           "strict"   UV generator, temporal generator and background net in split precision (3 x fp16 MMAs, fp32-class):
                      the mode that meets north_star's 2e-2 / 45 dB on the reference's real configuration - default;
+          "strict2"  UV generator in split precision; temporal generator and background net with split ACTIVATIONS and 16-bit weights
+                     (2 MMAs per product instead of 3; measured parity in profiles/r02c_strict2.md);
           "balanced" UV generator in split precision, the others fp16: PSNR ~67 dB, max-abs ~2e-2 at the few pixels where
                      InstanceNorm of a stick-figure pose map produces |z| ~ 25-50 (fp16 is relative precision);
           "fast"     everything fp16: PSNR >= 50 dB on a texture-like atlas, UV error ~3e-2 (1.5 texels).
-        uv_precision / g_precision ("f16" | "split3") override the preset per network."""
+        uv_precision / g_precision ("f16" | "split3" | "split2") override the preset per network."""
         super().__init__()
         if precision not in PRECISION_PRESETS:
             raise ValueError("precision must be one of %s" % sorted(PRECISION_PRESETS))

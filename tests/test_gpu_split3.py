@@ -53,11 +53,12 @@ def test_hilo_pack_unpack(cuda_dev, pad, split, halo):
     assert (err <= x.abs() * 2.0 ** -21 + 2.0 ** -24).all(), (err / x.abs().clamp(min=1e-6)).max().item()
 
 
-def _conv3_case(dev, kind, cin, cout, k, stride, pad, N, H, W, halo, epi, act=0):
-    """One split-precision conv through the C-ABI against torch in fp64 on the SAME fp32 operands."""
+def _conv3_case(dev, kind, cin, cout, k, stride, pad, N, H, W, halo, epi, act=0, no_wlo=False):
+    """One split-precision conv through the C-ABI against torch in fp64 on the SAME fp32 operands
+    (no_wlo: conv flag bit 6 - the reference then takes the weights rounded to 16 bits, which is all that variant drops)."""
     import torch.nn.functional as F
     from nhvr_b200 import ops, capi
-    plan = ops.ConvPlan(kind, cin, cout, k, stride, pad, N, H, W, halo, epi, act, split3=True)
+    plan = ops.ConvPlan(kind, cin, cout, k, stride, pad, N, H, W, halo, epi, act, split3=True, no_wlo=no_wlo)
     assert plan.in_desc.hilo == 1
     g = torch.Generator(device="cpu").manual_seed(cin * 1000 + cout + k)
     x = (torch.rand(N, cin, H, W, generator=g) * 2 - 1).to(dev)
@@ -67,7 +68,7 @@ def _conv3_case(dev, kind, cin, cout, k, stride, pad, N, H, W, halo, epi, act=0)
     xin = ops.P8Buffer(plan.in_desc.copy(), dev)
     ops.pack_nchw([x], xin)
     plan.pack_weights(w)
-    xd, wd = x.double(), w.double()
+    xd, wd = x.double(), (w.half() if no_wlo else w).double()
     if transposed:
         ref = F.conv_transpose2d(xd, wd, stride=2, padding=pad, output_padding=1 if k == 3 else 0)
     else:
@@ -114,6 +115,25 @@ def test_conv_split3(cuda_dev, name, kind, cin, cout, k, stride, pad, N, H, W, h
     assert info["kcp"] % 4 == 0, info
     assert err <= 2e-5, (name, err, info)
     assert stat_err <= 5e-4, (name, stat_err)       # fp32 atomics over H*W values
+
+
+@pytest.mark.parametrize("name,kind,cin,cout,k,stride,pad,N,H,W,halo,epi", [
+    ("res_192", "CONV", 192, 192, 3, 1, 1, 1, 40, 44, "R", "RAW_STATS"),
+    ("down_s2", "CONV", 48, 96, 3, 2, 1, 2, 130, 128, "Z", "RAW_STATS"),
+    ("up_convT", "CONV_TRANSPOSE", 192, 96, 3, 2, 1, 1, 24, 40, "Z", "RAW_STATS"),
+    ("stem_12ch", "CONV", 12, 48, 7, 1, 3, 2, 224, 128, "R", "RAW_STATS"),
+    ("stem_6ch_khalf", "CONV", 6, 64, 7, 1, 3, 1, 96, 128, "R", "RAW_STATS"),
+    ("head_rgb_rowmode", "CONV", 48, 4, 7, 1, 3, 2, 130, 300, "R", "BIAS_ACT_F32"),
+    ("bg_head", "CONV", 48, 3, 7, 1, 3, 1, 64, 64, "R", "BIAS_ACT_F32"),
+])
+def test_conv_split2(cuda_dev, name, kind, cin, cout, k, stride, pad, N, H, W, halo, epi):
+    """Conv flag bit 6: hi/lo activations, weights rounded to 16 bits, 2 MMAs per K step (the temporal generator of the
+    "strict2" preset).  Against fp64 on the fp32 activations and the 16-bit-rounded weights: the same 2e-5 as the 3-MMA form."""
+    from nhvr_b200 import capi
+    err, stat_err, info = _conv3_case(cuda_dev, getattr(capi, kind), cin, cout, k, stride, pad, N, H, W,
+                                      capi.HALO_REFLECT if halo == "R" else capi.HALO_ZERO, getattr(capi, "EPI_" + epi), no_wlo=True)
+    assert err <= 2e-5, (name, err, info)
+    assert stat_err <= 5e-4, (name, stat_err)
 
 
 def test_in_apply_hilo(cuda_dev):
@@ -206,7 +226,7 @@ def _oracle_frames(ref, poses):
     return outs
 
 
-@pytest.mark.parametrize("precision,atlas_kind", [("strict", "smooth"), ("strict", "uniform"), ("balanced", "smooth")])
+@pytest.mark.parametrize("precision,atlas_kind", [("strict", "smooth"), ("strict", "uniform"), ("strict2", "smooth"), ("balanced", "smooth")])
 def test_frame_parity_start_sh_configuration(cuda_dev, precision, atlas_kind):
     """The frame function of `bash test_start/start.sh`'s configuration on the 8 first bundled keypoint frames: for every
     frame t the path renders (pose_t, previous frame of the ORACLE) - "the same inputs and weights" of north_star - with its
@@ -216,6 +236,8 @@ def test_frame_parity_start_sh_configuration(cuda_dev, precision, atlas_kind):
     strict / U(-1,1) white-noise atlas (the bench's): a UV error e moves the lookup by 100 e texels of independent noise, so
       the fp32 oracle's OWN rounding noise (against an fp64 evaluation of the same model, computed here) already costs
       4e-3 .. 7e-3 of the 2e-2; held to PSNR >= 45 dB, max-abs <= 6e-2 and <= 12 x that reference noise floor.
+    strict2 (temporal generator with hi + lo activations but 16-bit weights, 2 MMAs per product) / texture-like atlas: the same
+      north_star bar, 2e-2 / 45 dB, with a smaller margin (measured 5.5e-3 .. 7.9e-3, 74-75 dB) - additionally held to 1.2e-2.
     balanced (temporal generator in plain fp16) / texture-like atlas: PSNR >= 60 dB; max-abs <= 4e-2 (fp16 is a RELATIVE
       precision, and InstanceNorm of a 98 %-flat stick-figure map puts |z| ~ 25-50 on the limb pixels: the few pixels next
       to them sit at 1e-2 .. 2.5e-2, run-to-run)."""
@@ -250,7 +272,7 @@ def test_frame_parity_start_sh_configuration(cuda_dev, precision, atlas_kind):
             if precision == "balanced":
                 assert e <= 4e-2 and db >= 60.0, (t, e, db)
             elif atlas_kind == "smooth":
-                assert e <= 2e-2 and db >= 45.0, (t, e, db)
+                assert e <= (1.2e-2 if precision == "strict2" else 2e-2) and db >= 45.0, (t, e, db)
             else:
                 assert db >= 45.0 and e <= 6e-2 and e <= 12.0 * floor[t], (t, e, db, floor[t])
     from nhvr_b200 import capi

@@ -73,10 +73,15 @@ def main():
             print("[%s] oracle fp32 vs fp64 free-running: " % atlas_kind + " ".join("%.2e" % v for v in d64))
             print("[%s] oracle fp32 vs fp64 same-input  : " % atlas_kind + " ".join("%.2e" % v for v in d64_same))
             del ref64
-        for mode, prec in (("uv=split3,g=f16", dict(uv_precision="split3", g_precision="f16")),
+        modes_all = (("uv=split3,g=f16", dict(uv_precision="split3", g_precision="f16")),
+                           ("uv=split3,g=split2", dict(uv_precision="split3", g_precision="split2")),
                            ("uv=split3,g=split3", dict(uv_precision="split3", g_precision="split3")),
                            ("uv=split3,g=f16,pose+1", dict(uv_precision="split3", g_precision="f16")),
-                           ("uv=f16,g=f16", dict(uv_precision="f16", g_precision="f16"))):
+                           ("uv=f16,g=f16", dict(uv_precision="f16", g_precision="f16")))
+        only = os.environ.get("NHVR_PROBE_MODES")          # comma-free filter, e.g. NHVR_PROBE_MODES=split2
+        for mode, prec in modes_all:
+            if only and only not in mode:
+                continue
             pipe = RenderPipeline(**KW, **prec).to(dev)
             pipe.load_state_dict(ref.state_dict())
             with torch.no_grad():
