@@ -85,6 +85,27 @@ def test_conv_plans_of_the_reference_networks():
     assert pl.flops == pytest.approx(10.87e9, rel=1e-3)
 
 
+def test_split_precision_plans_block_counts():
+    """Split precision (conv flag bit 3) carries two weight blocks per group of four physical planes and tap (w_hi, w_lo), flag bit 6
+    ("split2": no w_lo) one: the MMA table, the packed weight bytes and the presets that use them (host logic only)."""
+    from nhvr_b200 import capi, ops
+    from nhvr_b200.pipeline import PRECISION_PRESETS
+    R = capi.HALO_REFLECT
+    for (cin, cout, k, H) in ((192, 192, 3, 128), (256, 256, 3, 128), (48, 4, 7, 512), (64, 73, 7, 512)):
+        p3 = ops.ConvPlan(capi.CONV, cin, cout, k, 1, k // 2, 1, H, H, R, capi.EPI_RAW_STATS if cout > 8 and cout != 73 else capi.EPI_BIAS_ACT_F32,
+                          capi.ACT_NONE, split3=True)
+        p2 = ops.ConvPlan(capi.CONV, cin, cout, k, 1, k // 2, 1, H, H, R, capi.EPI_RAW_STATS if cout > 8 and cout != 73 else capi.EPI_BIAS_ACT_F32,
+                          capi.ACT_NONE, split3=True, no_wlo=True)
+        i3, i2 = p3.info(), p2.info()
+        assert p3.in_desc.hilo == 1 and p2.in_desc.hilo == 1
+        assert i3["kcp"] % 4 == 0 and i2["kcp"] % 4 == 0
+        assert i3["nblocks"] == i3["nchunks"] * i3["njobs"] * 2 * (i3["kcp"] // 4)
+        assert i2["nblocks"] == i2["nchunks"] * i2["njobs"] * (i2["kcp"] // 4)
+        assert i2["nchunks"] * i2["kcp"] == i3["nchunks"] * i3["kcp"]                   # the same physical planes
+        assert p2.weight_bytes < p3.weight_bytes and p2.flops == p3.flops
+    assert PRECISION_PRESETS["strict"] == ("split3", "split3") and PRECISION_PRESETS["strict2"] == ("split3", "split2")
+
+
 def test_conv_plan_rejects_bad_shapes():
     from nhvr_b200 import capi
     with pytest.raises(capi.NhvrError):
