@@ -106,6 +106,19 @@ def test_split_precision_plans_block_counts():
     assert PRECISION_PRESETS["strict"] == ("split3", "split3") and PRECISION_PRESETS["strict2"] == ("split3", "split2")
 
 
+def test_precision_presets_are_offered_consistently():
+    """The preset names of RenderPipeline are the choices of test.py's --precision and of bench.py, and every non-default one has a
+    parity note for the bench's `modes` block."""
+    import bench
+    from nhvr_b200.options import TestOptions
+    from nhvr_b200.pipeline import PRECISION_PRESETS
+    to = TestOptions()
+    to.initialize()
+    act = next(a for a in to.parser._actions if "--precision" in a.option_strings)
+    assert sorted(act.choices) == sorted(PRECISION_PRESETS) and act.default == "strict"
+    assert sorted(bench.PARITY_NOTE) == sorted(PRECISION_PRESETS)
+
+
 def test_conv_plan_rejects_bad_shapes():
     from nhvr_b200 import capi
     with pytest.raises(capi.NhvrError):
